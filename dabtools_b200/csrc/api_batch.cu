@@ -1,0 +1,159 @@
+// api_batch.cu -- stateless batched entry points of include/dabgpu.h.
+#include "../../include/dabgpu.h"
+#include "vitbatch.cuh"
+
+using namespace dabgpu;
+
+namespace {
+
+// per-thread workspace of the stateless batched calls
+struct Workspace {
+  DevBuf in, steps, out, aux, shape;
+  VitBatch vb;
+  uint64_t last_steps = 0;
+};
+thread_local Workspace t_ws;
+
+}  // namespace
+
+namespace dabgpu {
+Workspace &thread_workspace() { return t_ws; }
+}  // namespace dabgpu
+
+DABGPU_EXPORT uint64_t dabgpu_last_trellis_steps(void) { return t_ws.last_steps; }
+
+// ---- tables -----------------------------------------------------------------------------------
+DABGPU_EXPORT int dabgpu_tab_shape(int kind, int a, int b, int32_t *out23) {
+  dabgpu_cw_shape sh;
+  int rc = 0;
+  if (kind == 0)
+    dabgpu_shape_fic(&sh);
+  else if (kind == 1)
+    rc = dabgpu_shape_uep(&sh, a);
+  else if (kind == 2)
+    rc = dabgpu_shape_eep(&sh, a, b);
+  else
+    rc = -1;
+  if (rc) {
+    set_error(DABGPU_ERR_ARG, "dabgpu_tab_shape: no such profile (kind=%d a=%d b=%d)", kind, a, b);
+    return DABGPU_ERR_ARG;
+  }
+  static_assert(sizeof(sh) == 23 * sizeof(int32_t), "shape layout");
+  memcpy(out23, &sh, sizeof sh);
+  return DABGPU_OK;
+}
+DABGPU_EXPORT void dabgpu_tab_uep(int32_t *o) {
+  for (int i = 0; i < 64; i++) {
+    const dabgpu_uep_profile &p = DABGPU_UEP[i];
+    int32_t *r = o + 12 * i;
+    r[0] = p.bitrate;
+    r[1] = p.size_cu;
+    r[2] = p.prot_level;
+    for (int k = 0; k < 4; k++) {
+      r[3 + k] = p.L[k];
+      r[7 + k] = p.PI[k];
+    }
+    r[11] = p.pad_bits;
+  }
+}
+DABGPU_EXPORT uint32_t dabgpu_tab_puncture_mask(int pi) { return dabgpu_puncture_mask(pi); }
+DABGPU_EXPORT void dabgpu_tab_freq_deint(uint16_t *rev) { dabgpu_build_freq_deint(rev); }
+DABGPU_EXPORT void dabgpu_tab_prs(uint8_t *q) { dabgpu_build_prs(q); }
+DABGPU_EXPORT void dabgpu_tab_prbs(uint8_t *out, int nbytes) { dabgpu_build_prbs(out, nbytes); }
+
+// ---- viterbi batch -------------------------------------------------------------------------------
+DABGPU_EXPORT int dabgpu_viterbi_batch(const uint8_t *soft, size_t soft_pitch, int n, int nbits,
+                                       uint8_t *out, size_t out_pitch, int descramble, int on_device) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  if (n < 0 || nbits <= 0 || !soft || !out) {
+    set_error(DABGPU_ERR_ARG, "dabgpu_viterbi_batch: bad argument");
+    return DABGPU_ERR_ARG;
+  }
+  const uint32_t nsteps = (uint32_t)nbits + 6;
+  const size_t out_row = 4 * (((size_t)nbits + 31) / 32);
+  if (soft_pitch < 4ull * nsteps || (descramble && nbits > 9216) ||
+      (on_device && (out_pitch < out_row || (out_pitch & 3)))) {
+    set_error(DABGPU_ERR_ARG, "dabgpu_viterbi_batch: pitch/size constraint violated");
+    return DABGPU_ERR_ARG;
+  }
+  if (n == 0) return DABGPU_OK;
+  cudaStream_t st = current_stream();
+  Workspace &ws = t_ws;
+  const uint32_t row = vit_row_bytes(nsteps);
+  if ((rc = ws.steps.reserve((size_t)n * row))) return rc;
+  const uint8_t *d_soft = soft;
+  uint8_t *d_out = out;
+  size_t d_out_pitch = out_pitch;
+  if (!on_device) {
+    if ((rc = ws.in.reserve((size_t)n * soft_pitch))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ws.in.p, soft, (size_t)n * soft_pitch, cudaMemcpyHostToDevice, st));
+    d_soft = ws.in.as<uint8_t>();
+    d_out_pitch = out_row;
+    if ((rc = ws.out.reserve((size_t)n * d_out_pitch))) return rc;
+    d_out = ws.out.as<uint8_t>();
+  }
+  if ((rc = launch_prep_soft(d_soft, soft_pitch, ws.steps.as<uint8_t>(), row, n, nsteps, st))) return rc;
+  ws.vb.clear();
+  for (int i = 0; i < n; i++)
+    ws.vb.add((uint64_t)i * row, (uint64_t)i * d_out_pitch, (uint32_t)nbits, descramble ? VIT_DESCRAMBLE : 0);
+  if ((rc = ws.vb.run(ws.steps.as<uint8_t>(), d_out, st))) return rc;
+  ws.last_steps = ws.vb.total_steps;
+  if (!on_device) {
+    const size_t nbytes = ((size_t)nbits + 7) / 8;
+    CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch ? out_pitch : nbytes, d_out, d_out_pitch, nbytes, n,
+                               cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return DABGPU_OK;
+}
+
+// ---- FIC decode batch ------------------------------------------------------------------------------
+DABGPU_EXPORT int dabgpu_fic_decode_batch(const uint8_t *fic_bits, int n_groups, uint8_t *fibs,
+                                          uint8_t *crc_ok, int on_device) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  if (n_groups < 0 || !fic_bits || !fibs || !crc_ok) {
+    set_error(DABGPU_ERR_ARG, "dabgpu_fic_decode_batch: bad argument");
+    return DABGPU_ERR_ARG;
+  }
+  if (n_groups == 0) return DABGPU_OK;
+  cudaStream_t st = current_stream();
+  Workspace &ws = t_ws;
+  const uint32_t nsteps = 774, row = vit_row_bytes(nsteps);
+  if ((rc = ws.steps.reserve((size_t)n_groups * row))) return rc;
+  if (!ws.shape.p) {
+    dabgpu_cw_shape sh;
+    ShapeDev sd;
+    dabgpu_shape_fic(&sh);
+    shape_to_dev(sh, &sd);
+    if ((rc = ws.shape.reserve(sizeof sd))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ws.shape.p, &sd, sizeof sd, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // sd lives on this stack frame
+  }
+  const uint8_t *d_bits = fic_bits;
+  uint8_t *d_fibs = fibs, *d_ok = crc_ok;
+  if (!on_device) {
+    if ((rc = ws.in.reserve((size_t)n_groups * 2304))) return rc;
+    if ((rc = ws.out.reserve((size_t)n_groups * 96))) return rc;
+    if ((rc = ws.aux.reserve((size_t)n_groups * 3))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ws.in.p, fic_bits, (size_t)n_groups * 2304, cudaMemcpyHostToDevice, st));
+    d_bits = ws.in.as<uint8_t>();
+    d_fibs = ws.out.as<uint8_t>();
+    d_ok = ws.aux.as<uint8_t>();
+  }
+  if ((rc = launch_prep_hard(d_bits, 2304, ws.steps.as<uint8_t>(), row, n_groups, ws.shape.as<ShapeDev>(),
+                             nsteps, st)))
+    return rc;
+  ws.vb.clear();
+  for (int i = 0; i < n_groups; i++) ws.vb.add((uint64_t)i * row, (uint64_t)i * 96, 768, VIT_DESCRAMBLE);
+  if ((rc = ws.vb.run(ws.steps.as<uint8_t>(), d_fibs, st))) return rc;
+  ws.last_steps = ws.vb.total_steps;
+  if ((rc = launch_fib_crc(d_fibs, d_ok, 3 * n_groups, st))) return rc;
+  if (!on_device) {
+    CUDA_TRY(cudaMemcpyAsync(fibs, d_fibs, (size_t)n_groups * 96, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaMemcpyAsync(crc_ok, d_ok, (size_t)n_groups * 3, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return DABGPU_OK;
+}

@@ -1,0 +1,63 @@
+// viterbi.cuh -- batched K=7 rate-1/4 Viterbi decoder for DAB (sm_100a).
+//
+// Replaces the reference's viterbi() (src/viterbi.c:352-452) plus the energy-dispersal
+// descrambler that always follows it (src/misc.c:41-58), bit-exactly, for the symbol
+// alphabet the reference's depuncturers emit ({127,128,129} = 0 / erasure / 1).
+//
+// Input format ("step bytes"): one byte per trellis step,
+//     bits 0..3 = received hard bit for generator j (0 if punctured)
+//     bits 4..7 = 1 where generator j's symbol was transmitted (0 = erasure)
+// one row of step bytes per codeword, rows 16-byte aligned and padded to 16 bytes.
+#pragma once
+#include "common.cuh"
+
+namespace dabgpu {
+
+struct VitJob {
+  uint64_t in_off;   // byte offset of this codeword's step-byte row
+  uint64_t out_off;  // byte offset of the decoded bytes (4-byte aligned)
+  uint32_t nbits;    // information bits (trellis steps = nbits + 6)
+  uint32_t flags;    // VIT_DESCRAMBLE
+};
+enum : uint32_t { VIT_DESCRAMBLE = 1u };
+
+// One warp decodes up to 32 codewords of identical length, one per lane.
+struct VitGroup {
+  uint32_t job0;     // index of lane 0's job; lanes use job0 + lane
+  uint32_t nlanes;   // active lanes (<= 32)
+  uint32_t nsteps;   // nbits + 6, identical for all lanes of the group
+  uint32_t pad;
+  uint64_t dec_off;  // offset into the decision scratch, in uint2 units
+};
+
+// decision scratch needed by a group: nsteps * 32 uint2
+__host__ __device__ static inline uint64_t vit_group_dec_words(uint32_t nsteps) { return (uint64_t)nsteps * 32u; }
+__host__ __device__ static inline uint32_t vit_row_bytes(uint32_t nsteps) { return (nsteps + 15u) & ~15u; }
+
+int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
+                   const VitGroup *d_groups, int ngroups, cudaStream_t st);
+
+// step-byte producers -------------------------------------------------------------------
+// (a) from the reference's soft-symbol bytes (4 per step; <128 -> 0, 128 -> erasure, >128 -> 1)
+int launch_prep_soft(const uint8_t *d_soft, uint64_t soft_stride, uint8_t *d_steps, uint64_t row_stride,
+                     int n_cw, uint32_t nsteps, cudaStream_t st);
+// (b) from contiguous punctured hard bits (1 byte per bit) and a puncturing layout
+struct ShapeDev {  // device copy of dabgpu_cw_shape with expanded masks
+  int32_t nbits, in_bits, n_regions, pad;
+  struct {
+    int32_t steps, step0, in0, ones;  // ones = kept bits per 32-bit period
+    uint32_t mask;
+    int32_t pad[3];
+  } r[5];
+};
+void shape_to_dev(const dabgpu_cw_shape &s, ShapeDev *o);
+int launch_prep_hard(const uint8_t *d_bits, uint64_t bits_stride, uint8_t *d_steps, uint64_t row_stride,
+                     int n_cw, const ShapeDev *d_shape, uint32_t nsteps, cudaStream_t st);
+
+// FIB CRC check (src/misc.c:145-150) over n FIBs of 32 bytes -> 1/0 per FIB
+int launch_fib_crc(const uint8_t *d_fibs, uint8_t *d_ok, int n_fibs, cudaStream_t st);
+
+// in-place XOR with the energy-dispersal PRBS (standalone form of misc.c:41-58)
+int launch_descramble(uint8_t *d_buf, uint64_t stride, int n_rows, int nbytes, cudaStream_t st);
+
+}  // namespace dabgpu

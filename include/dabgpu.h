@@ -1,0 +1,79 @@
+/* dabgpu.h -- C ABI of libdabgpu: the dabtools receive hot path on NVIDIA B200 (sm_100a).
+ *
+ * Two layers:
+ *
+ *  1. include/dabgpu_ref_abi.h -- the reference's own function signatures and struct
+ *     layouts for this path (sdr_demod, *_depuncture, viterbi, fic_decode, create_eti,
+ *     dab_process_frame, ...), so that an unmodified dab2eti.o links against libdabgpu
+ *     instead of the reference's objects.  Those are batch-of-one calls.
+ *
+ *  2. this header -- the additive batched API the throughput path uses: many independent
+ *     codewords / CIFs / ensemble streams per call, device-resident or host buffers.
+ *
+ * Conventions: every function returns 0 on success or a negative DABGPU_ERR_* code and
+ * records a message retrievable with dabgpu_last_error_string() (per thread).  There is
+ * no CPU fallback: without a usable sm_100 device every compute entry point fails with
+ * DABGPU_ERR_NO_DEVICE.  Pointers are plain host pointers unless `on_device` is non-zero,
+ * in which case they are device pointers valid on the current device.  Work is enqueued
+ * on the stream set with dabgpu_set_stream() (default: the legacy default stream); calls
+ * taking host pointers synchronise that stream before returning.
+ */
+#ifndef DABGPU_H
+#define DABGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DABGPU_OK 0
+#define DABGPU_ERR_CUDA (-1)
+#define DABGPU_ERR_ARG (-2)
+#define DABGPU_ERR_NO_DEVICE (-3)
+#define DABGPU_ERR_STATE (-4)
+
+/* ---- status / device ------------------------------------------------------------------ */
+int dabgpu_last_error(void);
+const char *dabgpu_last_error_string(void);
+void dabgpu_clear_error(void);
+int dabgpu_device_count(void);
+int dabgpu_set_device(int dev);
+void dabgpu_set_stream(void *cuda_stream);
+int dabgpu_synchronize(void);
+
+/* ---- constant tables (host only, no GPU needed; include/dabgpu_tables.h) ---------------- */
+/* kind: 0 = FIC, 1 = UEP (a = table index 0..63), 2 = EEP (a = level 0..7, b = size in CU).
+ * out receives the dabgpu_cw_shape as 23 int32 (nbits, in_bits, n_regions, then 5 x
+ * {steps, pi, step0, in0}).  Replaces ueptable/eeptable/pvec (dab_tables.c:16-127). */
+int dabgpu_tab_shape(int kind, int a, int b, int32_t *out23);
+/* 64 rows x {bitrate, size_cu, prot_level, L1..L4, PI1..PI4, pad_bits} */
+void dabgpu_tab_uep(int32_t *out64x12);
+uint32_t dabgpu_tab_puncture_mask(int pi);
+void dabgpu_tab_freq_deint(uint16_t *rev1536);   /* rev_freq_deint_tab, dab_tables.c:164-357 */
+void dabgpu_tab_prs(uint8_t *quarter_turns1536); /* prs_static, sdr_prstab.c */
+void dabgpu_tab_prbs(uint8_t *out, int nbytes);  /* energy-dispersal sequence, misc.c:41-58 */
+
+/* ---- batched channel decoding ------------------------------------------------------------ */
+/* n codewords of `nbits` information bits each.  soft: n rows of 4*(nbits+6) reference
+ * soft symbols (127 = 0, 128 = erasure, 129 = 1; anything <128 / >128 is sliced), row pitch
+ * soft_pitch bytes.  out: n rows of ceil(nbits/8) bytes, pitch out_pitch (multiple of 4,
+ * >= 4*ceil(nbits/32)).  descramble != 0 additionally XORs the energy-dispersal PRBS
+ * (needs nbits <= 9216).  Batched form of viterbi(), viterbi.c:352-452. */
+int dabgpu_viterbi_batch(const uint8_t *soft, size_t soft_pitch, int n, int nbits, uint8_t *out,
+                         size_t out_pitch, int descramble, int on_device);
+
+/* n_groups FIC groups of 2304 hard bits (one byte per bit, values 0/1; 4 groups = the 3
+ * FIC symbols of one transmission frame) -> 96 descrambled bytes (3 FIBs) + 3 CRC flags
+ * each.  Batched form of the loop body of fic_decode(), fic.c:185-206. */
+int dabgpu_fic_decode_batch(const uint8_t *fic_bits, int n_groups, uint8_t *fibs, uint8_t *crc_ok,
+                            int on_device);
+
+/* Work accounting of the last dabgpu_*_batch call on this thread: trellis steps decoded. */
+uint64_t dabgpu_last_trellis_steps(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DABGPU_H */

@@ -1,0 +1,123 @@
+"""Pin the CPU restatement (oracle/dab_oracle.c) against the reference itself, compiled unmodified
+into oracle/_ref.  The reference ships no tests or golden vectors, so this is the pinning of record;
+it runs wherever oracle/_ref exists (the build container; the prebuilt .so also travels)."""
+import numpy as np
+import pytest
+
+from dabtools_b200 import synth
+from dabtools_b200 import tables as T
+
+
+def _noisy_soft(rng, sym, p_flip, p_erase):
+    s = sym ^ (rng.random(sym.size) < p_flip).astype(np.uint8)
+    soft = (127 + 2 * s).astype(np.uint8)
+    soft[rng.random(sym.size) < p_erase] = 128
+    return soft
+
+
+@pytest.mark.parametrize("nbits", [8, 192, 768, 1536, 3072, 9216])
+def test_viterbi_and_encoder(ref, port, nbits):
+    rng = np.random.default_rng(nbits)
+    for p_flip, p_erase in [(0, 0), (0.02, 0.25), (0.05, 0.4), (0.10, 0.5), (0.5, 0.0)]:
+        data = rng.integers(0, 256, nbits // 8, dtype=np.uint8)
+        sym = port.encode(data)
+        assert np.array_equal(sym, ref.encode(data))
+        soft = _noisy_soft(rng, sym, p_flip, p_erase)
+        assert np.array_equal(port.viterbi(soft, nbits), ref.viterbi(soft, nbits)), (p_flip, p_erase)
+
+
+def test_viterbi_adversarial(ref, port):
+    nbits = 768
+    n = 4 * (nbits + 6)
+    rng = np.random.default_rng(5)
+    cases = [np.full(n, 128, np.uint8), np.full(n, 127, np.uint8), np.full(n, 129, np.uint8),
+             np.tile(np.array([127, 129], np.uint8), n // 2),
+             rng.choice(np.array([127, 128, 129], np.uint8), n)]
+    for soft in cases:
+        assert np.array_equal(port.viterbi(soft, nbits), ref.viterbi(soft, nbits))
+
+
+def test_depuncture_all_profiles(ref, port):
+    rng = np.random.default_rng(3)
+    bits = rng.integers(0, 2, 2304, dtype=np.uint8)
+    assert np.array_equal(port.fic_depuncture(bits), ref.fic_depuncture(bits))
+    for idx in range(64):
+        bits = rng.integers(0, 2, 64 * T.UEP[idx][1], dtype=np.uint8)
+        a, b = port.uep_depuncture(bits, idx), ref.uep_depuncture(bits, idx)
+        assert a.size == b.size == 4 * (24 * T.UEP[idx][0] + 6) and np.array_equal(a, b), idx
+    for lvl in range(8):
+        mul = {0: 12, 1: 8, 2: 6, 3: 4, 4: 27, 5: 21, 6: 18, 7: 15}[lvl]
+        for n in (1, 2, 3, 7, 12):
+            size = mul * n
+            if size > 864:
+                continue
+            bitrate = n * (8 if lvl < 4 else 32)
+            if bitrate > 384:
+                continue
+            bits = rng.integers(0, 2, 64 * size, dtype=np.uint8)
+            a, b = port.eep_depuncture(bits, lvl, size, bitrate), ref.eep_depuncture(bits, lvl, size, bitrate)
+            assert a.size == b.size and np.array_equal(a, b), (lvl, n)
+
+
+def test_descramble_crc_deinterleave(ref, port):
+    rng = np.random.default_rng(4)
+    for n in (1, 96, 384, 1152):
+        buf = rng.integers(0, 256, n, dtype=np.uint8)
+        assert np.array_equal(port.descramble(buf), ref.descramble(buf))
+    null_fib = np.zeros(32, np.uint8)
+    null_fib[0], null_fib[30], null_fib[31] = 0xFF, 0xA8, 0xA8     # fic.c:150-155
+    assert port.check_fib_crc(null_fib) == ref.check_fib_crc(null_fib) == 1
+    for _ in range(20):
+        fib = rng.integers(0, 256, 32, dtype=np.uint8)
+        assert port.check_fib_crc(fib) == ref.check_fib_crc(fib)
+    cifs = [rng.integers(0, 2, 55296, dtype=np.uint8) for _ in range(16)]
+    assert np.array_equal(port.time_deinterleave(cifs), ref.time_deinterleave(cifs))
+
+
+@pytest.mark.parametrize("ens_name,flip", [("small", 0.0), ("small", 0.03), ("reference", 0.0), ("reference", 0.05)])
+def test_backend_eti(ref, port, ens_name, flip):
+    ens = synth.small_ensemble() if ens_name == "small" else synth.reference_ensemble()
+    g = synth.ModeITransmitter(ens).generate(1, 18, seed=11, want_iq=False)
+    bits = g["bits"][0].numpy().copy()
+    if flip:
+        rng = np.random.default_rng(1)
+        bits ^= (rng.random(bits.shape) < flip).astype(np.uint8)
+        bits[7, :9216] ^= (rng.random(9216) < 0.3).astype(np.uint8)     # kill one FIC -> lock loss path
+    eti_r, fibs_r, crc_r = ref.run_backend(bits)
+    eti_p, fibs_p, crc_p = port.run_backend(bits)
+    assert np.array_equal(crc_r, crc_p) and np.array_equal(fibs_r, fibs_p)
+    assert eti_r.shape == eti_p.shape and np.array_equal(eti_r, eti_p)
+    if not flip:
+        assert eti_r.shape[0] == 4 * (18 - 13)
+
+
+def test_frontend_single_frame(ref, port):
+    ens = synth.small_ensemble()
+    g = synth.ModeITransmitter(ens).generate(1, 2, seed=5, snr_db=25)
+    frame = g["iq"][0].numpy()[:393216]
+    a, b = ref.demod_frame(frame), port.demod_frame(frame)
+    for k in ("ok", "coarse_timeshift", "fine_timeshift", "coarse_freq_shift"):
+        assert a[k] == b[k], k
+    assert a["ok"] == 1
+    assert abs(a["fine_freq_shift"] - b["fine_freq_shift"]) < 1e-9
+    assert np.allclose(a["symbols"], b["symbols"], rtol=0, atol=1e-6)
+    assert np.allclose(a["symbols_d"][1:], b["symbols_d"][1:], rtol=1e-9, atol=1e-9)
+    assert np.array_equal(a["bits"], b["bits"])
+    assert (a["bits"] != g["bits"][0, 0].numpy()).sum() <= 20
+    # a misaligned frame takes the coarse-resync branch identically
+    frame2 = g["iq"][0].numpy()[100000:100000 + 393216]
+    a2, b2 = ref.demod_frame(frame2, want_spectra=False), port.demod_frame(frame2, want_spectra=False)
+    assert a2["ok"] == b2["ok"] == 0 and a2["coarse_timeshift"] == b2["coarse_timeshift"] != 0
+
+
+@pytest.mark.parametrize("cut,cfo", [(0, 0.0), (123456, 0.0), (50000, 180.0), (77777, -2300.0)])
+def test_full_path_iq(ref, port, cut, cfo):
+    ens = synth.small_ensemble()
+    g = synth.ModeITransmitter(ens).generate(1, 22, seed=9, snr_db=28, cfo_hz=cfo, tail_samples=262144)
+    iq = g["iq"][0].numpy()[2 * cut:]
+    a, b = ref.run_iq(iq, want_tfs=3), port.run_iq(iq, want_tfs=3)
+    assert np.array_equal(a["trace"], b["trace"])
+    assert np.array_equal(a["tfs"], b["tfs"])
+    assert a["eti"].shape == b["eti"].shape and np.array_equal(a["eti"], b["eti"])
+    if cfo == 0.0:
+        assert a["eti"].shape[0] >= 16
