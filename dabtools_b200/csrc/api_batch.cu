@@ -1,5 +1,6 @@
 // api_batch.cu -- stateless batched entry points of include/dabgpu.h.
 #include "../../include/dabgpu.h"
+#include "ofdm.cuh"
 #include "vitbatch.cuh"
 
 using namespace dabgpu;
@@ -31,7 +32,7 @@ DABGPU_EXPORT int dabgpu_tab_shape(int kind, int a, int b, int32_t *out23) {
   else if (kind == 1)
     rc = dabgpu_shape_uep(&sh, a);
   else if (kind == 2)
-    rc = dabgpu_shape_eep(&sh, a, b);
+    rc = dabgpu_shape_eep(&sh, a, b, -1);
   else
     rc = -1;
   if (rc) {
@@ -142,7 +143,7 @@ DABGPU_EXPORT int dabgpu_fic_decode_batch(const uint8_t *fic_bits, int n_groups,
     d_fibs = ws.out.as<uint8_t>();
     d_ok = ws.aux.as<uint8_t>();
   }
-  if ((rc = launch_prep_hard(d_bits, 2304, ws.steps.as<uint8_t>(), row, n_groups, ws.shape.as<ShapeDev>(),
+  if ((rc = launch_prep_hard(d_bits, 2304, 1, 2304, nullptr, ws.steps.as<uint8_t>(), row, n_groups, ws.shape.as<ShapeDev>(),
                              nsteps, st)))
     return rc;
   ws.vb.clear();
@@ -155,5 +156,55 @@ DABGPU_EXPORT int dabgpu_fic_decode_batch(const uint8_t *fic_bits, int n_groups,
     CUDA_TRY(cudaMemcpyAsync(crc_ok, d_ok, (size_t)n_groups * 3, cudaMemcpyDeviceToHost, st));
     CUDA_TRY(cudaStreamSynchronize(st));
   }
+  return DABGPU_OK;
+}
+
+// ---- single-frame front-end ---------------------------------------------------------------------------
+DABGPU_EXPORT int dabgpu_sync_frame(const uint8_t *frame, int force_timesync, int32_t *out4, float *fine_freq_hz) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  cudaStream_t st = current_stream();
+  Workspace &ws = t_ws;
+  if ((rc = ws.in.reserve(DABGPU_TF_BYTES))) return rc;
+  if ((rc = ws.aux.reserve(sizeof(StepCtl) + sizeof(SyncOut)))) return rc;
+  StepCtl ctl;
+  memset(&ctl, 0, sizeof ctl);
+  ctl.run = 1;
+  ctl.force_timesync = force_timesync ? 1u : 0u;
+  SyncOut so;
+  memset(&so, 0, sizeof so);
+  CUDA_TRY(cudaMemcpyAsync(ws.in.p, frame, DABGPU_TF_BYTES, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ws.aux.p, &ctl, sizeof ctl, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ws.aux.as<uint8_t>() + sizeof ctl, &so, sizeof so, cudaMemcpyHostToDevice, st));
+  SyncOut *d_so = reinterpret_cast<SyncOut *>(ws.aux.as<uint8_t>() + sizeof ctl);
+  if ((rc = launch_sync(ws.in.as<uint8_t>(), ws.aux.as<StepCtl>(), d_so, 1, st))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(&so, d_so, sizeof so, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  out4[0] = so.coarse_timeshift;
+  out4[1] = so.fine_timeshift;
+  out4[2] = so.coarse_freq_shift;
+  out4[3] = so.ok;
+  if (fine_freq_hz) *fine_freq_hz = so.fine_freq_shift;
+  return DABGPU_OK;
+}
+
+DABGPU_EXPORT int dabgpu_demod_frame_debug(const uint8_t *frame, float *symbols, float *symbols_d, uint8_t *bits) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  cudaStream_t st = current_stream();
+  Workspace &ws = t_ws;
+  const size_t nsym = (size_t)76 * 2048 * sizeof(float2);
+  if ((rc = ws.in.reserve(DABGPU_TF_BYTES))) return rc;
+  if ((rc = ws.out.reserve(2 * nsym + 230400))) return rc;
+  float2 *d_sym = ws.out.as<float2>();
+  float2 *d_symd = d_sym + 76 * 2048;
+  uint8_t *d_bits = ws.out.as<uint8_t>() + 2 * nsym;
+  CUDA_TRY(cudaMemcpyAsync(ws.in.p, frame, DABGPU_TF_BYTES, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(ws.out.p, 0, 2 * nsym + 230400, st));
+  if ((rc = launch_demod_debug(ws.in.as<uint8_t>(), d_sym, d_symd, d_bits, st))) return rc;
+  if (symbols) CUDA_TRY(cudaMemcpyAsync(symbols, d_sym, nsym, cudaMemcpyDeviceToHost, st));
+  if (symbols_d) CUDA_TRY(cudaMemcpyAsync(symbols_d, d_symd, nsym, cudaMemcpyDeviceToHost, st));
+  if (bits) CUDA_TRY(cudaMemcpyAsync(bits, d_bits, 230400, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return DABGPU_OK;
 }

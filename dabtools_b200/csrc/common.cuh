@@ -33,6 +33,15 @@ int last_error_code();
     }                                                                                       \
   } while (0)
 
+// every kernel launch of the library is counted (bench.py reports it as gpu_launches)
+void note_launch();
+uint64_t launch_count();
+#define LAUNCH_CHECK()               \
+  do {                               \
+    ::dabgpu::note_launch();         \
+    CUDA_TRY(cudaGetLastError());    \
+  } while (0)
+
 // ---- the stream every launch of the calling thread goes to ---------------------------
 cudaStream_t current_stream();
 

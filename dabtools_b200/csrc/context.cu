@@ -1,5 +1,6 @@
 // context.cu -- error state, stream selection, scratch buffers, one-time device setup.
 #include <cstdarg>
+#include <atomic>
 #include <mutex>
 
 #include "common.cuh"
@@ -56,6 +57,10 @@ void PinBuf::release() {
   cap = 0;
 }
 
+static std::atomic<uint64_t> g_launches{0};
+void note_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+uint64_t launch_count() { return g_launches.load(std::memory_order_relaxed); }
+
 static std::mutex g_init_mu;
 static bool g_ready[64];
 
@@ -108,6 +113,7 @@ DABGPU_EXPORT int dabgpu_set_device(int dev) {
   return ensure_device_ready();
 }
 DABGPU_EXPORT void dabgpu_set_stream(void *cuda_stream) { t_stream = (cudaStream_t)cuda_stream; }
+DABGPU_EXPORT uint64_t dabgpu_launch_count(void) { return launch_count(); }
 DABGPU_EXPORT int dabgpu_synchronize(void) {
   CUDA_TRY(cudaStreamSynchronize(t_stream));
   return DABGPU_OK;

@@ -1,0 +1,532 @@
+// engine.cu -- batched receiver (see engine.cuh) and its C ABI (include/dabgpu.h).
+#include "engine.cuh"
+
+#include <cmath>
+
+namespace dabgpu {
+
+enum { FIC_ROW = 784 /* vit_row_bytes(774) */, FIBS_PER_TF = 384, TF_SLOTS = 5, CIF_SLOTS = 20 };
+
+int Engine::shape_index(const dabgpu_cw_shape &s) {
+  for (size_t i = 0; i < shapes.size(); i++)
+    if (memcmp(&shapes[i], &s, sizeof s) == 0) return (int)i;
+  shapes.push_back(s);
+  shapes_dirty = true;
+  return (int)shapes.size() - 1;
+}
+
+int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  if (n_streams <= 0) {
+    set_error(DABGPU_ERR_ARG, "engine: n_streams must be positive");
+    return DABGPU_ERR_ARG;
+  }
+  S = n_streams;
+  f0 = tuner_hz;
+  quiet = !(flags & DABGPU_ENGINE_VERBOSE);
+  virtual_tuner = flags & DABGPU_ENGINE_VIRTUAL_TUNER;
+  front.assign(S, FrontState());
+  back.resize(S);
+  layout.assign(S, EnsLayout());
+  stats.assign(S, StreamStats());
+  for (int s = 0; s < S; s++) {
+    front[s].frequency = tuner_hz;
+    front[s].rng.seed(1);
+    back[s].reset();
+  }
+  if ((rc = d_cifs.reserve((size_t)S * CIF_SLOTS * CIF_BYTES))) return rc;
+  if ((rc = d_fibs.reserve((size_t)S * TF_SLOTS * FIBS_PER_TF))) return rc;
+  if ((rc = d_ficbits.reserve((size_t)S * 9216))) return rc;
+  if ((rc = d_steps_fic.reserve((size_t)S * 4 * FIC_ROW))) return rc;
+  if ((rc = d_eti.reserve((size_t)S * 4 * DABGPU_ETI_BYTES))) return rc;
+  if ((rc = d_ens.reserve((size_t)S * sizeof(EnsDev)))) return rc;
+  if ((rc = d_gather_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
+  if ((rc = h_fic_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
+  CUDA_TRY(cudaMemset(d_cifs.p, 0, (size_t)S * CIF_SLOTS * CIF_BYTES));
+  CUDA_TRY(cudaMemset(d_fibs.p, 0, (size_t)S * TF_SLOTS * FIBS_PER_TF));
+  dabgpu_cw_shape fs;
+  ShapeDev fsd;
+  dabgpu_shape_fic(&fs);
+  shape_to_dev(fs, &fsd);
+  if ((rc = d_fic_shape.reserve(sizeof fsd))) return rc;
+  CUDA_TRY(cudaMemcpy(d_fic_shape.p, &fsd, sizeof fsd, cudaMemcpyHostToDevice));
+  return DABGPU_OK;
+}
+
+void Engine::destroy() {
+  DevBuf *db[] = {&d_ring, &d_frames, &d_chunk, &d_ctl, &d_sync, &d_cifs, &d_fibs, &d_crc, &d_ficbits,
+                  &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
+                  &d_subjobs, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
+  for (DevBuf *b : db) b->release();
+  PinBuf *pb[] = {&h_ctl, &h_sync, &h_fic_out, &h_jobs, &h_eti, &h_chunk};
+  for (PinBuf *b : pb) b->release();
+  vb_fic.release();
+  vb_msc.release();
+}
+
+// (re)derive the ETI/MSC layout of stream s from its ens_info (misc.c:153-213, :246-278)
+int Engine::refresh_layout(int s) {
+  EnsLayout &L = layout[s];
+  const ens_info_t &ei = back[s].ens_info;
+  if (L.version == back[s].ens_version) return DABGPU_OK;
+  L.version = back[s].ens_version;
+  L.nsub = 0;
+  memset(&L.dev, 0, sizeof L.dev);
+  uint32_t row = 0, nst = 0, fl = 0, payload = 0;
+  for (int j = 0; j < 64; j++)
+    if (ei.subchans[j].id >= 0) nst++;
+  L.e1 = 12 + 4 * nst;
+  uint32_t e = L.e1 + 96;
+  for (int j = 0; j < 64; j++) {
+    const subchannel_info_t &sc = ei.subchans[j];
+    if (sc.id < 0) continue;
+    dabgpu_cw_shape sh;
+    if (host_subch_shape(&sc, &sh) || sh.nbits <= 0 || sh.nbits > 9216 ||
+        sc.start_cu * 64 + sh.in_bits > DABGPU_CIF_BITS) {
+      // the reference would read out of bounds / index past its tables here; refuse loudly
+      set_error(DABGPU_ERR_STATE, "stream %d: sub-channel %d has an undecodable description", s, sc.id);
+      L.version = 0;
+      return DABGPU_ERR_STATE;
+    }
+    EnsLayout::Sub &u = L.sub[L.nsub];
+    u.in_bit0 = (uint32_t)sc.start_cu * 64u;
+    u.shape = (uint32_t)shape_index(sh);
+    u.nbits = (uint32_t)sh.nbits;
+    u.row_off = row;
+    u.eti_off = e;
+    row += vit_row_bytes(u.nbits + 6);
+    const int obytes = host_subch_obytes(sh.nbits);
+    e += obytes;
+    payload += obytes;
+    fl += sc.bitrate * 3 / 4;
+    const int tpl = sc.slForm == 0 ? (0x10 | (sc.protlev - 1)) : (0x20 | sc.protlev);
+    const int stl = sc.bitrate * 3 / 8;
+    uint8_t *w = L.dev.stc[L.nsub];
+    w[0] = (uint8_t)((sc.id << 2) | ((sc.start_cu >> 8) & 3));
+    w[1] = (uint8_t)sc.start_cu;
+    w[2] = (uint8_t)((tpl << 2) | ((stl >> 8) & 3));
+    w[3] = (uint8_t)stl;
+    L.nsub++;
+  }
+  if (e + 8 > DABGPU_ETI_BYTES) {
+    set_error(DABGPU_ERR_STATE, "stream %d: multiplex does not fit an ETI frame", s);
+    L.version = 0;
+    return DABGPU_ERR_STATE;
+  }
+  L.rows_bytes = row;
+  L.dev.nst = nst;
+  L.dev.fl = fl + nst + 1 + 24;
+  L.dev.payload = payload;
+  CUDA_TRY(cudaMemcpyAsync(d_ens.as<EnsDev>() + s, &L.dev, sizeof(EnsDev), cudaMemcpyHostToDevice,
+                           current_stream()));
+  // L.dev lives in this object, and is not modified again before the next sync of the step
+  return DABGPU_OK;
+}
+
+int Engine::upload_tables(cudaStream_t st) {
+  if (!shapes_dirty) return DABGPU_OK;
+  std::vector<ShapeDev> sd(shapes.size());
+  for (size_t i = 0; i < shapes.size(); i++) shape_to_dev(shapes[i], &sd[i]);
+  int rc;
+  if ((rc = d_shapes.reserve(sd.size() * sizeof(ShapeDev) + 4096))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_shapes.p, sd.data(), sd.size() * sizeof(ShapeDev), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // sd is a local
+  shapes_dirty = false;
+  return DABGPU_OK;
+}
+
+// FIC decode of the `active` streams' frames, host state machines, MSC decode and ETI assembly.
+// d_fic_src + s*fic_stride holds stream s' 9216 demapped FIC bits (one byte each).
+// sync: SyncOut per stream (front-end path) or null (demapped path: every active frame is "ok").
+int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride,
+                            const SyncOut *sync) {
+  int rc;
+  const int na = (int)active.size();
+  n_eti = 0;
+  eti_stream.clear();
+  if (na == 0) return DABGPU_OK;
+
+  // ---- FIC: 4 groups per frame -> compact [na][384] FIBs + [na][12] CRC flags ----
+  uint8_t *d_fib_c = d_gather_out.as<uint8_t>();
+  uint8_t *d_crc_c = d_fib_c + (size_t)na * FIBS_PER_TF;
+  if ((rc = h_jobs.reserve((size_t)na * (sizeof(uint32_t) + sizeof(uint64_t))))) return rc;
+  uint32_t *h_idx = h_jobs.as<uint32_t>();
+  uint64_t *h_dst = reinterpret_cast<uint64_t *>(h_jobs.as<uint8_t>() + (((size_t)na * 4 + 7) & ~(size_t)7));
+  if ((rc = h_jobs.reserve((((size_t)na * 4 + 7) & ~(size_t)7) + (size_t)na * 8))) return rc;
+  h_idx = h_jobs.as<uint32_t>();
+  h_dst = reinterpret_cast<uint64_t *>(h_jobs.as<uint8_t>() + (((size_t)na * 4 + 7) & ~(size_t)7));
+  vb_fic.clear();
+  for (int a = 0; a < na; a++) {
+    const int s = active[a];
+    h_idx[a] = (uint32_t)s;
+    h_dst[a] = ((uint64_t)s * TF_SLOTS + (uint64_t)back[s].tfidx) * FIBS_PER_TF;
+    for (int k = 0; k < 4; k++)
+      vb_fic.add(((uint64_t)a * 4 + k) * FIC_ROW, (uint64_t)a * FIBS_PER_TF + 96 * k, 768, VIT_DESCRAMBLE);
+  }
+  if ((rc = d_gather_idx.reserve((((size_t)na * 4 + 7) & ~(size_t)7) + (size_t)na * 8))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_gather_idx.p, h_jobs.p, (((size_t)na * 4 + 7) & ~(size_t)7) + (size_t)na * 8,
+                           cudaMemcpyHostToDevice, st));
+  const uint32_t *d_idx = d_gather_idx.as<uint32_t>();
+  const uint64_t *d_dst = reinterpret_cast<const uint64_t *>(d_gather_idx.as<uint8_t>() +
+                                                             (((size_t)na * 4 + 7) & ~(size_t)7));
+  if ((rc = launch_prep_hard(d_fic_src, 2304, 4, fic_stride, d_idx, d_steps_fic.as<uint8_t>(), FIC_ROW, 4 * na,
+                             d_fic_shape.as<ShapeDev>(), 774, st)))
+    return rc;
+  if ((rc = vb_fic.run(d_steps_fic.as<uint8_t>(), d_fib_c, st))) return rc;
+  trellis_steps += vb_fic.total_steps;
+  if ((rc = launch_fib_crc(d_fib_c, d_crc_c, 12 * na, st))) return rc;
+  if ((rc = launch_scatter_rows(d_fib_c, FIBS_PER_TF, d_dst, d_fibs.as<uint8_t>(), na, st))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(h_fic_out.p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+
+  // ---- host: per-stream sdr_demod epilogue + dab_process_frame ----
+  const uint8_t *h_fibs = h_fic_out.as<uint8_t>();
+  const uint8_t *h_crc = h_fibs + (size_t)na * FIBS_PER_TF;
+  cifjobs.clear();
+  subjobs.clear();
+  etijobs.clear();
+  vb_msc.clear();
+  uint64_t row_base = 0;
+  for (int a = 0; a < na; a++) {
+    const int s = active[a];
+    FrontState &fr = front[s];
+    fr.pending = false;
+    if (sync) {
+      // input_sdr.c:65-112: the order in which sdr_demod updates its state and bails out
+      const SyncOut &so = sync[s];
+      fr.coarse_timeshift = so.coarse_timeshift;
+      fr.force_timesync = 0;
+      fr.last_ok = 0;
+      if (so.coarse_timeshift) continue;
+      fr.fine_timeshift = so.fine_timeshift;
+      fr.coarse_freq_shift = so.coarse_freq_shift;
+      if (std::abs(so.coarse_freq_shift) > 1) {
+        fr.force_timesync = 1;
+        continue;
+      }
+      fr.fine_freq_shift = (double)so.fine_freq_shift;
+      fr.last_ok = 1;
+    }
+    stats[s].frames_demodulated++;
+    for (int i = 0; i < 12; i++) stats[s].fib_crc_errors += h_crc[12 * a + i] ? 0 : 1;
+    FrameWork work;
+    host_process_frame(back[s], h_fibs + (size_t)a * FIBS_PER_TF, h_crc + 12 * a, &work, quiet);
+    if (!work.n_eti) continue;
+    if ((rc = refresh_layout(s))) return rc;
+    const EnsLayout &L = layout[s];
+    for (int k = 0; k < work.n_eti; k++) {
+      const int f = n_eti++;
+      eti_stream.push_back(s);
+      CifJob cj;
+      for (int j = 0; j < 16; j++)
+        cj.slot_off[j] = ((uint64_t)s * CIF_SLOTS + (uint64_t)work.win[k][j]) * CIF_BYTES;
+      cj.sub0 = (uint32_t)subjobs.size();
+      cj.nsub = (uint32_t)L.nsub;
+      for (int u = 0; u < L.nsub; u++) {
+        SubJob sj;
+        sj.row_off = row_base + L.sub[u].row_off;
+        sj.in_bit0 = L.sub[u].in_bit0;
+        sj.shape = L.sub[u].shape;
+        subjobs.push_back(sj);
+        vb_msc.add(sj.row_off, (uint64_t)f * DABGPU_ETI_BYTES + L.sub[u].eti_off, L.sub[u].nbits, VIT_DESCRAMBLE);
+      }
+      row_base += L.rows_bytes;
+      cifjobs.push_back(cj);
+      EtiJob ej;
+      const int w0 = work.win[k][0];
+      ej.fib_off = ((uint64_t)s * TF_SLOTS + (uint64_t)(w0 >> 2)) * FIBS_PER_TF + 96u * (uint32_t)(w0 & 3);
+      ej.ens = (uint32_t)s;
+      ej.cif_hi = work.cif_hi[k];
+      ej.cif_lo = work.cif_lo[k];
+      ej.pad[0] = ej.pad[1] = 0;
+      etijobs.push_back(ej);
+    }
+    stats[s].eti_frames += work.n_eti;
+  }
+  if (!n_eti) return DABGPU_OK;
+
+  // ---- MSC: time de-interleave + depuncture gather -> Viterbi + descramble -> ETI ----
+  if ((rc = upload_tables(st))) return rc;
+  const size_t b_cif = cifjobs.size() * sizeof(CifJob), b_sub = subjobs.size() * sizeof(SubJob),
+               b_eti = etijobs.size() * sizeof(EtiJob);
+  if ((rc = h_jobs.reserve(b_cif + b_sub + b_eti))) return rc;
+  if ((rc = d_cifjobs.reserve(b_cif + b_sub + b_eti))) return rc;
+  if ((rc = d_steps_msc.reserve(row_base + 64))) return rc;
+  if ((rc = d_eti.reserve((size_t)n_eti * DABGPU_ETI_BYTES))) return rc;
+  uint8_t *hp = h_jobs.as<uint8_t>();
+  memcpy(hp, cifjobs.data(), b_cif);
+  memcpy(hp + b_cif, subjobs.data(), b_sub);
+  memcpy(hp + b_cif + b_sub, etijobs.data(), b_eti);
+  CUDA_TRY(cudaMemcpyAsync(d_cifjobs.p, hp, b_cif + b_sub + b_eti, cudaMemcpyHostToDevice, st));
+  const CifJob *dj = d_cifjobs.as<CifJob>();
+  const SubJob *ds = reinterpret_cast<const SubJob *>(d_cifjobs.as<uint8_t>() + b_cif);
+  const EtiJob *de = reinterpret_cast<const EtiJob *>(d_cifjobs.as<uint8_t>() + b_cif + b_sub);
+  if ((rc = launch_msc_gather(d_cifs.as<uint8_t>(), dj, ds, d_shapes.as<ShapeDev>(), d_steps_msc.as<uint8_t>(),
+                              n_eti, st)))
+    return rc;
+  if ((rc = vb_msc.run(d_steps_msc.as<uint8_t>(), d_eti.as<uint8_t>(), st))) return rc;
+  trellis_steps += vb_msc.total_steps;
+  if ((rc = launch_eti_pack(de, d_ens.as<EnsDev>(), d_fibs.as<uint8_t>(), d_eti.as<uint8_t>(), n_eti, st)))
+    return rc;
+  return DABGPU_OK;
+}
+
+int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *mask, bool on_device) {
+  int rc;
+  cudaStream_t st = current_stream();
+  if (pitch < 230400) {
+    set_error(DABGPU_ERR_ARG, "process_demapped: pitch must be >= 230400");
+    return DABGPU_ERR_ARG;
+  }
+  active.clear();
+  for (int s = 0; s < S; s++)
+    if (!mask || mask[s]) active.push_back(s);
+  const uint8_t *d_tf = tfs;
+  if (!on_device) {
+    if ((rc = d_tfbytes.reserve((size_t)S * pitch))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_tfbytes.p, tfs, (size_t)S * pitch, cudaMemcpyHostToDevice, st));
+    d_tf = d_tfbytes.as<uint8_t>();
+  }
+  // MSC bytes -> planes in the slot of the stream's current tfidx (dab.c:35: tfs[tfidx])
+  const int na = (int)active.size();
+  n_eti = 0;
+  eti_stream.clear();
+  if (!na) return DABGPU_OK;
+  if (na == S) {
+    if ((rc = h_ctl.reserve((size_t)S * 4 * sizeof(uint64_t)))) return rc;
+    if ((rc = d_planeoff.reserve((size_t)S * 4 * sizeof(uint64_t)))) return rc;
+    uint64_t *off = h_ctl.as<uint64_t>();
+    for (int s = 0; s < S; s++)
+      for (int k = 0; k < 4; k++) off[4 * s + k] = ((uint64_t)s * CIF_SLOTS + back[s].tfidx * 4 + k) * CIF_BYTES;
+    CUDA_TRY(cudaMemcpyAsync(d_planeoff.p, off, (size_t)S * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
+    if ((rc = launch_pack_planes(d_tf + 9216, pitch, d_planeoff.as<uint64_t>(), d_cifs.as<uint8_t>(), S, st)))
+      return rc;
+  } else {
+    // masked call: pack stream by stream (not a throughput path)
+    if ((rc = h_ctl.reserve(4 * sizeof(uint64_t) * (size_t)na))) return rc;
+    if ((rc = d_planeoff.reserve(4 * sizeof(uint64_t) * (size_t)na))) return rc;
+    uint64_t *off = h_ctl.as<uint64_t>();
+    for (int a = 0; a < na; a++)
+      for (int k = 0; k < 4; k++)
+        off[4 * a + k] = ((uint64_t)active[a] * CIF_SLOTS + back[active[a]].tfidx * 4 + k) * CIF_BYTES;
+    CUDA_TRY(cudaMemcpyAsync(d_planeoff.p, off, 4 * sizeof(uint64_t) * (size_t)na, cudaMemcpyHostToDevice, st));
+    for (int a = 0; a < na; a++)
+      if ((rc = launch_pack_planes(d_tf + (size_t)active[a] * pitch + 9216, pitch,
+                                   d_planeoff.as<uint64_t>() + 4 * a, d_cifs.as<uint8_t>(), 1, st)))
+        return rc;
+  }
+  return fic_and_backend(st, d_tf, pitch, nullptr);
+}
+
+int Engine::ensure_frontend() {
+  int rc;
+  if (d_ring.p) return DABGPU_OK;
+  if ((rc = d_ring.reserve((size_t)S * IQ_RING_BYTES))) return rc;
+  if ((rc = d_frames.reserve((size_t)S * DABGPU_TF_BYTES))) return rc;
+  if ((rc = d_ctl.reserve((size_t)S * sizeof(StepCtl)))) return rc;
+  if ((rc = d_sync.reserve((size_t)S * sizeof(SyncOut)))) return rc;
+  if ((rc = h_ctl.reserve((size_t)S * sizeof(StepCtl)))) return rc;
+  if ((rc = h_sync.reserve((size_t)S * sizeof(SyncOut)))) return rc;
+  CUDA_TRY(cudaMemset(d_ring.p, 0, (size_t)S * IQ_RING_BYTES));
+  CUDA_TRY(cudaMemset(d_frames.p, 0, (size_t)S * DABGPU_TF_BYTES));
+  CUDA_TRY(cudaMemset(d_sync.p, 0, (size_t)S * sizeof(SyncOut)));
+  return DABGPU_OK;
+}
+
+// dab2eti.c:75-103, applied after every callback
+static void tuner_feedback(FrontState &fr) {
+  const int cfs = fr.coarse_freq_shift;
+  if (std::abs(cfs) > 1) fr.frequency = cfs < 0 ? fr.frequency - 1000u : fr.frequency + 1000u;
+  if (std::abs(cfs) == 1) {
+    const uint32_t d = (uint32_t)(fr.rng.next() % 1000);
+    fr.frequency = cfs < 0 ? fr.frequency - d : fr.frequency + d;
+  }
+  if (std::abs(cfs) < 1 && std::abs((int)fr.fine_freq_shift) > 50)
+    fr.frequency = (uint32_t)((double)fr.frequency + fr.fine_freq_shift / 3);
+}
+
+int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_device) {
+  int rc;
+  if (chunk_len <= 0 || chunk_len > 262144 || (chunk_len & 15) || pitch < (size_t)chunk_len) {
+    set_error(DABGPU_ERR_ARG, "feed_iq: chunk_len must be a multiple of 16 in (0, 262144], pitch >= chunk_len");
+    return DABGPU_ERR_ARG;
+  }
+  if ((rc = ensure_frontend())) return rc;
+  cudaStream_t st = current_stream();
+  StepCtl *ctl = h_ctl.as<StepCtl>();
+  active.clear();
+  bool any_read = false;
+  for (int s = 0; s < S; s++) {
+    FrontState &fr = front[s];
+    StepCtl &c = ctl[s];
+    memset(&c, 0, sizeof c);
+    fr.coarse_freq_shift = 0;  // input_sdr.c:33
+    fr.last_ok = 0;
+    // cbWrite x chunk_len (input_sdr.c:36-38)
+    if (fr.fifo_count + (uint32_t)chunk_len > IQ_RING_BYTES) {
+      set_error(DABGPU_ERR_STATE, "stream %d: FIFO overflow", s);
+      return DABGPU_ERR_STATE;
+    }
+    c.wr_pos = (fr.fifo_start + fr.fifo_count) % IQ_RING_BYTES;
+    c.nco_hz = virtual_tuner ? (int32_t)(fr.frequency - f0) : 0;
+    c.nco_sample0 = fr.samples_in;
+    fr.samples_in += (uint64_t)chunk_len / 2;
+    fr.fifo_count += (uint32_t)chunk_len;
+    if (fr.fifo_count < 196608u * 3u) continue;  // input_sdr.c:41-43
+    // sdr_read_fifo(fifo, 393216, coarse+fine shift, buffer) (sdr_fifo.c:43-61)
+    const int32_t shift = fr.coarse_timeshift + fr.fine_timeshift;
+    const uint32_t bytes = DABGPU_TF_BYTES;
+    if (shift > 0) {
+      const uint32_t skip = std::min<uint32_t>((uint32_t)shift, fr.fifo_count);
+      const uint32_t skip_pos = fr.fifo_start;
+      fr.fifo_start = (fr.fifo_start + skip) % IQ_RING_BYTES;
+      fr.fifo_count -= skip;
+      const uint32_t n = std::min(bytes, fr.fifo_count);
+      c.rd_pos[0] = fr.fifo_start;
+      c.rd_dst[0] = 0;
+      c.rd_bytes[0] = n;
+      fr.fifo_start = (fr.fifo_start + n) % IQ_RING_BYTES;
+      fr.fifo_count -= n;
+      // the skipped bytes were parked in buffer[0..skip) and are only overwritten up to n
+      const uint32_t lim = std::min(skip, bytes);
+      if (n < lim) {
+        c.rd_pos[1] = (skip_pos + n) % IQ_RING_BYTES;
+        c.rd_dst[1] = n;
+        c.rd_bytes[1] = lim - n;
+      }
+    } else {
+      const uint32_t n = bytes + (uint32_t)shift;  // stale tail of -shift bytes is kept
+      c.rd_pos[0] = fr.fifo_start;
+      c.rd_dst[0] = 0;
+      c.rd_bytes[0] = n;
+      fr.fifo_start = (fr.fifo_start + n) % IQ_RING_BYTES;
+      fr.fifo_count -= n;
+    }
+    any_read = true;
+    if (fr.startup_delay <= 0) {  // GAIN_SETTLE_TIME == 0: the first frame is read and dropped
+      fr.startup_delay++;
+      if (!quiet) fprintf(stderr, "startup_delay=%i\n", fr.startup_delay);
+      continue;
+    }
+    fr.coarse_timeshift = 0;  // input_sdr.c:66
+    c.run = 1;
+    c.force_timesync = fr.force_timesync;
+    for (int k = 0; k < 4; k++)
+      c.cif_off[k] = ((uint64_t)s * CIF_SLOTS + (uint64_t)back[s].tfidx * 4 + k) * CIF_BYTES;
+    fr.pending = true;
+    active.push_back(s);
+  }
+  CUDA_TRY(cudaMemcpyAsync(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), cudaMemcpyHostToDevice, st));
+  const uint8_t *d_src = iq;
+  if (!on_device) {
+    if ((rc = d_chunk.reserve((size_t)S * chunk_len))) return rc;
+    CUDA_TRY(cudaMemcpy2DAsync(d_chunk.p, chunk_len, iq, pitch, chunk_len, S, cudaMemcpyHostToDevice, st));
+    d_src = d_chunk.as<uint8_t>();
+    pitch = chunk_len;
+  }
+  if ((rc = launch_ingest(d_src, pitch, (uint32_t)chunk_len, d_ring.as<uint8_t>(), d_ctl.as<StepCtl>(), S, st)))
+    return rc;
+  n_eti = 0;
+  eti_stream.clear();
+  if (any_read) {
+    if ((rc = launch_fifo_read(d_ring.as<uint8_t>(), d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), S, st)))
+      return rc;
+    if (!active.empty()) {
+      if ((rc = launch_sync(d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), S, st))) return rc;
+      if ((rc = launch_demod(d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(),
+                             d_ficbits.as<uint8_t>(), d_cifs.as<uint8_t>(), S, st)))
+        return rc;
+      CUDA_TRY(cudaMemcpyAsync(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st));
+      if ((rc = fic_and_backend(st, d_ficbits.as<uint8_t>(), 9216, h_sync.as<SyncOut>()))) return rc;
+    }
+  }
+  for (int s = 0; s < S; s++) tuner_feedback(front[s]);
+  return DABGPU_OK;
+}
+
+}  // namespace dabgpu
+
+// =============================== C ABI ===========================================================
+using namespace dabgpu;
+
+struct dabgpu_engine {
+  Engine e;
+};
+
+DABGPU_EXPORT int dabgpu_engine_create(dabgpu_engine **out, int n_streams, uint32_t tuner_hz, int flags) {
+  if (!out) return DABGPU_ERR_ARG;
+  dabgpu_engine *h = new dabgpu_engine();
+  int rc = h->e.init(n_streams, tuner_hz, flags);
+  if (rc) {
+    h->e.destroy();
+    delete h;
+    *out = nullptr;
+    return rc;
+  }
+  *out = h;
+  return DABGPU_OK;
+}
+DABGPU_EXPORT void dabgpu_engine_destroy(dabgpu_engine *h) {
+  if (!h) return;
+  cudaDeviceSynchronize();
+  h->e.destroy();
+  delete h;
+}
+DABGPU_EXPORT int dabgpu_engine_feed_iq(dabgpu_engine *h, const uint8_t *iq, size_t pitch, int chunk_len,
+                                        int on_device) {
+  return h->e.feed_iq(iq, pitch, chunk_len, on_device != 0);
+}
+DABGPU_EXPORT int dabgpu_engine_process_demapped(dabgpu_engine *h, const uint8_t *tfs, size_t pitch,
+                                                 const uint8_t *mask, int on_device) {
+  return h->e.process_demapped(tfs, pitch, mask, on_device != 0);
+}
+DABGPU_EXPORT int dabgpu_engine_eti_count(dabgpu_engine *h) { return h->e.n_eti; }
+DABGPU_EXPORT const uint8_t *dabgpu_engine_eti_device(dabgpu_engine *h) { return h->e.d_eti.as<uint8_t>(); }
+DABGPU_EXPORT int dabgpu_engine_fetch_eti(dabgpu_engine *h, uint8_t *eti, int32_t *stream_ids, int max_frames) {
+  Engine &e = h->e;
+  const int n = std::min(e.n_eti, max_frames);
+  if (n <= 0) return 0;
+  cudaStream_t st = current_stream();
+  if (eti) {
+    cudaError_t err = cudaMemcpyAsync(eti, e.d_eti.p, (size_t)n * DABGPU_ETI_BYTES, cudaMemcpyDeviceToHost, st);
+    if (err == cudaSuccess) err = cudaStreamSynchronize(st);
+    if (err != cudaSuccess) {
+      set_error(DABGPU_ERR_CUDA, "fetch_eti: %s", cudaGetErrorString(err));
+      return DABGPU_ERR_CUDA;
+    }
+  }
+  if (stream_ids) memcpy(stream_ids, e.eti_stream.data(), (size_t)n * sizeof(int32_t));
+  return n;
+}
+DABGPU_EXPORT int dabgpu_engine_status(dabgpu_engine *h, int stream, dabgpu_stream_status *out) {
+  Engine &e = h->e;
+  if (stream < 0 || stream >= e.S || !out) {
+    set_error(DABGPU_ERR_ARG, "engine_status: bad stream index");
+    return DABGPU_ERR_ARG;
+  }
+  const FrontState &fr = e.front[stream];
+  const BackendState &bk = e.back[stream];
+  out->locked = bk.locked;
+  out->okcount = bk.okcount;
+  out->ncifs = bk.ncifs;
+  out->tfidx = bk.tfidx;
+  out->coarse_timeshift = fr.coarse_timeshift;
+  out->fine_timeshift = fr.fine_timeshift;
+  out->coarse_freq_shift = fr.coarse_freq_shift;
+  out->last_ok = fr.last_ok;
+  out->fine_freq_shift = fr.fine_freq_shift;
+  out->frequency = fr.frequency;
+  out->n_subchannels = 0;
+  for (int i = 0; i < 64; i++) out->n_subchannels += bk.ens_info.subchans[i].id >= 0;
+  out->frames_demodulated = e.stats[stream].frames_demodulated;
+  out->eti_frames = e.stats[stream].eti_frames;
+  out->fib_crc_errors = e.stats[stream].fib_crc_errors;
+  return DABGPU_OK;
+}
+DABGPU_EXPORT int dabgpu_engine_set_seed(dabgpu_engine *h, int stream, unsigned seed) {
+  if (stream < 0 || stream >= h->e.S) return DABGPU_ERR_ARG;
+  h->e.front[stream].rng.seed(seed);
+  return DABGPU_OK;
+}
+DABGPU_EXPORT uint64_t dabgpu_engine_trellis_steps(dabgpu_engine *h) { return h->e.trellis_steps; }

@@ -1,0 +1,101 @@
+// engine.cuh -- the batched receiver: S independent ensemble streams in lock-step, each one
+// an instance of the reference's demod_thread_fn loop (dab2eti.c:60-115):
+//      sdr_demod -> dab_process_frame -> tuner feedback
+// with the sample/bit arithmetic on the GPU and the per-stream control state on the host.
+#pragma once
+#include <vector>
+
+#include "hostlogic.cuh"
+#include "msc.cuh"
+#include "ofdm.cuh"
+#include "vitbatch.cuh"
+
+namespace dabgpu {
+
+// derived from a stream's ens_info whenever its sub-channel table changes
+struct EnsLayout {
+  uint64_t version = 0;
+  int nsub = 0;
+  struct Sub {
+    uint32_t in_bit0, shape, nbits, row_off, eti_off;
+  } sub[64];
+  uint32_t rows_bytes = 0;  // step-byte rows of all sub-channels of one CIF
+  uint32_t e1 = 0;          // header length
+  EnsDev dev;
+};
+
+// sdr_state_t's scalar part (input_sdr.h:12-41) + FIFO bookkeeping (sdr_fifo.h:27-33)
+struct FrontState {
+  uint32_t frequency = 0;
+  uint32_t fifo_start = 0, fifo_count = 0;
+  int32_t coarse_timeshift = 0, fine_timeshift = 0, coarse_freq_shift = 0;
+  double fine_freq_shift = 0;
+  int32_t startup_delay = 0;
+  uint8_t force_timesync = 0;
+  uint64_t samples_in = 0;  // samples ingested so far (virtual-tuner phase reference)
+  int last_ok = 0;
+  bool pending = false;     // a frame of this stream is in flight in the current step
+  GlibcRand rng;
+};
+
+struct StreamStats {
+  uint64_t frames_demodulated = 0, eti_frames = 0, fib_crc_errors = 0;
+};
+
+struct Engine {
+  int S = 0;
+  uint32_t f0 = 0;
+  bool quiet = true;
+  bool virtual_tuner = false;
+  std::vector<FrontState> front;
+  std::vector<BackendState> back;
+  std::vector<EnsLayout> layout;
+  std::vector<StreamStats> stats;
+
+  // shapes seen so far (host list mirrored in d_shapes)
+  std::vector<dabgpu_cw_shape> shapes;
+  bool shapes_dirty = false;
+  int shape_index(const dabgpu_cw_shape &s);
+
+  // device stores
+  DevBuf d_ring, d_frames, d_chunk, d_ctl, d_sync;
+  DevBuf d_cifs;      // [S][20][CIF_BYTES]
+  DevBuf d_fibs;      // [S][5][384]
+  DevBuf d_crc;       // [S][5][12]
+  DevBuf d_ficbits;   // [S][9216]
+  DevBuf d_tfbytes;   // staging of demapped TFs given on the host
+  DevBuf d_steps_fic, d_steps_msc;
+  DevBuf d_eti;       // [4*S][6144]
+  DevBuf d_ens;       // EnsDev[S]
+  DevBuf d_shapes, d_fic_shape;
+  DevBuf d_cifjobs, d_subjobs, d_etijobs, d_planeoff, d_gather_idx, d_gather_out;
+  PinBuf h_ctl, h_sync, h_fic_out, h_jobs, h_eti, h_chunk;
+  VitBatch vb_fic, vb_msc;
+
+  // results of the last step
+  int n_eti = 0;
+  std::vector<int32_t> eti_stream;
+  uint64_t trellis_steps = 0;
+
+  // scratch vectors reused between steps
+  std::vector<int> active;
+  std::vector<CifJob> cifjobs;
+  std::vector<SubJob> subjobs;
+  std::vector<EtiJob> etijobs;
+
+  int init(int n_streams, uint32_t tuner_hz, int flags);
+  void destroy();
+  int ensure_frontend();
+  // one rtlsdr callback worth of IQ for every stream
+  int feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_device);
+  // one demapped TF (fic 9216 + msc 221184 bytes of 0/1) for every stream with mask[s] != 0
+  int process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *mask, bool on_device);
+
+ private:
+  int fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride,
+                      const SyncOut *h_sync_or_null);
+  int refresh_layout(int s);
+  int upload_tables(cudaStream_t st);
+};
+
+}  // namespace dabgpu

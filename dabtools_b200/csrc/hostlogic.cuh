@@ -1,0 +1,49 @@
+// hostlogic.cuh -- the reference's host-side control logic for the path (no arithmetic on
+// sample or bit streams happens here): FIG parsing, ensemble bookkeeping, the lock state
+// machine and the 16-CIF window.  The reference keeps this in C on the host too
+// (fic.c:47-147, misc.c:14-27, dab.c:35-99); libdabgpu runs one instance per stream.
+#pragma once
+#include "../../include/dabgpu_ref_abi.h"
+#include "common.cuh"
+
+namespace dabgpu {
+
+void host_fib_decode(tf_info_t *info, const uint8_t *fibs384, const uint8_t *crc_ok12, int nfibs);
+void host_merge_info(ens_info_t *ei, const tf_info_t *info);
+void host_init_ens(ens_info_t *ei);
+// puncturing layout of a sub-channel as the reference's create_eti would decode it
+int host_subch_shape(const subchannel_info_t *sc, dabgpu_cw_shape *out);
+// bytes the sub-channel contributes to the ETI MST (misc.c:259-260)
+static inline int host_subch_obytes(int nbits) { return ((nbits / 8) + 7) & 0xfff8; }
+
+// glibc rand() compatible generator (TYPE_3), one per stream, for dab2eti.c:88-96
+struct GlibcRand {
+  int32_t r[31];
+  int idx;
+  void seed(unsigned s);
+  int next();
+};
+
+// per-stream back-end state: dab_state_t without the 1.2 MB of frame buffers, which
+// live on the device (dab.h:70-89)
+struct BackendState {
+  tf_info_t tf_info;
+  ens_info_t ens_info;
+  int win[16];      // CIF store slots (tf*4+cif) of the 16-CIF window, [0] oldest
+  int ncifs, tfidx, locked, okcount, ens_info_shown;
+  uint64_t ens_version;  // bumped whenever ens_info's sub-channel table changes
+  void reset();
+};
+
+// one reference-shaped result of dab_process_frame(): how many ETI frames to build and from what
+struct FrameWork {
+  int n_eti;            // 0 or 4
+  int win[4][16];       // window slots for each of the ETI frames
+  uint8_t cif_hi[4], cif_lo[4];
+};
+// dab.c:35-99 with the FIC results (fibs, crc, ok_count) already decoded on the GPU.
+// tf_slot is the slot the frame was written to (== st.tfidx on entry).
+void host_process_frame(BackendState &st, const uint8_t *fibs384, const uint8_t *crc_ok12, FrameWork *out,
+                        bool quiet);
+
+}  // namespace dabgpu

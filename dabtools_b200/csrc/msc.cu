@@ -1,0 +1,265 @@
+// msc.cu -- time de-interleave + depuncture gather, CIF plane packing, ETI assembly.
+#include "msc.cuh"
+
+namespace dabgpu {
+
+__constant__ uint8_t c_tdi_slot[16];    // window slot that supplies plane m (misc.c:32 map[])
+__constant__ uint16_t c_x8pow[16];      // x^(8*2^j) mod (x^16+x^12+x^5+1), for CRC combination
+
+static uint16_t host_mulmod(uint16_t a, uint16_t b) {
+  uint32_t r = 0;
+  for (int i = 15; i >= 0; i--) {
+    r = (r & 0x8000u) ? ((r << 1) ^ 0x1021u) & 0xffffu : (r << 1) & 0xffffu;
+    if ((b >> i) & 1u) r ^= a;
+  }
+  return (uint16_t)r;
+}
+
+int msc_init_constants() {
+  CUDA_TRY(cudaMemcpyToSymbol(c_tdi_slot, DABGPU_TDI_DELAY, 16));
+  uint16_t p[16];
+  // x^8 mod P: a CRC register holding 1 shifted by one byte
+  uint16_t v = 1;
+  for (int b = 0; b < 8; b++) v = (v & 0x8000u) ? (uint16_t)((v << 1) ^ 0x1021u) : (uint16_t)(v << 1);
+  p[0] = v;
+  for (int j = 1; j < 16; j++) p[j] = host_mulmod(p[j - 1], p[j - 1]);
+  CUDA_TRY(cudaMemcpyToSymbol(c_x8pow, p, sizeof p));
+  return DABGPU_OK;
+}
+
+// ---- shared first half: 16 planes -> packed bits in logical order ---------------------------
+// lin must hold CIF_WORDS + 1 words
+__device__ __forceinline__ void deinterleave_to_smem(const uint8_t *__restrict__ cifs, const CifJob &job,
+                                                     uint32_t (*pl)[CIF_PLANE_WORDS], uint32_t *lin) {
+  for (int idx = threadIdx.x; idx < CIF_WORDS; idx += blockDim.x) {
+    const int m = idx / CIF_PLANE_WORDS, w = idx - m * CIF_PLANE_WORDS;
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(cifs + job.slot_off[c_tdi_slot[m]]);
+    pl[m][w] = __ldg(src + idx);
+  }
+  __syncthreads();
+  for (int W = threadIdx.x; W < CIF_WORDS; W += blockDim.x) {
+    // logical bits 32W..32W+31 = (q = 2W, m = 0..15), (q = 2W+1, m = 0..15)
+    const int pw = W >> 4, sh = 2 * (W & 15);
+    uint32_t out = 0;
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      const uint32_t t = (pl[m][pw] >> sh) & 3u;
+      out |= ((t & 1u) << m) | ((t >> 1) << (16 + m));
+    }
+    lin[W] = out;
+  }
+  if (threadIdx.x == 0) lin[CIF_WORDS] = 0;
+  __syncthreads();
+}
+
+// K3: one block per logical CIF
+__global__ void __launch_bounds__(256) msc_gather_kernel(const uint8_t *__restrict__ cifs,
+                                                         const CifJob *__restrict__ jobs,
+                                                         const SubJob *__restrict__ subs,
+                                                         const ShapeDev *__restrict__ shapes,
+                                                         uint8_t *__restrict__ steps) {
+  __shared__ uint32_t pl[16][CIF_PLANE_WORDS];
+  __shared__ uint32_t lin[CIF_WORDS + 1];
+  __shared__ CifJob job;
+  if (threadIdx.x < sizeof(CifJob) / 4)
+    reinterpret_cast<uint32_t *>(&job)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&jobs[blockIdx.x])[threadIdx.x];
+  __syncthreads();
+  deinterleave_to_smem(cifs, job, pl, lin);
+
+  for (uint32_t s = 0; s < job.nsub; s++) {
+    const SubJob sj = subs[job.sub0 + s];
+    const ShapeDev *sh = &shapes[sj.shape];
+    const uint32_t nsteps = (uint32_t)sh->nbits + 6u;
+    const uint32_t periods = vit_row_bytes(nsteps) >> 3;
+    const int nreg = sh->n_regions;
+    for (uint32_t p = threadIdx.x; p < periods; p += blockDim.x) {
+      const uint32_t t0 = p << 3;
+      uint64_t packed = 0;
+      if (t0 < nsteps) {
+        int r = 0;
+        while (r + 1 < nreg && (int)t0 >= sh->r[r + 1].step0) r++;
+        const uint32_t mask = sh->r[r].mask;
+        const uint32_t in = sj.in_bit0 + (uint32_t)sh->r[r].in0 +
+                            ((t0 - (uint32_t)sh->r[r].step0) >> 3) * (uint32_t)sh->r[r].ones;
+        const uint32_t wi = in >> 5;
+        // `ones` <= 32 consecutive channel bits starting at bit `in`
+        uint32_t x = wi < CIF_WORDS ? __funnelshift_r(lin[wi], lin[wi + 1], in & 31u) : 0u;
+        const int nst = min(8, (int)(nsteps - t0));
+        for (int k = 0; k < nst; k++) {
+          const uint32_t e = (mask >> (4 * k)) & 15u;  // kept symbols are always the first popc(e)
+          const uint32_t n = __popc(e);
+          packed |= (uint64_t)((x & e) | (e << 4)) << (8 * k);
+          x >>= n;
+        }
+      }
+      *reinterpret_cast<uint64_t *>(steps + sj.row_off + 8ull * p) = packed;
+    }
+  }
+}
+
+int launch_msc_gather(const uint8_t *d_cifs, const CifJob *d_jobs, const SubJob *d_subs,
+                      const ShapeDev *d_shapes, uint8_t *d_steps, int n_jobs, cudaStream_t st) {
+  if (n_jobs <= 0) return DABGPU_OK;
+  msc_gather_kernel<<<n_jobs, 256, 0, st>>>(d_cifs, d_jobs, d_subs, d_shapes, d_steps);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+__global__ void __launch_bounds__(256) deinterleave_bytes_kernel(const uint8_t *__restrict__ cifs,
+                                                                 const CifJob *__restrict__ jobs,
+                                                                 uint8_t *__restrict__ out) {
+  __shared__ uint32_t pl[16][CIF_PLANE_WORDS];
+  __shared__ uint32_t lin[CIF_WORDS + 1];
+  __shared__ CifJob job;
+  if (threadIdx.x < sizeof(CifJob) / 4)
+    reinterpret_cast<uint32_t *>(&job)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&jobs[blockIdx.x])[threadIdx.x];
+  __syncthreads();
+  deinterleave_to_smem(cifs, job, pl, lin);
+  uint8_t *dst = out + (size_t)blockIdx.x * DABGPU_CIF_BITS;
+  for (int i = threadIdx.x; i < DABGPU_CIF_BITS; i += blockDim.x) dst[i] = (lin[i >> 5] >> (i & 31)) & 1u;
+}
+
+int launch_deinterleave_bytes(const uint8_t *d_cifs, const CifJob *d_jobs, uint8_t *d_out, int n_jobs,
+                              cudaStream_t st) {
+  if (n_jobs <= 0) return DABGPU_OK;
+  deinterleave_bytes_kernel<<<n_jobs, 256, 0, st>>>(d_cifs, d_jobs, d_out);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// ---- demapped bytes -> planes -------------------------------------------------------------------
+__global__ void pack_planes_kernel(const uint8_t *__restrict__ msc, uint64_t tf_stride,
+                                   const uint64_t *__restrict__ dst_off, uint8_t *__restrict__ cifs, int n_tf) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;  // (tf, cif, word)
+  const uint64_t cif = idx / CIF_WORDS;
+  const int word = (int)(idx - cif * CIF_WORDS);
+  if (cif >= (uint64_t)n_tf * 4) return;
+  const int m = word / CIF_PLANE_WORDS, w = word - m * CIF_PLANE_WORDS;
+  const uint8_t *src = msc + (cif >> 2) * tf_stride + (cif & 3) * (uint64_t)DABGPU_CIF_BITS;
+  uint32_t v = 0;
+#pragma unroll 8
+  for (int b = 0; b < 32; b++) v |= (uint32_t)(src[16 * (32 * w + b) + m] & 1u) << b;
+  reinterpret_cast<uint32_t *>(cifs + dst_off[cif])[word] = v;
+}
+
+int launch_pack_planes(const uint8_t *d_msc_bytes, uint64_t tf_stride, const uint64_t *d_dst_off,
+                       uint8_t *d_cifs, int n_tf, cudaStream_t st) {
+  const uint64_t total = (uint64_t)n_tf * 4 * CIF_WORDS;
+  if (!total) return DABGPU_OK;
+  pack_planes_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_msc_bytes, tf_stride, d_dst_off,
+                                                                      d_cifs, n_tf);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// ---- ETI(NI) assembly: one warp per frame -----------------------------------------------------
+__device__ __forceinline__ uint32_t crc_byte(uint32_t crc, uint32_t byte) {
+  crc ^= byte << 8;
+#pragma unroll
+  for (int k = 0; k < 8; k++) crc = (crc & 0x8000u) ? ((crc << 1) ^ 0x1021u) & 0xffffu : (crc << 1) & 0xffffu;
+  return crc;
+}
+__device__ __forceinline__ uint32_t gf_mulmod(uint32_t a, uint32_t b) {
+  uint32_t r = 0;
+#pragma unroll
+  for (int i = 15; i >= 0; i--) {
+    r = (r & 0x8000u) ? ((r << 1) ^ 0x1021u) & 0xffffu : (r << 1) & 0xffffu;
+    if ((b >> i) & 1u) r ^= a;
+  }
+  return r;
+}
+// v * x^(8*nbytes) mod P
+__device__ __forceinline__ uint32_t crc_shift(uint32_t v, uint32_t nbytes) {
+  for (int j = 0; nbytes; j++, nbytes >>= 1)
+    if (nbytes & 1u) v = gf_mulmod(v, c_x8pow[j]);
+  return v;
+}
+// CRC-16-CCITT (init 0xffff, no final xor) of n bytes (n % 4 == 0, p 4-byte aligned) by one warp
+__device__ uint32_t warp_crc16(const uint8_t *p, uint32_t n, int lane) {
+  const uint32_t words = n >> 2;
+  const uint32_t per = (words + 31) / 32;
+  const uint32_t w0 = min(words, per * lane), w1 = min(words, per * (lane + 1));
+  uint32_t crc = 0;
+  const uint32_t *pw = reinterpret_cast<const uint32_t *>(p);
+  for (uint32_t w = w0; w < w1; w++) {
+    const uint32_t v = pw[w];
+    crc = crc_byte(crc, v & 0xffu);
+    crc = crc_byte(crc, (v >> 8) & 0xffu);
+    crc = crc_byte(crc, (v >> 16) & 0xffu);
+    crc = crc_byte(crc, v >> 24);
+  }
+  uint32_t part = crc_shift(crc, 4 * (words - w1));
+  if (lane == 0) part ^= crc_shift(0xffffu, n);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) part ^= __shfl_xor_sync(0xffffffffu, part, o);
+  return part;
+}
+
+__global__ void __launch_bounds__(128) eti_pack_kernel(const EtiJob *__restrict__ jobs,
+                                                       const EnsDev *__restrict__ ens,
+                                                       const uint8_t *__restrict__ fibs,
+                                                       uint8_t *__restrict__ eti_all, int n_frames) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= n_frames) return;
+  const EtiJob job = jobs[f];
+  const EnsDev *en = &ens[job.ens];
+  uint8_t *eti = eti_all + (size_t)f * DABGPU_ETI_BYTES;
+  const uint32_t nst = en->nst, fl = en->fl;
+  // SYNC + FC (misc.c:158-183)
+  if (lane == 0) {
+    const bool odd = job.cif_lo & 1;
+    eti[0] = 0xff;
+    eti[1] = odd ? 0xf8 : 0x07;
+    eti[2] = odd ? 0xc5 : 0x3a;
+    eti[3] = odd ? 0x49 : 0xb6;
+    eti[4] = job.cif_lo;
+    eti[5] = (uint8_t)(0x80u | nst);
+    const uint32_t fp = (job.cif_hi * 250u + job.cif_lo) & 7u;
+    eti[6] = (uint8_t)((fp << 5) | (1u << 3) | ((fl >> 8) & 7u));
+    eti[7] = (uint8_t)(fl & 0xffu);
+  }
+  // STC (misc.c:185-202)
+  for (uint32_t j = lane; j < nst; j += 32)
+    *reinterpret_cast<uint32_t *>(eti + 8 + 4 * j) = *reinterpret_cast<const uint32_t *>(en->stc[j]);
+  __syncwarp();
+  const uint32_t eoh = 8 + 4 * nst;
+  // EOH: MNSC + HCRC over eti[4 .. eoh+2) (misc.c:203-211)
+  if (lane == 0) {
+    eti[eoh] = 0xff;
+    eti[eoh + 1] = 0xff;
+    uint32_t crc = 0xffffu;
+    for (uint32_t i = 4; i < eoh + 2; i++) crc = crc_byte(crc, eti[i]);
+    crc = ~crc & 0xffffu;
+    eti[eoh + 2] = (uint8_t)(crc >> 8);
+    eti[eoh + 3] = (uint8_t)(crc & 0xffu);
+  }
+  const uint32_t e1 = eoh + 4;
+  // FIC of the oldest CIF (misc.c:239)
+  if (lane < 24)
+    *reinterpret_cast<uint32_t *>(eti + e1 + 4 * lane) = *reinterpret_cast<const uint32_t *>(fibs + job.fib_off + 4 * lane);
+  __syncwarp();
+  // EOF: CRC over MST = FIC + sub-channel payload (misc.c:280-296)
+  const uint32_t mst = 96 + en->payload;
+  uint32_t crc = ~warp_crc16(eti + e1, mst, lane) & 0xffffu;
+  uint32_t e = e1 + mst;
+  if (lane == 0) {
+    eti[e] = (uint8_t)(crc >> 8);
+    eti[e + 1] = (uint8_t)(crc & 0xffu);
+    eti[e + 2] = 0xff;  // RFU
+    eti[e + 3] = 0xff;
+    *reinterpret_cast<uint32_t *>(eti + e + 4) = 0xffffffffu;  // TIST unused
+  }
+  e += 8;
+  for (uint32_t i = e + 4 * lane; i < DABGPU_ETI_BYTES; i += 128) *reinterpret_cast<uint32_t *>(eti + i) = 0x55555555u;
+}
+
+int launch_eti_pack(const EtiJob *d_jobs, const EnsDev *d_ens, const uint8_t *d_fibs, uint8_t *d_eti,
+                    int n_frames, cudaStream_t st) {
+  if (n_frames <= 0) return DABGPU_OK;
+  eti_pack_kernel<<<(n_frames + 3) / 4, 128, 0, st>>>(d_jobs, d_ens, d_fibs, d_eti, n_frames);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+}  // namespace dabgpu

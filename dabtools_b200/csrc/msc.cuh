@@ -1,0 +1,57 @@
+// msc.cuh -- MSC side of the back-end: CIF storage, time de-interleave + depuncture
+// gather (feeds the Viterbi kernel) and ETI(NI) frame assembly.
+//
+// Device format of one received CIF ("planes"): the 55296 channel bits are kept packed
+// and split by i mod 16, because the time de-interleaver (misc.c:29-39) takes bit i of
+// the logical frame from window slot map[i & 15]: plane m holds bits i = 16q + m,
+// q = 0..3455, bit q at word q>>5, bit q&31 (LSB first).  A CIF is 16 planes x 108
+// words = 6912 bytes, and de-interleaving one logical frame is 16 contiguous 432-byte
+// reads, one plane from each of the 16 window slots.
+#pragma once
+#include "viterbi.cuh"
+
+namespace dabgpu {
+
+enum { CIF_PLANE_WORDS = 108, CIF_WORDS = 16 * 108, CIF_BYTES = 6912 };
+
+// one logical (output) CIF to de-interleave and turn into Viterbi step bytes
+struct CifJob {
+  uint64_t slot_off[16];  // byte offsets of the 16 window CIFs (slot 0 = oldest) in the CIF store
+  uint32_t sub0, nsub;    // range in the SubJob array
+};
+struct SubJob {
+  uint64_t row_off;   // step-byte row of this codeword (16-byte aligned)
+  uint32_t in_bit0;   // first channel bit of the sub-channel inside the CIF (start_cu * 64)
+  uint32_t shape;     // index into the ShapeDev table
+};
+
+int launch_msc_gather(const uint8_t *d_cifs, const CifJob *d_jobs, const SubJob *d_subs,
+                      const ShapeDev *d_shapes, uint8_t *d_steps, int n_jobs, cudaStream_t st);
+
+// 1 byte/bit demapped MSC (72 x 3072 per TF, the reference's msc_symbols_demapped) ->
+// 4 CIF plane buffers; dst_off[4*i + c] = byte offset of CIF c of TF i in the CIF store
+int launch_pack_planes(const uint8_t *d_msc_bytes, uint64_t tf_stride, const uint64_t *d_dst_off,
+                       uint8_t *d_cifs, int n_tf, cudaStream_t st);
+// inverse of the gather's first half, for the time_deinterleave() drop-in and tests:
+// 16 window CIFs (planes) -> 55296 bytes of 0/1 in logical order
+int launch_deinterleave_bytes(const uint8_t *d_cifs, const CifJob *d_jobs, uint8_t *d_out, int n_jobs,
+                              cudaStream_t st);
+
+// ---- ETI assembly (misc.c:153-314) -------------------------------------------------------
+struct EnsDev {          // per stream, changes only when the multiplex description changes
+  uint32_t nst;          // number of sub-channels
+  uint32_t fl;           // FL field (words)
+  uint32_t payload;      // sum of sub-channel bytes in the MST
+  uint32_t pad;
+  uint8_t stc[64][4];    // STC words in SubChId order, as they appear in the frame
+};
+struct EtiJob {
+  uint64_t fib_off;      // byte offset of the 96 FIB bytes of the oldest CIF in the FIB store
+  uint32_t ens;          // index into EnsDev array (stream)
+  uint8_t cif_hi, cif_lo, pad[2];
+};
+// frame f is written to d_eti + 6144*f; the sub-channel payload must already be in place
+int launch_eti_pack(const EtiJob *d_jobs, const EnsDev *d_ens, const uint8_t *d_fibs, uint8_t *d_eti,
+                    int n_frames, cudaStream_t st);
+
+}  // namespace dabgpu

@@ -1,0 +1,792 @@
+// ofdm.cu -- RTL-SDR front-end kernels (see ofdm.cuh).
+//
+//  ingest_kernel     rtlsdr_callback + cbWrite loop  (dab2eti.c:125, input_sdr.c:36-38), with the
+//                    virtual tuner (the reference retunes hardware, dab2eti.c:75-103)
+//  fifo_read_kernel  sdr_read_fifo                   (sdr_fifo.c:43-61)
+//  sync_kernel       dab_coarse_time_sync, dab_fine_time_sync, dab_coarse_freq_sync_2,
+//                    dab_fine_freq_corr              (sdr_sync.c:34-302, input_sdr.c:60-112)
+//  demod_kernel      76 x FFT2048 + DQPSK + frequency de-interleave + hard slicing
+//                                                    (input_sdr.c:114-162)
+//
+// The demodulator never materialises a spectrum in memory: each CTA walks the symbols of one CIF
+// (or of the FIC), keeps the previous symbol's bins in registers, and only the sliced bits leave
+// the SM -- FIC as the reference's byte-per-bit array, MSC as packed planes (msc.cuh).
+#include "ofdm.cuh"
+
+#include "msc.cuh"
+
+namespace dabgpu {
+
+// ---- constant tables ---------------------------------------------------------------------------
+__device__ float2 g_tw2048[2048];    // exp(-2*pi*i*k/2048)
+__device__ uint16_t g_bin_dst[2048]; // FFT bin -> n = rev_freq_deint_tab[c] (0xffff: unused bin)
+__device__ uint8_t g_prs_q[1536];    // phase reference symbol, quarter turns, by carrier index c
+
+int ofdm_init_constants() {
+  static float2 tw[2048];
+  for (int k = 0; k < 2048; k++) {
+    const double a = -2.0 * M_PI * (double)k / 2048.0;
+    tw[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(g_tw2048, tw, sizeof tw));
+  uint16_t rev[1536];
+  static uint16_t dst[2048];
+  dabgpu_build_freq_deint(rev);
+  for (int b = 0; b < 2048; b++) {
+    // fftshifted index i = (b + 1024) % 2048 runs 256..1792 over the carriers, 1024 = DC
+    // (input_sdr.c:152-158); carrier index c counts them in that order
+    const int i = (b + 1024) & 2047;
+    if (i < 256 || i > 1792 || i == 1024)
+      dst[b] = 0xffff;
+    else
+      dst[b] = rev[i < 1024 ? i - 256 : i - 257];
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(g_bin_dst, dst, sizeof dst));
+  uint8_t q[1536];
+  dabgpu_build_prs(q);
+  CUDA_TRY(cudaMemcpyToSymbol(g_prs_q, q, sizeof q));
+  return DABGPU_OK;
+}
+
+// uint8 sample -> the reference's int8 (input_sdr.c:61-62: buffer-127 stored in int8_t, 255 -> -128)
+__device__ __forceinline__ float u8_to_sample(uint32_t b) {
+  int v = (int)b - 127;
+  return (float)(v == 128 ? -128 : v);
+}
+
+// =================================================================================================
+// ingest
+// =================================================================================================
+__global__ void __launch_bounds__(256) ingest_kernel(const uint8_t *__restrict__ src, uint64_t pitch,
+                                                     uint32_t chunk_len, uint8_t *__restrict__ ring,
+                                                     const StepCtl *__restrict__ ctl) {
+  const int s = blockIdx.y;
+  const StepCtl *c = &ctl[s];
+  const uint32_t vec = blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte vector index
+  if (vec * 16u >= chunk_len) return;
+  uint4 v = *reinterpret_cast<const uint4 *>(src + (uint64_t)s * pitch + 16ull * vec);
+  const int32_t df = c->nco_hz;
+  if (df != 0) {
+    // virtual tuner: multiply by exp(-j*2*pi*df*n/fs) and re-quantise, as the oracle harness does
+    const int64_t M = 2048000;
+    const int64_t a = ((int64_t)df % M + M) % M;
+    uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 8; k++) {
+      const uint64_t n = c->nco_sample0 + 8ull * vec + k;
+      const int64_t r = (int64_t)(((uint64_t)a * (n % (uint64_t)M)) % (uint64_t)M);
+      float sn, cs;
+      sincospif(-2.0f * ((float)r / 2048000.0f), &sn, &cs);
+      const uint32_t pair = (w[k >> 1] >> (16 * (k & 1))) & 0xffffu;
+      const float xr = (float)(int)(pair & 0xffu) - 127.0f, xi = (float)(int)(pair >> 8) - 127.0f;
+      const float yr = floorf(xr * cs - xi * sn + 0.5f) + 127.0f, yi = floorf(xr * sn + xi * cs + 0.5f) + 127.0f;
+      const uint32_t qr = (uint32_t)fminf(fmaxf(yr, 0.0f), 255.0f), qi = (uint32_t)fminf(fmaxf(yi, 0.0f), 255.0f);
+      const uint32_t np = qr | (qi << 8);
+      w[k >> 1] = (w[k >> 1] & ~(0xffffu << (16 * (k & 1)))) | (np << (16 * (k & 1)));
+    }
+    v = make_uint4(w[0], w[1], w[2], w[3]);
+  }
+  const uint32_t pos = (c->wr_pos + 16u * vec) % IQ_RING_BYTES;
+  *reinterpret_cast<uint4 *>(ring + (uint64_t)s * IQ_RING_BYTES + pos) = v;
+}
+
+int launch_ingest(const uint8_t *d_src, uint64_t src_pitch, uint32_t chunk_len, uint8_t *d_ring,
+                  const StepCtl *d_ctl, int n_streams, cudaStream_t st) {
+  if (n_streams <= 0 || !chunk_len) return DABGPU_OK;
+  if ((src_pitch & 15) || ((uintptr_t)d_src & 15)) {
+    set_error(DABGPU_ERR_ARG, "ingest: device IQ buffer and pitch must be 16-byte aligned");
+    return DABGPU_ERR_ARG;
+  }
+  dim3 grid((chunk_len / 16 + 255) / 256, n_streams);
+  ingest_kernel<<<grid, 256, 0, st>>>(d_src, src_pitch, chunk_len, d_ring, d_ctl);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// =================================================================================================
+// FIFO read into the persistent per-stream frame buffer
+// =================================================================================================
+__global__ void __launch_bounds__(256) fifo_read_kernel(const uint8_t *__restrict__ ring,
+                                                        uint8_t *__restrict__ frames,
+                                                        const StepCtl *__restrict__ ctl) {
+  const int s = blockIdx.y;
+  const StepCtl *c = &ctl[s];
+  const uint8_t *rs = ring + (uint64_t)s * IQ_RING_BYTES;
+  uint8_t *fs = frames + (uint64_t)s * DABGPU_TF_BYTES;
+  const uint32_t vec = blockIdx.x * blockDim.x + threadIdx.x;
+  // segment 0 always lands at offset 0: 16 destination bytes per thread from an even, possibly
+  // unaligned ring position (all shifts are even byte counts)
+  const uint32_t n0 = c->rd_bytes[0];
+  if (16u * vec < n0) {
+    const uint32_t p = c->rd_pos[0] + 16u * vec;
+    const uint32_t sh = (p & 3u) * 8u;
+    uint32_t w[5];
+#pragma unroll
+    for (int k = 0; k < 5; k++) w[k] = *reinterpret_cast<const uint32_t *>(rs + (((p & ~3u) + 4u * k) % IQ_RING_BYTES));
+    uint32_t o[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(w[k], w[k + 1], sh);
+    if (16u * vec + 16u <= n0) {
+      *reinterpret_cast<uint4 *>(fs + 16u * vec) = make_uint4(o[0], o[1], o[2], o[3]);
+    } else {
+      for (uint32_t b = 0; 16u * vec + b < n0; b++) fs[16u * vec + b] = (uint8_t)(o[b >> 2] >> (8 * (b & 3)));
+    }
+  }
+  // segment 1 (rare: FIFO ran dry during a large positive shift): plain byte copy
+  const uint32_t n1 = c->rd_bytes[1];
+  for (uint32_t b = 16u * vec; b < min(n1, 16u * vec + 16u); b++)
+    fs[c->rd_dst[1] + b] = rs[(c->rd_pos[1] + b) % IQ_RING_BYTES];
+}
+
+int launch_fifo_read(const uint8_t *d_ring, uint8_t *d_frames, const StepCtl *d_ctl, int n_streams,
+                     cudaStream_t st) {
+  if (n_streams <= 0) return DABGPU_OK;
+  dim3 grid(DABGPU_TF_BYTES / 16 / 256, n_streams);
+  fifo_read_kernel<<<grid, 256, 0, st>>>(d_ring, d_frames, d_ctl);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// =================================================================================================
+// complex helpers and in-register DFTs
+// =================================================================================================
+__device__ __forceinline__ float2 cadd(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+__device__ __forceinline__ float2 csub(float2 a, float2 b) { return make_float2(a.x - b.x, a.y - b.y); }
+__device__ __forceinline__ float2 cmul(float2 a, float2 b) {
+  return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__device__ __forceinline__ float2 cmulc(float2 a, float2 b) {  // a * conj(b)
+  return make_float2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+// multiply by -i (forward) : (x,y) -> (y,-x)
+__device__ __forceinline__ float2 mul_mi(float2 a) { return make_float2(a.y, -a.x); }
+
+// forward 4-point DFT in place: v[k] = sum_j v[j] * exp(-2*pi*i*j*k/4)
+__device__ __forceinline__ void dft4(float2 &a, float2 &b, float2 &c, float2 &d) {
+  const float2 s0 = cadd(a, c), s1 = csub(a, c), s2 = cadd(b, d), s3 = mul_mi(csub(b, d));
+  a = cadd(s0, s2);
+  c = csub(s0, s2);
+  b = cadd(s1, s3);
+  d = csub(s1, s3);
+}
+
+// forward 8-point DFT: in natural order, out natural order
+__device__ __forceinline__ void dft8(float2 *v) {
+  const float h = 0.70710678118654752f;
+  // decimation in time: evens (0,2,4,6) and odds (1,3,5,7)
+  float2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  float2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  dft4(e0, e1, e2, e3);
+  dft4(o0, o1, o2, o3);
+  // twiddles W8^k: 1, (1-i)/sqrt2, -i, (-1-i)/sqrt2
+  o1 = make_float2(h * (o1.x + o1.y), h * (o1.y - o1.x));
+  o2 = mul_mi(o2);
+  o3 = make_float2(h * (o3.y - o3.x), -h * (o3.x + o3.y));
+  v[0] = cadd(e0, o0);
+  v[4] = csub(e0, o0);
+  v[1] = cadd(e1, o1);
+  v[5] = csub(e1, o1);
+  v[2] = cadd(e2, o2);
+  v[6] = csub(e2, o2);
+  v[3] = cadd(e3, o3);
+  v[7] = csub(e3, o3);
+}
+
+// forward 16-point DFT, natural order in and out (4 x 4 decomposition)
+__device__ __forceinline__ void dft16(float2 *v) {
+  const float h = 0.70710678118654752f, c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
+  // columns: n = 4*a + b -> first DFT4 over a for each b
+  float2 x[4][4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    x[b][0] = v[b];
+    x[b][1] = v[4 + b];
+    x[b][2] = v[8 + b];
+    x[b][3] = v[12 + b];
+    dft4(x[b][0], x[b][1], x[b][2], x[b][3]);  // x[b][p], p = output index of the a-DFT
+  }
+  // twiddle W16^(b*p)
+  // b=1: p=1: W^1, p=2: W^2, p=3: W^3 ; b=2: W^2, W^4, W^6 ; b=3: W^3, W^6, W^9
+  const float2 W1 = make_float2(c1, -s1), W2 = make_float2(h, -h), W3 = make_float2(s1, -c1);
+  const float2 W6 = make_float2(-h, -h), W9 = make_float2(-c1, s1);
+  x[1][1] = cmul(x[1][1], W1);
+  x[1][2] = cmul(x[1][2], W2);
+  x[1][3] = cmul(x[1][3], W3);
+  x[2][1] = cmul(x[2][1], W2);
+  x[2][2] = mul_mi(x[2][2]);
+  x[2][3] = cmul(x[2][3], W6);
+  x[3][1] = cmul(x[3][1], W3);
+  x[3][2] = cmul(x[3][2], W6);
+  x[3][3] = cmul(x[3][3], W9);
+  // second DFT4 over b for each p: output k = p + 4*q
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    dft4(x[0][p], x[1][p], x[2][p], x[3][p]);
+    v[p] = x[0][p];
+    v[p + 4] = x[1][p];
+    v[p + 8] = x[2][p];
+    v[p + 12] = x[3][p];
+  }
+}
+
+// =================================================================================================
+// 2048-point forward FFT by 128 threads: 16 x 16 x 8, decimation in frequency.
+//   stage 1: thread t: DFT16 over x[t + 128 j]            -> k1, twiddle W2048^(t k1)
+//   stage 2: thread (u = p>>4, k1 = p&15): DFT16 over j2 of z_k1[u + 8 j2] -> k2, twiddle W128^(u k2)
+//   stage 3: thread p: two DFT8 over u for q = p and p+128 (q = 16 k2 + k1)  -> k3
+// result: thread p holds bins p + 128 m, m = 0..15  (m = 2 k3 for q = p, 2 k3 + 1 for q = p + 128)
+// `xch` is a 2080-element float2 exchange buffer.
+// =================================================================================================
+enum { FFT_THREADS = 128, XCH_ELEMS = 16 * 130 };
+
+struct FftTwiddles {  // per-thread twiddles, constant over symbols
+  float2 s1[15];      // W2048^(t*k1), k1 = 1..15
+  float2 s2[15];      // W128^(u*k2),  k2 = 1..15
+};
+__device__ __forceinline__ void load_twiddles(FftTwiddles &tw, int p) {
+  const int t = p, u = p >> 4;
+#pragma unroll
+  for (int k = 1; k < 16; k++) {
+    tw.s1[k - 1] = g_tw2048[(t * k) & 2047];
+    tw.s2[k - 1] = g_tw2048[(16 * u * k) & 2047];
+  }
+}
+
+__device__ __forceinline__ void fft2048_from_regs(float2 *v, const FftTwiddles &tw, float2 *xch, int p) {
+  // stage 1 (v = x[p + 128 j])
+  dft16(v);
+#pragma unroll
+  for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw.s1[k - 1]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) xch[k * 130 + p] = v[k];
+  __syncthreads();
+  const int u = p >> 4, k1 = p & 15;
+#pragma unroll
+  for (int j = 0; j < 16; j++) v[j] = xch[k1 * 130 + u + 8 * j];
+  __syncthreads();
+  // stage 2
+  dft16(v);
+#pragma unroll
+  for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw.s2[k - 1]);
+#pragma unroll
+  for (int k = 0; k < 16; k++) xch[u * 256 + k * 16 + k1] = v[k];
+  __syncthreads();
+  // stage 3
+  float2 a[8], b[8];
+#pragma unroll
+  for (int uu = 0; uu < 8; uu++) {
+    a[uu] = xch[uu * 256 + p];
+    b[uu] = xch[uu * 256 + p + 128];
+  }
+  __syncthreads();
+  dft8(a);
+  dft8(b);
+#pragma unroll
+  for (int k3 = 0; k3 < 8; k3++) {
+    v[2 * k3] = a[k3];
+    v[2 * k3 + 1] = b[k3];
+  }
+}
+
+// load the 16 samples x[p + 128 j] of one symbol from a byte buffer (I,Q uint8 pairs)
+__device__ __forceinline__ void load_symbol(float2 *v, const uint8_t *sym, int p) {
+  const uint16_t *h = reinterpret_cast<const uint16_t *>(sym);
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const uint32_t w = h[p + 128 * j];
+    v[j] = make_float2(u8_to_sample(w & 0xffu), u8_to_sample(w >> 8));
+  }
+}
+
+// =================================================================================================
+// demodulator
+// =================================================================================================
+// TMA (1-D bulk copy) + mbarrier plumbing
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "bra WAIT_%=;\n\t"
+      "DONE_%=:\n\t}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+          smem_u32(dst_smem)),
+      "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+enum { SYM_BYTES = 4096, N_STAGES = 3 };
+
+struct DemodSmem {
+  float2 xch[XCH_ELEMS];                       // 16640 B
+  __align__(16) uint8_t stage[N_STAGES][SYM_BYTES];
+  uint8_t bits[3072];                          // one symbol's sliced bits, one per byte
+  uint32_t planes[16][CIF_PLANE_WORDS];        // the CIF being assembled
+  uint64_t full[N_STAGES];
+};
+
+// symbol l of a frame starts (useful part) at this byte offset (input_sdr.c:116)
+__device__ __forceinline__ uint32_t sym_byte_off(int l) { return 2u * (2656u + 2552u * (uint32_t)l + 504u); }
+
+template <bool DEBUG>
+__global__ void __launch_bounds__(FFT_THREADS) demod_kernel(const uint8_t *__restrict__ frames,
+                                                            const StepCtl *__restrict__ ctl,
+                                                            const SyncOut *__restrict__ sync,
+                                                            uint8_t *__restrict__ fic_bits,
+                                                            uint8_t *__restrict__ cifs,
+                                                            float2 *__restrict__ dbg_sym,
+                                                            float2 *__restrict__ dbg_symd,
+                                                            uint8_t *__restrict__ dbg_bits) {
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  DemodSmem &sm = *reinterpret_cast<DemodSmem *>(smem_raw);
+  const int p = threadIdx.x;
+  const int s = blockIdx.y, seg = blockIdx.x;  // seg 0: PRS + FIC symbols, seg 1..4: CIF seg-1
+  if (!DEBUG) {
+    if (!ctl[s].run || sync[s].ok != 1) return;
+  }
+  const uint8_t *frame = frames + (uint64_t)s * DABGPU_TF_BYTES;
+  const int l0 = seg == 0 ? 0 : 3 + 18 * (seg - 1);
+  const int nsym = seg == 0 ? 4 : 19;
+
+  if (p == 0) {
+    for (int i = 0; i < N_STAGES; i++) mbar_init(&sm.full[i], 1);
+    fence_barrier_init();
+  }
+  __syncthreads();
+  if (p == 0) {
+    for (int i = 0; i < N_STAGES && i < nsym; i++) {
+      mbar_expect_tx(&sm.full[i], SYM_BYTES);
+      tma_load_1d(sm.stage[i], frame + sym_byte_off(l0 + i), SYM_BYTES, &sm.full[i]);
+    }
+  }
+  FftTwiddles tw;
+  load_twiddles(tw, p);
+  // destination of this thread's bins p + 128 m (constant over symbols)
+  uint16_t dst[16];
+#pragma unroll
+  for (int m = 0; m < 16; m++) dst[m] = g_bin_dst[p + 128 * m];
+
+  float2 prev[16];
+#pragma unroll
+  for (int m = 0; m < 16; m++) prev[m] = make_float2(0.f, 0.f);
+
+  for (int i = 0; i < nsym; i++) {
+    const int l = l0 + i, st = i % N_STAGES;
+    float2 v[16];
+    mbar_wait(&sm.full[st], (uint32_t)(i / N_STAGES) & 1u);
+    load_symbol(v, sm.stage[st], p);
+    __syncthreads();  // everyone has consumed the staging buffer -> refill it
+    if (p == 0 && i + N_STAGES < nsym) {
+      fence_proxy_async();
+      mbar_expect_tx(&sm.full[st], SYM_BYTES);
+      tma_load_1d(sm.stage[st], frame + sym_byte_off(l + N_STAGES), SYM_BYTES, &sm.full[st]);
+    }
+    fft2048_from_regs(v, tw, sm.xch, p);
+    if (DEBUG) {
+#pragma unroll
+      for (int m = 0; m < 16; m++) dbg_sym[(size_t)l * 2048 + ((p + 128 * m + 1024) & 2047)] = v[m];
+    }
+    if (i > 0) {
+      // DQPSK against the previous symbol and hard slicing (input_sdr.c:132-158):
+      //   re = Re(s_l conj(s_l-1)) / |s_l-1|^2 ,  im' = -Im(s_l conj(s_l-1)) / |s_l-1|^2
+      //   bit0 = !(re > 0) ; bit1 = (im' > 0)      (division by a positive number dropped)
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const float re = v[m].x * prev[m].x + v[m].y * prev[m].y;
+        const float imn = v[m].x * prev[m].y - v[m].y * prev[m].x;
+        if (DEBUG) {
+          const float den = prev[m].x * prev[m].x + prev[m].y * prev[m].y;
+          dbg_symd[(size_t)l * 2048 + ((p + 128 * m + 1024) & 2047)] = make_float2(re / den, imn / den);
+        }
+        const uint32_t n = dst[m];
+        if (n != 0xffffu) {
+          const uint8_t b0 = re > 0.f ? 0 : 1, b1 = imn > 0.f ? 1 : 0;
+          if (seg == 0 || DEBUG) {
+            sm.bits[n] = b0;
+            sm.bits[1536 + n] = b1;
+          } else {
+            const uint32_t idx = (n & 15u) * 192u + (n >> 4);
+            sm.bits[idx] = b0;
+            sm.bits[idx + 96] = b1;
+          }
+        }
+      }
+      __syncthreads();
+      if (DEBUG) {
+        for (int k = p; k < 3072 / 4; k += FFT_THREADS)
+          reinterpret_cast<uint32_t *>(dbg_bits + (size_t)(l - 1) * 3072)[k] = reinterpret_cast<uint32_t *>(sm.bits)[k];
+      } else if (seg == 0) {
+        uint32_t *o = reinterpret_cast<uint32_t *>(fic_bits + (uint64_t)s * 9216 + (size_t)(l - 1) * 3072);
+        for (int k = p; k < 3072 / 4; k += FFT_THREADS) o[k] = reinterpret_cast<uint32_t *>(sm.bits)[k];
+      } else if (p < 96) {
+        // 32 byte-bits -> one plane word; plane m = p / 6, word w = p % 6 of this symbol's 192 bits
+        const uint32_t *b = reinterpret_cast<const uint32_t *>(sm.bits + 32 * p);
+        uint32_t word = 0;
+#pragma unroll
+        for (int k = 0; k < 8; k++) word |= ((b[k] * 0x01020408u) >> 24) << (4 * k);
+        sm.planes[p / 6][(i - 1) * 6 + p % 6] = word;
+      }
+      // the next symbol's slicing must not overwrite sm.bits before it has been read: the
+      // three barriers inside fft2048_from_regs of the next iteration order that
+    }
+#pragma unroll
+    for (int m = 0; m < 16; m++) prev[m] = v[m];
+  }
+  if (!DEBUG && seg > 0) {
+    __syncthreads();
+    uint32_t *o = reinterpret_cast<uint32_t *>(cifs + ctl[s].cif_off[seg - 1]);
+    const uint32_t *src = &sm.planes[0][0];
+    for (int k = p; k < CIF_WORDS; k += FFT_THREADS) o[k] = src[k];
+  }
+}
+
+int launch_demod(const uint8_t *d_frames, const StepCtl *d_ctl, const SyncOut *d_sync, uint8_t *d_fic_bits,
+                 uint8_t *d_cifs, int n_streams, cudaStream_t st) {
+  if (n_streams <= 0) return DABGPU_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(demod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(DemodSmem)));
+    attr_set = true;
+  }
+  dim3 grid(5, n_streams);
+  demod_kernel<false><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_frames, d_ctl, d_sync, d_fic_bits, d_cifs,
+                                                                   nullptr, nullptr, nullptr);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+int launch_demod_debug(const uint8_t *d_frame, float2 *d_symbols, float2 *d_symbols_d, uint8_t *d_bits,
+                       cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(demod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(DemodSmem)));
+    attr_set = true;
+  }
+  // one "segment" walking all 76 symbols is what the debug variant needs: reuse seg 0 semantics
+  // by launching the five segments; each writes its own rows
+  dim3 grid(5, 1);
+  demod_kernel<true><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_frame, nullptr, nullptr, nullptr, nullptr,
+                                                                  d_symbols, d_symbols_d, d_bits);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// =================================================================================================
+// synchronisers: one CTA of 128 threads per stream
+// =================================================================================================
+// generic in-place radix-2 FFT of n = 2^logn points in shared memory by the whole CTA;
+// sign = -1 forward, +1 backward; unnormalised
+__device__ void block_fft_pow2(float2 *d, int logn, int sign) {
+  const int n = 1 << logn;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int j = (int)(__brev((unsigned)i) >> (32 - logn));
+    if (i < j) {
+      const float2 t = d[i];
+      d[i] = d[j];
+      d[j] = t;
+    }
+  }
+  __syncthreads();
+  for (int len = 2; len <= n; len <<= 1) {
+    const int half = len >> 1;
+    for (int b = threadIdx.x; b < n / 2; b += blockDim.x) {
+      const int k = b & (half - 1);
+      const int i0 = ((b - k) << 1) + k, i1 = i0 + half;
+      float2 w = g_tw2048[(k * (2048 / len)) & 2047];
+      if (sign > 0) w.y = -w.y;
+      const float2 x = d[i0], y = cmul(d[i1], w);
+      d[i0] = cadd(x, y);
+      d[i1] = csub(x, y);
+    }
+    __syncthreads();
+  }
+}
+
+struct SyncSmem {
+  float2 xch[XCH_ELEMS];
+  float2 spec[2048];   // FFT output in natural bin order
+  float2 work[1536];   // correlation buffers
+  float red_v[FFT_THREADS];
+  int red_i[FFT_THREADS];
+};
+
+__device__ __forceinline__ float2 prs_value(int c) {
+  const int q = g_prs_q[c];
+  return make_float2(q == 0 ? 1.f : q == 2 ? -1.f : 0.f, q == 1 ? 1.f : q == 3 ? -1.f : 0.f);
+}
+
+// sample sources: the uint8 frame buffer (batched path, sdr_demod) or caller-provided arrays
+// (the reference-signature entry points of sdr_sync.h)
+struct SrcU8 {
+  const uint8_t *f;
+  __device__ __forceinline__ float real(int n) const { return u8_to_sample(f[2 * n]); }
+  __device__ __forceinline__ float2 at(int n) const {
+    const uint32_t w = reinterpret_cast<const uint16_t *>(f)[n];
+    return make_float2(u8_to_sample(w & 0xffu), u8_to_sample(w >> 8));
+  }
+};
+struct SrcI8 {
+  const int8_t *r;
+  __device__ __forceinline__ float real(int n) const { return (float)r[n]; }
+  __device__ __forceinline__ float2 at(int) const { return make_float2(0.f, 0.f); }
+};
+struct SrcF2 {
+  const float2 *f;
+  __device__ __forceinline__ float real(int n) const { return f[n].x; }
+  __device__ __forceinline__ float2 at(int n) const { return f[n]; }
+};
+
+__device__ float block_sum(SyncSmem &sm, float v) {
+  const int p = threadIdx.x;
+  sm.red_v[p] = v;
+  __syncthreads();
+  for (int o = FFT_THREADS / 2; o; o >>= 1) {
+    if (p < o) sm.red_v[p] += sm.red_v[p + o];
+    __syncthreads();
+  }
+  const float r = sm.red_v[0];
+  __syncthreads();
+  return r;
+}
+
+// block-wide arg-extremum with lowest-index tie-break; is_max selects max or min
+__device__ void block_arg_reduce(SyncSmem &sm, float v, int idx, bool is_max, float *out_v, int *out_i) {
+  sm.red_v[threadIdx.x] = v;
+  sm.red_i[threadIdx.x] = idx;
+  __syncthreads();
+  for (int o = FFT_THREADS / 2; o; o >>= 1) {
+    if ((int)threadIdx.x < o) {
+      const float a = sm.red_v[threadIdx.x], b = sm.red_v[threadIdx.x + o];
+      const int ia = sm.red_i[threadIdx.x], ib = sm.red_i[threadIdx.x + o];
+      const bool take_b = is_max ? (b > a || (b == a && ib < ia)) : (b < a || (b == a && ib < ia));
+      if (take_b) {
+        sm.red_v[threadIdx.x] = b;
+        sm.red_i[threadIdx.x] = ib;
+      }
+    }
+    __syncthreads();
+  }
+  *out_v = sm.red_v[0];
+  *out_i = sm.red_i[0];
+  __syncthreads();
+}
+
+// sdr_sync.c:34-68: null-symbol energy gate; on a miss the first minimum of a 266-tap sliding
+// sum over |real[10 n]| locates the null symbol.  Returns the shift in bytes.
+template <typename Src>
+__device__ int coarse_time_sync(SyncSmem &sm, const Src &src, bool force, float *energy) {
+  const int p = threadIdx.x;
+  float e = 0.f;
+  for (int k = p; k < 266; k += FFT_THREADS) e += fabsf(src.real(10 * k));
+  const float ev = block_sum(sm, e);  // small integers: exact in float in any order
+  *energy = ev;
+  if (ev < 5000.f && !force) return 0;
+  const int nwin = (196608 - 2656) / 10;  // the reference searches 19395 windows
+  const int per = (nwin + FFT_THREADS - 1) / FFT_THREADS;
+  const int w0 = p * per, w1 = min(nwin, w0 + per);
+  float best = 9999999.f;
+  int best_w = 0x7fffffff;
+  if (w0 < w1) {
+    float sum = 0.f;
+    for (int j = 0; j < 266; j++) sum += fabsf(src.real(10 * (w0 + j)));
+    for (int w = w0; w < w1; w++) {
+      if (sum < best) {
+        best = sum;
+        best_w = w;
+      }
+      sum += fabsf(src.real(10 * (w + 266))) - fabsf(src.real(10 * w));
+    }
+  }
+  float bv;
+  int bi;
+  block_arg_reduce(sm, best, best_w, false, &bv, &bi);
+  return bv < 9999999.f ? 20 * bi : 0;
+}
+
+// FFT of the 2048 samples starting at `start` into sm.spec (natural bin order)
+template <typename Src>
+__device__ void fft_window(SyncSmem &sm, const Src &src, int start, const FftTwiddles &tw) {
+  const int p = threadIdx.x;
+  float2 v[16];
+#pragma unroll
+  for (int j = 0; j < 16; j++) v[j] = src.at(start + p + 128 * j);
+  fft2048_from_regs(v, tw, sm.xch, p);
+#pragma unroll
+  for (int m = 0; m < 16; m++) sm.spec[p + 128 * m] = v[m];
+  __syncthreads();
+}
+
+// sdr_sync.c:71-202 on the PRS spectrum in sm.spec: correlate 1536 carriers with conj(PRS),
+// 1536-point inverse DFT (3 x 512 + radix-3 combine), first maximum of the magnitude.
+__device__ int fine_time_from_spec(SyncSmem &sm) {
+  const int p = threadIdx.x;
+  for (int i = p; i < 1536; i += FFT_THREADS) {
+    const int bin = i < 768 ? i + 1280 : i - 765;  // sic: off by two in the upper half
+    sm.work[(i % 3) * 512 + i / 3] = cmulc(sm.spec[bin], prs_value(i));
+  }
+  __syncthreads();
+  for (int b = 0; b < 3; b++) block_fft_pow2(sm.work + 512 * b, 9, +1);
+  float best = -99999.f;
+  int best_i = 0x7fffffff;
+  for (int k = p; k < 1536; k += FFT_THREADS) {
+    const int km = k & 511;
+    float sn, cs;
+    float2 acc = sm.work[km];
+    sincospif(2.0f * (float)k / 1536.0f, &sn, &cs);
+    acc = cadd(acc, cmul(sm.work[512 + km], make_float2(cs, sn)));
+    sincospif(2.0f * (float)((2 * k) % 1536) / 1536.0f, &sn, &cs);
+    acc = cadd(acc, cmul(sm.work[1024 + km], make_float2(cs, sn)));
+    const float mag = sqrtf(acc.x * acc.x + acc.y * acc.y);
+    if (mag > best) {  // ascending k per thread: the first maximum is kept
+      best = mag;
+      best_i = k;
+    }
+  }
+  float bv;
+  int bi;
+  block_arg_reduce(sm, best, best_i, true, &bv, &bi);
+  return bi < 768 ? 2 * bi + 16 : 2 * (bi - 1536);
+}
+
+// sdr_sync.c:205-258 on the spectrum in sm.spec (natural order; the reference's fftshifted
+// index i is bin (i + 1024) mod 2048)
+__device__ int coarse_freq_from_spec(SyncSmem &sm) {
+  const int p = threadIdx.x;
+  float gbest = -99999.f;
+  int gk = 0;
+  for (int k = -14; k <= 14; k++) {
+    if (p < 128) sm.work[p] = cmulc(sm.spec[(14 + k + 256 + p + 1024) & 2047], prs_value(14 + p));
+    __syncthreads();
+    block_fft_pow2(sm.work, 7, +1);
+    const float mag = sqrtf(sm.work[p].x * sm.work[p].x + sm.work[p].y * sm.work[p].y);
+    float bv;
+    int bi;
+    block_arg_reduce(sm, mag, p, true, &bv, &bi);
+    if (bv > gbest) {
+      gbest = bv;
+      gk = k;
+    }
+  }
+  return gk;
+}
+
+// sdr_sync.c:259-302: mean phase of x[n+2048] conj(x[n]) over the PRS guard interval, in Hz
+template <typename Src>
+__device__ float fine_freq(SyncSmem &sm, const Src &src) {
+  float acc = 0.f;
+  for (int i = threadIdx.x; i < 504; i += FFT_THREADS) {
+    const float2 lr = cmulc(src.at(2656 + 2048 + i), src.at(2656 + i));
+    acc += atan2f(lr.y, lr.x);
+  }
+  return block_sum(sm, acc) / 504.f / (2.f * 3.14159265358979323846f) * 1000.f;
+}
+
+// the synchroniser half of sdr_demod (input_sdr.c:65-112) for every stream with ctl.run
+__global__ void __launch_bounds__(FFT_THREADS) sync_kernel(const uint8_t *__restrict__ frames,
+                                                           const StepCtl *__restrict__ ctl,
+                                                           SyncOut *__restrict__ out) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SyncSmem &sm = *reinterpret_cast<SyncSmem *>(smem_raw);
+  const int s = blockIdx.x, p = threadIdx.x;
+  if (!ctl[s].run) return;
+  const SrcU8 src{frames + (uint64_t)s * DABGPU_TF_BYTES};
+  SyncOut r = out[s];  // fine_timeshift / fine_freq_shift persist across early exits (sdr_state_t)
+  r.ok = 0;
+  r.coarse_freq_shift = 0;
+  r.stage = 1;
+  r.coarse_timeshift = coarse_time_sync(sm, src, ctl[s].force_timesync != 0, &r.null_energy);
+  if (r.coarse_timeshift == 0) {
+    FftTwiddles tw;
+    load_twiddles(tw, p);
+    fft_window(sm, src, 2656 + 504, tw);
+    r.fine_timeshift = fine_time_from_spec(sm);
+    // input_sdr.c:91: the reference indexes the frame with the *byte* shift here
+    fft_window(sm, src, 2656 + 505 + r.fine_timeshift, tw);
+    r.coarse_freq_shift = coarse_freq_from_spec(sm);
+    r.stage = 2;
+    if (abs(r.coarse_freq_shift) <= 1) {
+      r.fine_freq_shift = fine_freq(sm, src);
+      r.ok = 1;
+      r.stage = 3;
+    }
+  }
+  if (p == 0) out[s] = r;
+}
+
+int launch_sync(const uint8_t *d_frames, const StepCtl *d_ctl, SyncOut *d_out, int n_streams, cudaStream_t st) {
+  if (n_streams <= 0) return DABGPU_OK;
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncSmem)));
+    attr_set = true;
+  }
+  sync_kernel<<<n_streams, FFT_THREADS, sizeof(SyncSmem), st>>>(d_frames, d_ctl, d_out);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// single-function variants behind the reference's sdr_sync.h entry points
+//   mode 0: dab_coarse_time_sync(int8 real[196608])      -> res[0] (bytes)
+//   mode 1: dab_fine_time_sync(frame as float2[196608])  -> res[0] (bytes)
+//   mode 2: dab_coarse_freq_sync_2(shifted spectrum float2[2048]) -> res[0] (carriers)
+//   mode 3: dab_fine_freq_corr(frame as float2[>= 5208]) -> fres[0] (Hz)
+__global__ void __launch_bounds__(FFT_THREADS) sync_single_kernel(int mode, const void *in, int force, int *res,
+                                                                  float *fres) {
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  SyncSmem &sm = *reinterpret_cast<SyncSmem *>(smem_raw);
+  const int p = threadIdx.x;
+  int r = 0;
+  float fr = 0.f;
+  if (mode == 0) {
+    float e;
+    r = coarse_time_sync(sm, SrcI8{(const int8_t *)in}, force != 0, &e);
+    fr = e;
+  } else if (mode == 1) {
+    FftTwiddles tw;
+    load_twiddles(tw, p);
+    fft_window(sm, SrcF2{(const float2 *)in}, 2656 + 504, tw);
+    r = fine_time_from_spec(sm);
+  } else if (mode == 2) {
+    const float2 *sh = (const float2 *)in;
+    for (int i = p; i < 2048; i += FFT_THREADS) sm.spec[(i + 1024) & 2047] = sh[i];
+    __syncthreads();
+    r = coarse_freq_from_spec(sm);
+  } else {
+    fr = fine_freq(sm, SrcF2{(const float2 *)in});
+  }
+  if (p == 0) {
+    res[0] = r;
+    fres[0] = fr;
+  }
+}
+
+int launch_sync_single(int mode, const void *d_in, int force, int *d_res, float *d_fres, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    CUDA_TRY(cudaFuncSetAttribute(sync_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(SyncSmem)));
+    attr_set = true;
+  }
+  sync_single_kernel<<<1, FFT_THREADS, sizeof(SyncSmem), st>>>(mode, d_in, force, d_res, d_fres);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+}  // namespace dabgpu

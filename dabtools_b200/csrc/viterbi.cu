@@ -211,7 +211,7 @@ int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const V
                    const VitGroup *d_groups, int ngroups, cudaStream_t st) {
   if (ngroups <= 0) return DABGPU_OK;
   viterbi_kernel<<<ngroups, 32, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return DABGPU_OK;
 }
 
@@ -243,7 +243,7 @@ int launch_prep_soft(const uint8_t *d_soft, uint64_t soft_stride, uint8_t *d_ste
   if (!total) return DABGPU_OK;
   prep_soft_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_soft, soft_stride, d_steps,
                                                                     row_stride, n_cw, nsteps);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return DABGPU_OK;
 }
 
@@ -263,6 +263,8 @@ void shape_to_dev(const dabgpu_cw_shape &s, ShapeDev *o) {
 
 // one thread per 8-step puncturing period (the tail region has 6 steps)
 __global__ void prep_hard_kernel(const uint8_t *__restrict__ bits, uint64_t bits_stride,
+                                 uint32_t per_group, uint64_t group_stride,
+                                 const uint32_t *__restrict__ group_index,
                                  uint8_t *__restrict__ steps, uint64_t row_stride, int n_cw,
                                  const ShapeDev *__restrict__ shape, uint32_t nsteps) {
   const uint32_t periods = vit_row_bytes(nsteps) / 8;
@@ -277,7 +279,8 @@ __global__ void prep_hard_kernel(const uint8_t *__restrict__ bits, uint64_t bits
     while (r + 1 < shape->n_regions && (int)t0 >= shape->r[r + 1].step0) r++;
     const uint32_t mask = shape->r[r].mask;
     const int in = shape->r[r].in0 + (int)((t0 - shape->r[r].step0) >> 3) * shape->r[r].ones;
-    const uint8_t *p = bits + cw * bits_stride + in;
+    const uint64_t grp = group_index ? (uint64_t)group_index[cw / per_group] : cw / per_group;
+    const uint8_t *p = bits + grp * group_stride + (cw % per_group) * bits_stride + in;
     const int nst = min(8, (int)nsteps - (int)t0);
     int k = 0;
     for (int s = 0; s < nst; s++) {
@@ -295,14 +298,35 @@ __global__ void prep_hard_kernel(const uint8_t *__restrict__ bits, uint64_t bits
   *reinterpret_cast<uint64_t *>(steps + cw * row_stride + t0) = packed;
 }
 
-int launch_prep_hard(const uint8_t *d_bits, uint64_t bits_stride, uint8_t *d_steps,
-                     uint64_t row_stride, int n_cw, const ShapeDev *d_shape, uint32_t nsteps,
-                     cudaStream_t st) {
+int launch_prep_hard(const uint8_t *d_bits, uint64_t bits_stride, uint32_t per_group,
+                     uint64_t group_stride, const uint32_t *d_group_index, uint8_t *d_steps,
+                     uint64_t row_stride, int n_cw,
+                     const ShapeDev *d_shape, uint32_t nsteps, cudaStream_t st) {
   const uint64_t total = (uint64_t)n_cw * (vit_row_bytes(nsteps) / 8);
   if (!total) return DABGPU_OK;
-  prep_hard_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(d_bits, bits_stride, d_steps,
-                                                                    row_stride, n_cw, d_shape, nsteps);
-  CUDA_TRY(cudaGetLastError());
+  if (per_group == 0) per_group = 1;
+  prep_hard_kernel<<<(unsigned)((total + 127) / 128), 128, 0, st>>>(
+      d_bits, bits_stride, per_group, group_stride, d_group_index, d_steps, row_stride, n_cw, d_shape, nsteps);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+__global__ void scatter_rows_kernel(const uint8_t *__restrict__ src, uint32_t row_words,
+                                    const uint64_t *__restrict__ dst_off, uint8_t *__restrict__ dst, int n_rows) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t row = idx / row_words;
+  const uint32_t w = (uint32_t)(idx - row * row_words);
+  if (row >= (uint64_t)n_rows) return;
+  reinterpret_cast<uint32_t *>(dst + dst_off[row])[w] = reinterpret_cast<const uint32_t *>(src)[idx];
+}
+
+int launch_scatter_rows(const uint8_t *d_src, uint32_t row_bytes, const uint64_t *d_dst_off, uint8_t *d_dst,
+                        int n_rows, cudaStream_t st) {
+  const uint64_t total = (uint64_t)n_rows * (row_bytes / 4);
+  if (!total) return DABGPU_OK;
+  scatter_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_src, row_bytes / 4, d_dst_off, d_dst,
+                                                                       n_rows);
+  LAUNCH_CHECK();
   return DABGPU_OK;
 }
 
@@ -328,7 +352,7 @@ __global__ void fib_crc_kernel(const uint8_t *__restrict__ fibs, uint8_t *__rest
 int launch_fib_crc(const uint8_t *d_fibs, uint8_t *d_ok, int n_fibs, cudaStream_t st) {
   if (n_fibs <= 0) return DABGPU_OK;
   fib_crc_kernel<<<(n_fibs + 127) / 128, 128, 0, st>>>(d_fibs, d_ok, n_fibs);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return DABGPU_OK;
 }
 
@@ -346,7 +370,7 @@ int launch_descramble(uint8_t *d_buf, uint64_t stride, int n_rows, int nbytes, c
   const uint64_t total = (uint64_t)n_rows * (uint64_t)nbytes;
   if (!total) return DABGPU_OK;
   descramble_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_buf, stride, n_rows, nbytes);
-  CUDA_TRY(cudaGetLastError());
+  LAUNCH_CHECK();
   return DABGPU_OK;
 }
 

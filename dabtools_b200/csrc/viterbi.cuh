@@ -51,8 +51,14 @@ struct ShapeDev {  // device copy of dabgpu_cw_shape with expanded masks
   } r[5];
 };
 void shape_to_dev(const dabgpu_cw_shape &s, ShapeDev *o);
-int launch_prep_hard(const uint8_t *d_bits, uint64_t bits_stride, uint8_t *d_steps, uint64_t row_stride,
-                     int n_cw, const ShapeDev *d_shape, uint32_t nsteps, cudaStream_t st);
+// codeword cw reads its bits at G * group_stride + (cw % per_group) * bits_stride with
+// G = cw / per_group, or d_group_index[cw / per_group] when an index is given
+int launch_prep_hard(const uint8_t *d_bits, uint64_t bits_stride, uint32_t per_group, uint64_t group_stride,
+                     const uint32_t *d_group_index, uint8_t *d_steps, uint64_t row_stride, int n_cw,
+                     const ShapeDev *d_shape, uint32_t nsteps, cudaStream_t st);
+// rows[i] of `row_bytes` bytes (multiple of 4): dst + dst_off[i] <- src + i * row_bytes
+int launch_scatter_rows(const uint8_t *d_src, uint32_t row_bytes, const uint64_t *d_dst_off, uint8_t *d_dst,
+                        int n_rows, cudaStream_t st);
 
 // FIB CRC check (src/misc.c:145-150) over n FIBs of 32 bytes -> 1/0 per FIB
 int launch_fib_crc(const uint8_t *d_fibs, uint8_t *d_ok, int n_fibs, cudaStream_t st);

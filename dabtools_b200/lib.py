@@ -92,3 +92,130 @@ def fic_decode_batch_device(fic_bits, fibs, crc_ok):
     assert fic_bits.is_cuda and fic_bits.is_contiguous() and fibs.is_contiguous() and crc_ok.is_contiguous()
     check(load().dabgpu_fic_decode_batch(C.c_void_p(fic_bits.data_ptr()), n, C.c_void_p(fibs.data_ptr()),
                                          C.c_void_p(crc_ok.data_ptr()), 1))
+
+
+# ---- single-frame front-end ------------------------------------------------------------------------
+def sync_frame(frame: np.ndarray, force_timesync: int = 0) -> dict:
+    frame = np.ascontiguousarray(frame, dtype=np.uint8).ravel()
+    assert frame.size == 393216
+    out = (C.c_int32 * 4)()
+    ffs = C.c_float(0)
+    check(load().dabgpu_sync_frame(_np_ptr(frame), force_timesync, out, C.byref(ffs)))
+    return dict(coarse_timeshift=out[0], fine_timeshift=out[1], coarse_freq_shift=out[2], ok=out[3],
+                fine_freq_shift=float(ffs.value))
+
+
+def demod_frame_debug(frame: np.ndarray) -> dict:
+    frame = np.ascontiguousarray(frame, dtype=np.uint8).ravel()
+    assert frame.size == 393216
+    sym = np.zeros((76, 2048), dtype=np.complex64)
+    symd = np.zeros((76, 2048), dtype=np.complex64)
+    bits = np.zeros(230400, dtype=np.uint8)
+    check(load().dabgpu_demod_frame_debug(_np_ptr(frame), _np_ptr(sym), _np_ptr(symd), _np_ptr(bits)))
+    return dict(symbols=sym, symbols_d=symd, bits=bits)
+
+
+# ---- batched receiver ---------------------------------------------------------------------------------
+class StreamStatus(C.Structure):
+    _fields_ = [("locked", C.c_int32), ("okcount", C.c_int32), ("ncifs", C.c_int32), ("tfidx", C.c_int32),
+                ("coarse_timeshift", C.c_int32), ("fine_timeshift", C.c_int32),
+                ("coarse_freq_shift", C.c_int32), ("last_ok", C.c_int32),
+                ("fine_freq_shift", C.c_double), ("frequency", C.c_uint32), ("n_subchannels", C.c_int32),
+                ("frames_demodulated", C.c_uint64), ("eti_frames", C.c_uint64), ("fib_crc_errors", C.c_uint64)]
+
+
+ENGINE_VERBOSE = 1
+ENGINE_VIRTUAL_TUNER = 2
+
+
+class Engine:
+    """S independent ensemble streams in lock-step (dabgpu_engine_* of include/dabgpu.h)."""
+
+    def __init__(self, n_streams: int, tuner_hz: int = 200_000_000, flags: int = 0):
+        lib = load()
+        lib.dabgpu_engine_create.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_uint32, C.c_int]
+        lib.dabgpu_engine_destroy.argtypes = [C.c_void_p]
+        lib.dabgpu_engine_feed_iq.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int, C.c_int]
+        lib.dabgpu_engine_process_demapped.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p, C.c_int]
+        lib.dabgpu_engine_eti_count.argtypes = [C.c_void_p]
+        lib.dabgpu_engine_eti_device.argtypes = [C.c_void_p]
+        lib.dabgpu_engine_eti_device.restype = C.c_void_p
+        lib.dabgpu_engine_fetch_eti.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        lib.dabgpu_engine_status.argtypes = [C.c_void_p, C.c_int, C.POINTER(StreamStatus)]
+        lib.dabgpu_engine_set_seed.argtypes = [C.c_void_p, C.c_int, C.c_uint]
+        lib.dabgpu_engine_trellis_steps.argtypes = [C.c_void_p]
+        lib.dabgpu_engine_trellis_steps.restype = C.c_uint64
+        lib.dabgpu_launch_count.restype = C.c_uint64
+        self._lib = lib
+        self.n_streams = n_streams
+        h = C.c_void_p()
+        check(lib.dabgpu_engine_create(C.byref(h), n_streams, tuner_hz, flags))
+        self._h = h
+
+    def close(self):
+        if self._h:
+            self._lib.dabgpu_engine_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # host buffers (numpy) --------------------------------------------------------------------
+    def feed_iq(self, iq: np.ndarray) -> int:
+        """iq: uint8 [n_streams][chunk_len] (host).  Returns the number of ETI frames produced."""
+        iq = np.ascontiguousarray(iq, dtype=np.uint8)
+        assert iq.shape[0] == self.n_streams
+        check(self._lib.dabgpu_engine_feed_iq(self._h, _np_ptr(iq), iq.shape[1], iq.shape[1], 0))
+        return self._lib.dabgpu_engine_eti_count(self._h)
+
+    def process_demapped(self, tfs: np.ndarray, mask=None) -> int:
+        tfs = np.ascontiguousarray(tfs, dtype=np.uint8).reshape(self.n_streams, -1)
+        m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+        check(self._lib.dabgpu_engine_process_demapped(self._h, _np_ptr(tfs), tfs.shape[1],
+                                                       None if m is None else _np_ptr(m), 0))
+        return self._lib.dabgpu_engine_eti_count(self._h)
+
+    # device buffers (torch CUDA tensors) ------------------------------------------------------
+    def feed_iq_device(self, iq) -> int:
+        assert iq.is_cuda and iq.dim() == 2 and iq.shape[0] == self.n_streams and iq.stride(1) == 1
+        check(self._lib.dabgpu_engine_feed_iq(self._h, C.c_void_p(iq.data_ptr()), iq.stride(0), iq.shape[1], 1))
+        return self._lib.dabgpu_engine_eti_count(self._h)
+
+    def process_demapped_device(self, tfs) -> int:
+        assert tfs.is_cuda and tfs.dim() == 2 and tfs.shape[0] == self.n_streams and tfs.stride(1) == 1
+        check(self._lib.dabgpu_engine_process_demapped(self._h, C.c_void_p(tfs.data_ptr()), tfs.stride(0), None, 1))
+        return self._lib.dabgpu_engine_eti_count(self._h)
+
+    def eti_count(self) -> int:
+        return self._lib.dabgpu_engine_eti_count(self._h)
+
+    def fetch_eti(self, out: np.ndarray = None):
+        n = self.eti_count()
+        if out is None:
+            out = np.empty((n, 6144), dtype=np.uint8)
+        ids = np.empty(max(n, 1), dtype=np.int32)
+        if n:
+            got = self._lib.dabgpu_engine_fetch_eti(self._h, _np_ptr(out), _np_ptr(ids), n)
+            if got < 0:
+                check(got)
+        return out[:n], ids[:n]
+
+    def status(self, stream: int) -> StreamStatus:
+        st = StreamStatus()
+        check(self._lib.dabgpu_engine_status(self._h, stream, C.byref(st)))
+        return st
+
+    def set_seed(self, stream: int, seed: int):
+        check(self._lib.dabgpu_engine_set_seed(self._h, stream, seed))
+
+    def trellis_steps(self) -> int:
+        return int(self._lib.dabgpu_engine_trellis_steps(self._h))
+
+
+def launch_count() -> int:
+    lib = load()
+    lib.dabgpu_launch_count.restype = C.c_uint64
+    return int(lib.dabgpu_launch_count())

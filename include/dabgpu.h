@@ -72,6 +72,56 @@ int dabgpu_fic_decode_batch(const uint8_t *fic_bits, int n_groups, uint8_t *fibs
 
 /* Work accounting of the last dabgpu_*_batch call on this thread: trellis steps decoded. */
 uint64_t dabgpu_last_trellis_steps(void);
+/* Number of CUDA kernels this library has launched since it was loaded (all threads). */
+uint64_t dabgpu_launch_count(void);
+
+/* ---- single-frame front-end (parity / debugging) ------------------------------------------ */
+/* frame: 393216 bytes of uint8 I/Q exactly as sdr_demod has them in sdr->buffer after
+ * sdr_read_fifo.  Runs the synchronisers of input_sdr.c:65-112; out[0..3] = coarse_timeshift,
+ * fine_timeshift (bytes), coarse_freq_shift (carriers), ok; *fine_freq_hz as sdr_state_t. */
+int dabgpu_sync_frame(const uint8_t *frame, int force_timesync, int32_t *out4, float *fine_freq_hz);
+/* FFT + DQPSK + demap of all 76 symbols regardless of the synchronisers (input_sdr.c:114-162):
+ * symbols / symbols_d: 76*2048 complex float each (fftshifted like sdr->symbols; row 0 of
+ * symbols_d is not written), bits: 230400 bytes (fic 9216 then msc 221184).  Any may be NULL. */
+int dabgpu_demod_frame_debug(const uint8_t *frame, float *symbols, float *symbols_d, uint8_t *bits);
+
+/* ---- the batched receiver ------------------------------------------------------------------- */
+/* S independent ensemble streams in lock-step; each stream is one instance of the reference's
+ * receive loop (dab2eti.c:60-115: sdr_demod -> dab_process_frame -> tuner feedback). */
+typedef struct dabgpu_engine dabgpu_engine;
+
+#define DABGPU_ENGINE_VERBOSE 1        /* print the reference's stderr messages (Locked, ...) */
+#define DABGPU_ENGINE_VIRTUAL_TUNER 2  /* apply the tuner feedback as a software NCO on ingest */
+
+typedef struct {
+  int32_t locked, okcount, ncifs, tfidx;          /* dab_state_t, dab.h:83-86 */
+  int32_t coarse_timeshift, fine_timeshift;       /* sdr_state_t, input_sdr.h:17-19 */
+  int32_t coarse_freq_shift, last_ok;             /* last_ok = return value of the last sdr_demod */
+  double fine_freq_shift;
+  uint32_t frequency;                             /* tuner frequency after feedback (Hz) */
+  int32_t n_subchannels;
+  uint64_t frames_demodulated, eti_frames, fib_crc_errors;
+} dabgpu_stream_status;
+
+int dabgpu_engine_create(dabgpu_engine **out, int n_streams, uint32_t tuner_hz, int flags);
+void dabgpu_engine_destroy(dabgpu_engine *e);
+/* One rtlsdr callback for every stream: iq + s*pitch holds chunk_len bytes (<= 262144, multiple
+ * of 16) for stream s.  Equivalent to one demod_thread_fn iteration per stream. */
+int dabgpu_engine_feed_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int chunk_len, int on_device);
+/* Back-end only: one demapped transmission frame (fic 9216 + msc 221184 bytes of 0/1, i.e. the
+ * payload of demapped_transmission_frame_t) for every stream with mask[s] != 0 (mask NULL = all);
+ * equivalent to dab_process_frame per stream. */
+int dabgpu_engine_process_demapped(dabgpu_engine *e, const uint8_t *tfs, size_t pitch, const uint8_t *mask,
+                                   int on_device);
+/* ETI frames produced by the last feed/process call (0 or 4 per stream), in stream order. */
+int dabgpu_engine_eti_count(dabgpu_engine *e);
+const uint8_t *dabgpu_engine_eti_device(dabgpu_engine *e);
+/* copies up to max_frames frames (6144 bytes each) and their stream indices to the host;
+ * returns the number of frames, or a negative error */
+int dabgpu_engine_fetch_eti(dabgpu_engine *e, uint8_t *eti, int32_t *stream_ids, int max_frames);
+int dabgpu_engine_status(dabgpu_engine *e, int stream, dabgpu_stream_status *out);
+int dabgpu_engine_set_seed(dabgpu_engine *e, int stream, unsigned seed); /* srand() of dab2eti.c:88-96 */
+uint64_t dabgpu_engine_trellis_steps(dabgpu_engine *e);
 
 #ifdef __cplusplus
 }

@@ -175,7 +175,9 @@ static inline int dabgpu_eep_size_mul(int level) {
   return sm[level & 7];
 }
 
-static inline int dabgpu_eep_layout(int level, int size_cu, dabgpu_eep_layout_t *o) {
+/* bitrate_field: the sub-channel's bitrate as the caller believes it (the reference keys
+ * its special case on that field, depuncture.c:113); pass -1 to derive it from the size. */
+static inline int dabgpu_eep_layout(int level, int size_cu, int bitrate_field, dabgpu_eep_layout_t *o) {
   /* L1 = a1*n + b1, L2 = a2*n + b2 */
   static const int a1[8] = {6, 2, 6, 4, 24, 24, 24, 24};
   static const int a2[8] = {0, 4, 0, 2, 0, 0, 0, 0};
@@ -188,7 +190,8 @@ static inline int dabgpu_eep_layout(int level, int size_cu, dabgpu_eep_layout_t 
   o->L[1] = a2[level] * n + 3;
   o->PI[0] = pi1[level];
   o->PI[1] = pi1[level] - 1;
-  if (level == 1 && o->bitrate == 8) {
+  if (bitrate_field < 0) bitrate_field = o->bitrate;
+  if (level == 1 && bitrate_field == 8) {
     /* 8 kbit/s at 2-A: the standard specifies L=(5,1), PI=(13,12).  The reference
      * (dab_tables.c:98-100, depuncture.c:113-114) uses PI=(4,13) here; parity with
      * the reference is the contract, so its values are used. */
@@ -253,9 +256,10 @@ static inline int dabgpu_shape_uep(dabgpu_cw_shape *s, int uep_index) {
   return 0;
 }
 
-static inline int dabgpu_shape_eep(dabgpu_cw_shape *s, int level, int size_cu) {
+static inline int dabgpu_shape_eep(dabgpu_cw_shape *s, int level, int size_cu, int bitrate_field) {
   dabgpu_eep_layout_t e;
-  if (dabgpu_eep_layout(level, size_cu, &e) <= 0) return -1;
+  if (level < 0 || level > 7) return -1;
+  if (dabgpu_eep_layout(level, size_cu, bitrate_field, &e) <= 0 && !(level == 1 && bitrate_field == 8)) return -1;
   if (e.L[0] < 0) return -1;
   dabgpu_shape_finish(s, e.L, e.PI, 2);
   return 0;

@@ -174,8 +174,7 @@ int orc_uep_depuncture(uint8_t *out, const uint8_t *in, int uep_index) {
  * only triggers when the *bitrate* field says 8) */
 int orc_eep_depuncture(uint8_t *out, const uint8_t *in, int protlev, int size_cu, int bitrate) {
   dabgpu_cw_shape sh;
-  (void)bitrate; /* bitrate is a function of (protlev,size) on the reference path */
-  if (dabgpu_shape_eep(&sh, protlev, size_cu)) return -1;
+  if (dabgpu_shape_eep(&sh, protlev, size_cu, bitrate)) return -1;
   return depuncture_shape(&sh, out, in);
 }
 
@@ -885,7 +884,7 @@ int orc_tab_shape(int kind, int a, int b, int32_t *out) {
   else if (kind == 1)
     rc = dabgpu_shape_uep(&sh, a);
   else
-    rc = dabgpu_shape_eep(&sh, a, b);
+    rc = dabgpu_shape_eep(&sh, a, b, -1);
   if (rc) return rc;
   memcpy(out, &sh, sizeof sh);
   return 0;
