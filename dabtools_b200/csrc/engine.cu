@@ -54,7 +54,38 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   return DABGPU_OK;
 }
 
+int Engine::enable_timing(bool on) {
+  if (on && !ev[0][0])
+    for (int k = 0; k < K_COUNT; k++)
+      for (int j = 0; j < 2; j++) CUDA_TRY(cudaEventCreate(&ev[k][j]));
+  timing = on;
+  for (int k = 0; k < K_COUNT; k++) {
+    ms_total[k] = 0;
+    n_total[k] = 0;
+    ev_used[k] = false;
+  }
+  return DABGPU_OK;
+}
+
+// called at the end of a step when timing is on: wait for the stream, accumulate elapsed times
+int Engine::collect_timing(cudaStream_t st) {
+  if (!timing) return DABGPU_OK;
+  CUDA_TRY(cudaStreamSynchronize(st));
+  for (int k = 0; k < K_COUNT; k++) {
+    if (!ev_used[k]) continue;
+    float ms = 0;
+    CUDA_TRY(cudaEventElapsedTime(&ms, ev[k][0], ev[k][1]));
+    ms_total[k] += ms;
+    n_total[k]++;
+    ev_used[k] = false;
+  }
+  return DABGPU_OK;
+}
+
 void Engine::destroy() {
+  if (ev[0][0])
+    for (int k = 0; k < K_COUNT; k++)
+      for (int j = 0; j < 2; j++) cudaEventDestroy(ev[k][j]);
   DevBuf *db[] = {&d_ring, &d_frames, &d_chunk, &d_ctl, &d_sync, &d_cifs, &d_fibs, &d_crc, &d_ficbits,
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
                   &d_subjobs, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
@@ -170,10 +201,14 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   const uint32_t *d_idx = d_gather_idx.as<uint32_t>();
   const uint64_t *d_dst = reinterpret_cast<const uint64_t *>(d_gather_idx.as<uint8_t>() +
                                                              (((size_t)na * 4 + 7) & ~(size_t)7));
+  t0(K_FIC_PREP, st);
   if ((rc = launch_prep_hard(d_fic_src, 2304, 4, fic_stride, d_idx, d_steps_fic.as<uint8_t>(), FIC_ROW, 4 * na,
                              d_fic_shape.as<ShapeDev>(), 774, st)))
     return rc;
+  t1(K_FIC_PREP, st);
+  t0(K_FIC_VIT, st);
   if ((rc = vb_fic.run(d_steps_fic.as<uint8_t>(), d_fib_c, st))) return rc;
+  t1(K_FIC_VIT, st);
   trellis_steps += vb_fic.total_steps;
   if ((rc = launch_fib_crc(d_fib_c, d_crc_c, 12 * na, st))) return rc;
   if ((rc = launch_scatter_rows(d_fib_c, FIBS_PER_TF, d_dst, d_fibs.as<uint8_t>(), na, st))) return rc;
@@ -262,13 +297,19 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   const CifJob *dj = d_cifjobs.as<CifJob>();
   const SubJob *ds = reinterpret_cast<const SubJob *>(d_cifjobs.as<uint8_t>() + b_cif);
   const EtiJob *de = reinterpret_cast<const EtiJob *>(d_cifjobs.as<uint8_t>() + b_cif + b_sub);
+  t0(K_MSC_GATHER, st);
   if ((rc = launch_msc_gather(d_cifs.as<uint8_t>(), dj, ds, d_shapes.as<ShapeDev>(), d_steps_msc.as<uint8_t>(),
                               n_eti, st)))
     return rc;
+  t1(K_MSC_GATHER, st);
+  t0(K_MSC_VIT, st);
   if ((rc = vb_msc.run(d_steps_msc.as<uint8_t>(), d_eti.as<uint8_t>(), st))) return rc;
+  t1(K_MSC_VIT, st);
   trellis_steps += vb_msc.total_steps;
+  t0(K_ETI, st);
   if ((rc = launch_eti_pack(de, d_ens.as<EnsDev>(), d_fibs.as<uint8_t>(), d_eti.as<uint8_t>(), n_eti, st)))
     return rc;
+  t1(K_ETI, st);
   return DABGPU_OK;
 }
 
@@ -316,7 +357,8 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
                                    d_planeoff.as<uint64_t>() + 4 * a, d_cifs.as<uint8_t>(), 1, st)))
         return rc;
   }
-  return fic_and_backend(st, d_tf, pitch, nullptr);
+  if ((rc = fic_and_backend(st, d_tf, pitch, nullptr))) return rc;
+  return collect_timing(st);
 }
 
 int Engine::ensure_frontend() {
@@ -425,24 +467,32 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     d_src = d_chunk.as<uint8_t>();
     pitch = chunk_len;
   }
+  t0(K_INGEST, st);
   if ((rc = launch_ingest(d_src, pitch, (uint32_t)chunk_len, d_ring.as<uint8_t>(), d_ctl.as<StepCtl>(), S, st)))
     return rc;
+  t1(K_INGEST, st);
   n_eti = 0;
   eti_stream.clear();
   if (any_read) {
+    t0(K_FIFO, st);
     if ((rc = launch_fifo_read(d_ring.as<uint8_t>(), d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), S, st)))
       return rc;
+    t1(K_FIFO, st);
     if (!active.empty()) {
+      t0(K_SYNC, st);
       if ((rc = launch_sync(d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), S, st))) return rc;
+      t1(K_SYNC, st);
+      t0(K_DEMOD, st);
       if ((rc = launch_demod(d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(),
                              d_ficbits.as<uint8_t>(), d_cifs.as<uint8_t>(), S, st)))
         return rc;
+      t1(K_DEMOD, st);
       CUDA_TRY(cudaMemcpyAsync(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st));
       if ((rc = fic_and_backend(st, d_ficbits.as<uint8_t>(), 9216, h_sync.as<SyncOut>()))) return rc;
     }
   }
   for (int s = 0; s < S; s++) tuner_feedback(front[s]);
-  return DABGPU_OK;
+  return collect_timing(st);
 }
 
 }  // namespace dabgpu
@@ -530,3 +580,12 @@ DABGPU_EXPORT int dabgpu_engine_set_seed(dabgpu_engine *h, int stream, unsigned 
   return DABGPU_OK;
 }
 DABGPU_EXPORT uint64_t dabgpu_engine_trellis_steps(dabgpu_engine *h) { return h->e.trellis_steps; }
+
+DABGPU_EXPORT int dabgpu_engine_enable_timing(dabgpu_engine *h, int on) { return h->e.enable_timing(on != 0); }
+DABGPU_EXPORT int dabgpu_engine_kernel_times(dabgpu_engine *h, double *ms_total, uint64_t *launches, int n) {
+  for (int k = 0; k < n && k < Engine::K_COUNT; k++) {
+    ms_total[k] = h->e.ms_total[k];
+    launches[k] = h->e.n_total[k];
+  }
+  return Engine::K_COUNT;
+}

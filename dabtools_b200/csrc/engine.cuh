@@ -72,6 +72,27 @@ struct Engine {
   PinBuf h_ctl, h_sync, h_fic_out, h_jobs, h_eti, h_chunk;
   VitBatch vb_fic, vb_msc;
 
+  // optional per-kernel device timing (CUDA events on the launch stream), for bench.py's roofline
+  enum KernelId { K_INGEST, K_FIFO, K_SYNC, K_DEMOD, K_FIC_PREP, K_FIC_VIT, K_MSC_GATHER, K_MSC_VIT, K_ETI, K_COUNT };
+  bool timing = false;
+  cudaEvent_t ev[K_COUNT][2] = {};
+  bool ev_used[K_COUNT] = {};
+  double ms_total[K_COUNT] = {};
+  uint64_t n_total[K_COUNT] = {};
+  void t0(int k, cudaStream_t st) {
+    if (timing) {
+      cudaEventRecord(ev[k][0], st);
+    }
+  }
+  void t1(int k, cudaStream_t st) {
+    if (timing) {
+      cudaEventRecord(ev[k][1], st);
+      ev_used[k] = true;
+    }
+  }
+  int collect_timing(cudaStream_t st);
+  int enable_timing(bool on);
+
   // results of the last step
   int n_eti = 0;
   std::vector<int32_t> eti_stream;

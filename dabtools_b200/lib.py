@@ -219,3 +219,24 @@ def launch_count() -> int:
     lib = load()
     lib.dabgpu_launch_count.restype = C.c_uint64
     return int(lib.dabgpu_launch_count())
+
+
+KERNEL_NAMES = ("ingest", "fifo_read", "sync", "demod", "fic_prep", "fic_viterbi", "msc_gather", "msc_viterbi",
+                "eti_pack")
+
+
+def _engine_enable_timing(self, on: bool = True):
+    self._lib.dabgpu_engine_enable_timing.argtypes = [C.c_void_p, C.c_int]
+    check(self._lib.dabgpu_engine_enable_timing(self._h, int(on)))
+
+
+def _engine_kernel_times(self) -> dict:
+    ms = (C.c_double * len(KERNEL_NAMES))()
+    n = (C.c_uint64 * len(KERNEL_NAMES))()
+    self._lib.dabgpu_engine_kernel_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+    self._lib.dabgpu_engine_kernel_times(self._h, ms, n, len(KERNEL_NAMES))
+    return {k: dict(ms=float(ms[i]), launches=int(n[i])) for i, k in enumerate(KERNEL_NAMES)}
+
+
+Engine.enable_timing = _engine_enable_timing
+Engine.kernel_times = _engine_kernel_times

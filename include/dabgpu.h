@@ -122,6 +122,12 @@ int dabgpu_engine_fetch_eti(dabgpu_engine *e, uint8_t *eti, int32_t *stream_ids,
 int dabgpu_engine_status(dabgpu_engine *e, int stream, dabgpu_stream_status *out);
 int dabgpu_engine_set_seed(dabgpu_engine *e, int stream, unsigned seed); /* srand() of dab2eti.c:88-96 */
 uint64_t dabgpu_engine_trellis_steps(dabgpu_engine *e);
+/* Optional device-side timing of the engine's kernels with CUDA events on the launch stream
+ * (adds a stream synchronisation to every feed/process call).  Order of the entries:
+ * ingest, fifo_read, sync, demod, fic_prep, fic_viterbi, msc_gather, msc_viterbi, eti_pack. */
+#define DABGPU_ENGINE_KERNELS 9
+int dabgpu_engine_enable_timing(dabgpu_engine *e, int on);
+int dabgpu_engine_kernel_times(dabgpu_engine *e, double *ms_total, uint64_t *launches, int n);
 
 #ifdef __cplusplus
 }
