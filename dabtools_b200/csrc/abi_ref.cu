@@ -1,0 +1,576 @@
+// abi_ref.cu -- the reference's own entry points for the receive path (include/dabgpu_ref_abi.h),
+// batch-of-one wrappers around the same CUDA kernels the batched engine uses.
+//
+// Same names, argument meaning and error behaviour as the reference: nothing here returns an
+// error code the reference would not; CUDA failures are reported on stderr and through
+// dabgpu_last_error(), and leave the outputs untouched.  The reference is non-re-entrant on this
+// path (static buffers in misc.c:215-216, viterbi.c:102-103); these wrappers share one
+// per-process workspace guarded by a mutex, so they are at least safe to call from several threads.
+#include <mutex>
+
+#include "engine.cuh"
+
+using namespace dabgpu;
+
+namespace {
+
+struct RefCtx {
+  std::mutex mu;
+  DevBuf in, out, steps, shape, cifs, jobs, aux, eti, ens, fibs;
+  VitBatch vb;
+  bool shape_is_fic = false;
+};
+RefCtx g_ref;
+
+void report(const char *fn) {
+  fprintf(stderr, "libdabgpu: %s failed: %s\n", fn, dabgpu_last_error_string());
+}
+
+// depuncture (depuncture.c): hard bits -> {127,129}, punctured -> 128, on the device
+__global__ void depuncture_soft_kernel(const uint8_t *__restrict__ in, uint8_t *__restrict__ out,
+                                       const ShapeDev *__restrict__ sh) {
+  const int nsym = 4 * (sh->nbits + 6);
+  for (int o = blockIdx.x * blockDim.x + threadIdx.x; o < nsym; o += gridDim.x * blockDim.x) {
+    const int t = o >> 2;
+    int r = 0;
+    while (r + 1 < sh->n_regions && t >= sh->r[r + 1].step0) r++;
+    const uint32_t mask = sh->r[r].mask;
+    const int rel = o - 4 * sh->r[r].step0;      // position inside the region
+    const int per = rel >> 5, pos = rel & 31;
+    if ((mask >> pos) & 1u) {
+      const int idx = sh->r[r].in0 + per * sh->r[r].ones + __popc(mask & ((1u << pos) - 1u));
+      out[o] = (uint8_t)(127 + 2 * (in[idx] & 1));  // to_viterbi(), depuncture.c:36-43
+    } else {
+      out[o] = 128;
+    }
+  }
+}
+
+int depuncture_common(uint8_t *obuf, const uint8_t *inbuf, const dabgpu_cw_shape &sh, int *len) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  std::lock_guard<std::mutex> lk(g_ref.mu);
+  cudaStream_t st = current_stream();
+  ShapeDev sd;
+  shape_to_dev(sh, &sd);
+  const int nsym = 4 * (sh.nbits + 6);
+  if ((rc = g_ref.in.reserve(sh.in_bits + 64))) return rc;
+  if ((rc = g_ref.out.reserve(nsym))) return rc;
+  if ((rc = g_ref.shape.reserve(sizeof sd))) return rc;
+  g_ref.shape_is_fic = false;
+  CUDA_TRY(cudaMemcpyAsync(g_ref.in.p, inbuf, sh.in_bits, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(g_ref.shape.p, &sd, sizeof sd, cudaMemcpyHostToDevice, st));
+  depuncture_soft_kernel<<<(nsym + 255) / 256, 256, 0, st>>>(g_ref.in.as<uint8_t>(), g_ref.out.as<uint8_t>(),
+                                                            g_ref.shape.as<ShapeDev>());
+  LAUNCH_CHECK();
+  CUDA_TRY(cudaMemcpyAsync(obuf, g_ref.out.p, nsym, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if (len) *len = nsym;
+  return DABGPU_OK;
+}
+
+}  // namespace
+
+// ---- depuncture.h:7-9 ----------------------------------------------------------------------------
+DABGPU_EXPORT void fic_depuncture(uint8_t *obuf, uint8_t *inbuf) {
+  dabgpu_cw_shape sh;
+  dabgpu_shape_fic(&sh);
+  if (depuncture_common(obuf, inbuf, sh, nullptr)) report("fic_depuncture");
+}
+DABGPU_EXPORT void uep_depuncture(uint8_t *obuf, uint8_t *inbuf, struct subchannel_info_t *s, int *len) {
+  dabgpu_cw_shape sh;
+  if (dabgpu_shape_uep(&sh, s->uep_index)) {
+    set_error(DABGPU_ERR_ARG, "uep_depuncture: uep_index %d out of range", s->uep_index);
+    report("uep_depuncture");
+    return;
+  }
+  if (depuncture_common(obuf, inbuf, sh, len)) report("uep_depuncture");
+}
+DABGPU_EXPORT void eep_depuncture(uint8_t *obuf, uint8_t *inbuf, struct subchannel_info_t *s, int *len) {
+  dabgpu_cw_shape sh;
+  if (dabgpu_shape_eep(&sh, s->protlev, s->size, s->bitrate)) {
+    set_error(DABGPU_ERR_ARG, "eep_depuncture: protlev %d / size %d not decodable", s->protlev, s->size);
+    report("eep_depuncture");
+    return;
+  }
+  if (depuncture_common(obuf, inbuf, sh, len)) report("eep_depuncture");
+}
+
+// ---- viterbi.h:6-8 ---------------------------------------------------------------------------------
+DABGPU_EXPORT int init_viterbi(void) {
+  // the reference builds its metric table here (viterbi.c:455-462); ours is the 256-entry
+  // branch-distance table each decoder CTA builds in shared memory, so only check the device
+  if (ensure_device_ready()) report("init_viterbi");
+  return 0;
+}
+DABGPU_EXPORT int viterbi(void *p, unsigned char *symbols, unsigned char *data, unsigned int framebits) {
+  (void)p;
+  if (!data) return 0;  // viterbi.c:437-438
+  if (dabgpu_viterbi_batch(symbols, 4ull * (framebits + 6), 1, (int)framebits, data, (framebits + 7) / 8, 0, 0))
+    report("viterbi");
+  return 0;
+}
+
+// ---- misc.h:9-10, misc.c:29 ---------------------------------------------------------------------------
+DABGPU_EXPORT void dab_descramble_bytes(uint8_t *buf, int32_t nbytes) {
+  if (nbytes <= 0) return;
+  if (ensure_device_ready()) return report("dab_descramble_bytes");
+  std::lock_guard<std::mutex> lk(g_ref.mu);
+  cudaStream_t st = current_stream();
+  auto run = [&]() -> int {
+    int rc;
+    if ((rc = g_ref.in.reserve(nbytes))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_ref.in.p, buf, nbytes, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_descramble(g_ref.in.as<uint8_t>(), nbytes, 1, nbytes, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(buf, g_ref.in.p, nbytes, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DABGPU_OK;
+  };
+  if (run()) report("dab_descramble_bytes");
+}
+
+DABGPU_EXPORT int check_fib_crc(uint8_t *data) {
+  if (ensure_device_ready()) {
+    report("check_fib_crc");
+    return 0;
+  }
+  std::lock_guard<std::mutex> lk(g_ref.mu);
+  cudaStream_t st = current_stream();
+  uint8_t ok = 0;
+  auto run = [&]() -> int {
+    int rc;
+    if ((rc = g_ref.in.reserve(64))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_ref.in.p, data, 32, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_fib_crc(g_ref.in.as<uint8_t>(), g_ref.in.as<uint8_t>() + 32, 1, st))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(&ok, g_ref.in.as<uint8_t>() + 32, 1, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DABGPU_OK;
+  };
+  if (run()) report("check_fib_crc");
+  return ok;
+}
+
+namespace {
+// upload 16 host CIFs (55296 bytes of 0/1 each) as planes; g_ref.cifs holds them in window order
+int upload_window(uint8_t *const cifs[16], cudaStream_t st) {
+  int rc;
+  if ((rc = g_ref.in.reserve((size_t)16 * DABGPU_CIF_BITS))) return rc;
+  if ((rc = g_ref.cifs.reserve((size_t)16 * CIF_BYTES))) return rc;
+  if ((rc = g_ref.aux.reserve(16 * sizeof(uint64_t)))) return rc;
+  uint64_t off[16];
+  for (int i = 0; i < 16; i++) {
+    CUDA_TRY(cudaMemcpyAsync(g_ref.in.as<uint8_t>() + (size_t)i * DABGPU_CIF_BITS, cifs[i], DABGPU_CIF_BITS,
+                             cudaMemcpyHostToDevice, st));
+    off[i] = (uint64_t)i * CIF_BYTES;
+  }
+  CUDA_TRY(cudaMemcpyAsync(g_ref.aux.p, off, sizeof off, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaStreamSynchronize(st));  // off is a local
+  // 16 CIFs = 4 "TFs" of 4 CIFs for the packer
+  return launch_pack_planes(g_ref.in.as<uint8_t>(), (uint64_t)4 * DABGPU_CIF_BITS, g_ref.aux.as<uint64_t>(),
+                            g_ref.cifs.as<uint8_t>(), 4, st);
+}
+}  // namespace
+
+DABGPU_EXPORT void time_deinterleave(uint8_t *dst, uint8_t *cifs[]) {
+  if (ensure_device_ready()) return report("time_deinterleave");
+  std::lock_guard<std::mutex> lk(g_ref.mu);
+  cudaStream_t st = current_stream();
+  auto run = [&]() -> int {
+    int rc;
+    if ((rc = upload_window(cifs, st))) return rc;
+    CifJob job;
+    memset(&job, 0, sizeof job);
+    for (int i = 0; i < 16; i++) job.slot_off[i] = (uint64_t)i * CIF_BYTES;
+    if ((rc = g_ref.jobs.reserve(sizeof job))) return rc;
+    if ((rc = g_ref.out.reserve(DABGPU_CIF_BITS))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(g_ref.jobs.p, &job, sizeof job, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_deinterleave_bytes(g_ref.cifs.as<uint8_t>(), g_ref.jobs.as<CifJob>(), g_ref.out.as<uint8_t>(), 1,
+                                        st)))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(dst, g_ref.out.p, DABGPU_CIF_BITS, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DABGPU_OK;
+  };
+  if (run()) report("time_deinterleave");
+}
+
+// ---- fic.h:5 -------------------------------------------------------------------------------------------
+DABGPU_EXPORT void fic_decode(struct dab_state_t *dab, struct demapped_transmission_frame_t *tf) {
+  (void)dab;
+  tf->fibs.ok_count = 0;
+  if (!tf->has_fic) {
+    // fic.c:167-175: no FIC in the received data -> NULL FIBs with a valid CRC
+    static const uint8_t null_tail[2] = {0xa8, 0xa8};
+    for (int i = 0; i < 12; i++) {
+      memset(tf->fibs.FIB[i], 0, 32);
+      tf->fibs.FIB[i][0] = 0xff;
+      tf->fibs.FIB[i][30] = null_tail[0];
+      tf->fibs.FIB[i][31] = null_tail[1];
+      tf->fibs.FIB_CRC_OK[i] = 1;
+    }
+    tf->fibs.ok_count = 12;
+    return;
+  }
+  uint8_t ok[12];
+  if (dabgpu_fic_decode_batch(&tf->fic_symbols_demapped[0][0], 4, &tf->fibs.FIB[0][0], ok, 0)) {
+    report("fic_decode");
+    memset(tf->fibs.FIB_CRC_OK, 0, 12);
+    return;
+  }
+  for (int i = 0; i < 12; i++) {
+    tf->fibs.FIB_CRC_OK[i] = ok[i];
+    tf->fibs.ok_count += ok[i];
+  }
+}
+
+// ---- misc.h:7 : create_eti ------------------------------------------------------------------------------
+DABGPU_EXPORT void create_eti(struct dab_state_t *dab) {
+  uint8_t eti[DABGPU_ETI_BYTES];
+  ens_info_t *info = &dab->ens_info;
+  auto run = [&]() -> int {
+    int rc;
+    if ((rc = ensure_device_ready())) return rc;
+    std::lock_guard<std::mutex> lk(g_ref.mu);
+    cudaStream_t st = current_stream();
+    if ((rc = upload_window(dab->cifs_msc, st))) return rc;
+    // layout of the frame, as misc.c:218-296 walks it
+    EnsDev ed;
+    memset(&ed, 0, sizeof ed);
+    std::vector<ShapeDev> shapes;
+    std::vector<SubJob> subs;
+    g_ref.vb.clear();
+    uint32_t nst = 0, fl = 0, payload = 0, row = 0;
+    for (int j = 0; j < 64; j++) nst += info->subchans[j].id >= 0;
+    uint32_t e = 12 + 4 * nst + 96;
+    uint32_t k = 0;
+    for (int j = 0; j < 64; j++) {
+      const subchannel_info_t &sc = info->subchans[j];
+      if (sc.id < 0) continue;
+      dabgpu_cw_shape sh;
+      if (host_subch_shape(&sc, &sh) || sc.start_cu * 64 + sh.in_bits > DABGPU_CIF_BITS) {
+        set_error(DABGPU_ERR_STATE, "create_eti: sub-channel %d is not decodable", sc.id);
+        return DABGPU_ERR_STATE;
+      }
+      ShapeDev sd;
+      shape_to_dev(sh, &sd);
+      shapes.push_back(sd);
+      SubJob sj;
+      sj.row_off = row;
+      sj.in_bit0 = (uint32_t)sc.start_cu * 64u;
+      sj.shape = k;
+      subs.push_back(sj);
+      g_ref.vb.add(row, e, (uint32_t)sh.nbits, VIT_DESCRAMBLE);
+      row += vit_row_bytes((uint32_t)sh.nbits + 6);
+      const int obytes = host_subch_obytes(sh.nbits);
+      e += obytes;
+      payload += obytes;
+      fl += sc.bitrate * 3 / 4;
+      const int tpl = sc.slForm == 0 ? (0x10 | (sc.protlev - 1)) : (0x20 | sc.protlev);
+      const int stl = sc.bitrate * 3 / 8;
+      ed.stc[k][0] = (uint8_t)((sc.id << 2) | ((sc.start_cu >> 8) & 3));
+      ed.stc[k][1] = (uint8_t)sc.start_cu;
+      ed.stc[k][2] = (uint8_t)((tpl << 2) | ((stl >> 8) & 3));
+      ed.stc[k][3] = (uint8_t)stl;
+      k++;
+    }
+    if (e + 8 > DABGPU_ETI_BYTES) {
+      set_error(DABGPU_ERR_STATE, "create_eti: multiplex does not fit an ETI frame");
+      return DABGPU_ERR_STATE;
+    }
+    ed.nst = nst;
+    ed.fl = fl + nst + 1 + 24;
+    ed.payload = payload;
+    CifJob cj;
+    for (int i = 0; i < 16; i++) cj.slot_off[i] = (uint64_t)i * CIF_BYTES;
+    cj.sub0 = 0;
+    cj.nsub = k;
+    EtiJob ej;
+    memset(&ej, 0, sizeof ej);
+    ej.fib_off = 0;
+    ej.ens = 0;
+    ej.cif_hi = info->CIFCount_hi;
+    ej.cif_lo = info->CIFCount_lo;
+    const size_t b_shapes = shapes.size() * sizeof(ShapeDev), b_subs = subs.size() * sizeof(SubJob);
+    if ((rc = g_ref.shape.reserve(b_shapes + 64))) return rc;
+    g_ref.shape_is_fic = false;
+    if ((rc = g_ref.jobs.reserve(sizeof cj + b_subs + sizeof ej + 64))) return rc;
+    if ((rc = g_ref.ens.reserve(sizeof ed))) return rc;
+    if ((rc = g_ref.fibs.reserve(96))) return rc;
+    if ((rc = g_ref.steps.reserve(row + 64))) return rc;
+    if ((rc = g_ref.eti.reserve(DABGPU_ETI_BYTES))) return rc;
+    uint8_t *dj = g_ref.jobs.as<uint8_t>();
+    if (b_shapes) CUDA_TRY(cudaMemcpyAsync(g_ref.shape.p, shapes.data(), b_shapes, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dj, &cj, sizeof cj, cudaMemcpyHostToDevice, st));
+    if (b_subs) CUDA_TRY(cudaMemcpyAsync(dj + sizeof cj, subs.data(), b_subs, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(dj + sizeof cj + b_subs, &ej, sizeof ej, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_ref.ens.p, &ed, sizeof ed, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaMemcpyAsync(g_ref.fibs.p, dab->cifs_fibs[0], 96, cudaMemcpyHostToDevice, st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // the host copies above are locals
+    if ((rc = launch_msc_gather(g_ref.cifs.as<uint8_t>(), reinterpret_cast<CifJob *>(dj),
+                                reinterpret_cast<SubJob *>(dj + sizeof cj), g_ref.shape.as<ShapeDev>(),
+                                g_ref.steps.as<uint8_t>(), 1, st)))
+      return rc;
+    if ((rc = g_ref.vb.run(g_ref.steps.as<uint8_t>(), g_ref.eti.as<uint8_t>(), st))) return rc;
+    if ((rc = launch_eti_pack(reinterpret_cast<EtiJob *>(dj + sizeof cj + b_subs), g_ref.ens.as<EnsDev>(),
+                              g_ref.fibs.as<uint8_t>(), g_ref.eti.as<uint8_t>(), 1, st)))
+      return rc;
+    CUDA_TRY(cudaMemcpyAsync(eti, g_ref.eti.p, DABGPU_ETI_BYTES, cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+    return DABGPU_OK;
+  };
+  if (run()) {
+    report("create_eti");
+    return;
+  }
+  if (dab->eti_callback) dab->eti_callback(eti);  // misc.c:301-303
+  if (++info->CIFCount_lo == 250) {                // misc.c:305-313
+    info->CIFCount_lo = 0;
+    if (++info->CIFCount_hi == 20) info->CIFCount_hi = 0;
+  }
+}
+
+// ---- dab.h:91-92 --------------------------------------------------------------------------------------------
+DABGPU_EXPORT void init_dab_state(struct dab_state_t **dab, void *device_state, void (*eti_callback)(uint8_t *eti)) {
+  struct dab_state_t *d = (struct dab_state_t *)calloc(sizeof(struct dab_state_t), 1);
+  *dab = d;
+  d->device_state = device_state;
+  d->eti_callback = eti_callback;
+  host_init_ens(&d->ens_info);
+  init_viterbi();
+}
+
+DABGPU_EXPORT void dab_process_frame(struct dab_state_t *dab) {
+  struct demapped_transmission_frame_t *tf = &dab->tfs[dab->tfidx];
+  fic_decode(dab, tf);
+  if (tf->fibs.ok_count > 0) fib_decode(&dab->tf_info, &tf->fibs, 12);
+  if (tf->fibs.ok_count == 12) {
+    dab->okcount++;
+    if (dab->okcount >= 10 && !dab->locked) {
+      dab->locked = 1;
+      fprintf(stderr, "Locked\n");
+    }
+  } else {
+    dab->okcount = 0;
+    if (dab->locked) {
+      dab->locked = 0;
+      fprintf(stderr, "Lock lost, resetting ringbuffer\n");
+      dab->ncifs = 0;
+      dab->tfidx = 0;
+      return;
+    }
+  }
+  if (!dab->locked) return;
+  merge_info(&dab->ens_info, &dab->tf_info);
+  if (dab->ncifs < 16) {
+    for (int k = 0; k < 4; k++) {
+      dab->cifs_fibs[dab->ncifs] = tf->fibs.FIB[3 * k];
+      dab->cifs_msc[dab->ncifs++] = tf->msc_symbols_demapped[18 * k];
+    }
+  } else {
+    if (!dab->ens_info_shown) {
+      dump_ens_info(&dab->ens_info);
+      dab->ens_info_shown = 1;
+    }
+    for (int k = 0; k < 4; k++) {
+      create_eti(dab);
+      memmove(dab->cifs_fibs, dab->cifs_fibs + 1, sizeof(dab->cifs_fibs[0]) * 15);
+      memmove(dab->cifs_msc, dab->cifs_msc + 1, sizeof(dab->cifs_msc[0]) * 15);
+      dab->cifs_fibs[15] = tf->fibs.FIB[3 * k];
+      dab->cifs_msc[15] = tf->msc_symbols_demapped[18 * k];
+    }
+  }
+  dab->tfidx = (dab->tfidx + 1) % 5;
+}
+
+// ---- sdr_fifo.h:36-43: byte FIFO (host data structure, unchanged semantics) ---------------------------------
+DABGPU_EXPORT void cbInit(CircularBuffer *cb, uint32_t size) {
+  cb->size = size;
+  cb->start = 0;
+  cb->count = 0;
+  cb->elems = (uint8_t *)calloc(size, 1);
+}
+DABGPU_EXPORT void cbFree(CircularBuffer *cb) { free(cb->elems); }
+DABGPU_EXPORT int cbIsFull(CircularBuffer *cb) { return cb->count == cb->size; }
+DABGPU_EXPORT int cbIsEmpty(CircularBuffer *cb) { return cb->count == 0; }
+DABGPU_EXPORT void cbWrite(CircularBuffer *cb, uint8_t *elem) {
+  cb->elems[(cb->start + cb->count) % cb->size] = *elem;
+  if (cb->count == cb->size) {
+    cb->start = (cb->start + 1) % cb->size;
+    fprintf(stderr, "fifo overflow!\n");
+  } else {
+    cb->count++;
+  }
+}
+DABGPU_EXPORT void cbRead(CircularBuffer *cb, uint8_t *elem) {
+  *elem = cb->elems[cb->start];
+  cb->start = (cb->start + 1) % cb->size;
+  cb->count--;
+}
+// bulk forms of the byte loops of sdr_fifo.c:43-61, same observable result
+static void fifo_take(CircularBuffer *cb, uint8_t *dst, uint32_t n) {
+  const uint32_t first = n < cb->size - cb->start ? n : cb->size - cb->start;
+  memcpy(dst, cb->elems + cb->start, first);
+  memcpy(dst + first, cb->elems, n - first);
+  cb->start = (cb->start + n) % cb->size;
+  cb->count -= n;
+}
+DABGPU_EXPORT int32_t sdr_read_fifo(CircularBuffer *fifo, uint32_t bytes, int32_t shift, uint8_t *buffer) {
+  if (shift > 0) {
+    const uint32_t skip = (uint32_t)shift < fifo->count ? (uint32_t)shift : fifo->count;
+    // the skipped bytes pass through buffer[0..skip) before being overwritten
+    std::vector<uint8_t> tmp(skip);
+    fifo_take(fifo, tmp.data(), skip);
+    const uint32_t n = bytes < fifo->count ? bytes : fifo->count;
+    const uint32_t keep = skip < bytes ? skip : bytes;
+    if (n < keep) memcpy(buffer + n, tmp.data() + n, keep - n);
+    fifo_take(fifo, buffer, n);
+  } else {
+    fifo_take(fifo, buffer, bytes + (uint32_t)shift);
+  }
+  return 1;
+}
+
+// ---- sdr_sync.h:28-31 ------------------------------------------------------------------------------------------
+namespace {
+int sync_single(int mode, const void *host_in, size_t in_bytes, int force, int *ires, float *fres) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  std::lock_guard<std::mutex> lk(g_ref.mu);
+  cudaStream_t st = current_stream();
+  if ((rc = g_ref.in.reserve(in_bytes))) return rc;
+  if ((rc = g_ref.aux.reserve(64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(g_ref.in.p, host_in, in_bytes, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_sync_single(mode, g_ref.in.p, force, g_ref.aux.as<int>(), g_ref.aux.as<float>() + 1, st)))
+    return rc;
+  int32_t res[2];
+  CUDA_TRY(cudaMemcpyAsync(res, g_ref.aux.p, 8, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  *ires = res[0];
+  memcpy(fres, &res[1], 4);
+  return DABGPU_OK;
+}
+std::vector<float> to_float2(const fftw_complex *x, size_t n) {
+  std::vector<float> f(2 * n);
+  for (size_t i = 0; i < n; i++) {
+    f[2 * i] = (float)x[i][0];
+    f[2 * i + 1] = (float)x[i][1];
+  }
+  return f;
+}
+}  // namespace
+
+DABGPU_EXPORT uint32_t dab_coarse_time_sync(int8_t *real, float *filt, uint8_t force_timesync) {
+  (void)filt;  // scratch in the reference; the sliding sums live in registers here
+  int r = 0;
+  float f;
+  if (sync_single(0, real, 196608, force_timesync, &r, &f)) report("dab_coarse_time_sync");
+  return (uint32_t)r;
+}
+DABGPU_EXPORT int32_t dab_fine_time_sync(fftw_complex *frame) {
+  // needs frame[3160 .. 3160+2048)
+  std::vector<float> f = to_float2(frame, 2656 + 504 + 2048);
+  int r = 0;
+  float x;
+  if (sync_single(1, f.data(), f.size() * 4, 0, &r, &x)) report("dab_fine_time_sync");
+  return r;
+}
+DABGPU_EXPORT int32_t dab_coarse_freq_sync_2(fftw_complex *symbols) {
+  std::vector<float> f = to_float2(symbols, 2048);
+  int r = 0;
+  float x;
+  if (sync_single(2, f.data(), f.size() * 4, 0, &r, &x)) report("dab_coarse_freq_sync_2");
+  return r;
+}
+DABGPU_EXPORT double dab_fine_freq_corr(fftw_complex *dab_frame, int32_t fine_timeshift) {
+  (void)fine_timeshift;  // overwritten with 0 by the reference (sdr_sync.c:270)
+  std::vector<float> f = to_float2(dab_frame, 2656 + 2048 + 504);
+  int r = 0;
+  float x = 0;
+  if (sync_single(3, f.data(), f.size() * 4, 0, &r, &x)) report("dab_fine_freq_corr");
+  return (double)x;
+}
+
+// ---- input_sdr.h:43-44 -------------------------------------------------------------------------------------------
+DABGPU_EXPORT void sdr_init(struct sdr_state_t *sdr) {
+  cbInit(&sdr->fifo, 196608 * 2 * 4);
+  sdr->coarse_timeshift = 0;
+  sdr->fine_timeshift = 0;
+  // the reference fftw_malloc()s these and dab2eti never frees them; they are kept so that code
+  // poking at sdr_state_t finds valid pointers, but the GPU path does not fill them
+  sdr->dab_frame = (fftw_complex *)calloc(196608, sizeof(fftw_complex));
+  sdr->prs_ifft = (fftw_complex *)calloc(2048 + 32, sizeof(fftw_complex));
+  sdr->prs_conj_ifft = (fftw_complex *)calloc(2048 + 32, sizeof(fftw_complex));
+  sdr->prs_syms = (fftw_complex *)calloc(2048 + 32, sizeof(fftw_complex));
+  sdr->symbols_d = (fftw_complex *)calloc(2048 * 76, sizeof(fftw_complex));
+  sdr->p_e_prior_dep = 0.0;
+  sdr->p_e_prior_vitdec = 0.0;
+  sdr->p_e_after_vitdec = 0.0;
+}
+
+DABGPU_EXPORT int sdr_demod(struct demapped_transmission_frame_t *tf, struct sdr_state_t *sdr) {
+  tf->has_fic = 0;
+  sdr->coarse_freq_shift = 0;
+  // FIFO write (input_sdr.c:36-38), bulk
+  {
+    CircularBuffer *cb = &sdr->fifo;
+    for (int i = 0; i < sdr->input_buffer_len; i++) cbWrite(cb, &sdr->input_buffer[i]);
+  }
+  if (sdr->fifo.count < 196608 * 3) return 0;
+  sdr_read_fifo(&sdr->fifo, 196608 * 2, sdr->coarse_timeshift + sdr->fine_timeshift, sdr->buffer);
+  if (sdr->startup_delay <= GAIN_SETTLE_TIME) {
+    sdr->startup_delay += 1;
+    fprintf(stderr, "startup_delay=%i\n", sdr->startup_delay);
+    return 0;
+  }
+  int32_t s4[4] = {0, 0, 0, 0};
+  float ffs = 0.f;
+  // the synchronisers keep fine_timeshift / fine_freq_shift on an early exit: seed them
+  sdr->coarse_timeshift = 0;
+  const uint8_t force = sdr->force_timesync;
+  sdr->force_timesync = 0;
+  if (dabgpu_sync_frame(sdr->buffer, force, s4, &ffs)) {
+    report("sdr_demod");
+    return 0;
+  }
+  sdr->coarse_timeshift = s4[0];
+  if (sdr->coarse_timeshift) return 0;
+  sdr->fine_timeshift = s4[1];
+  sdr->coarse_freq_shift = s4[2];
+  if (abs(sdr->coarse_freq_shift) > 1) {
+    sdr->force_timesync = 1;
+    return 0;
+  }
+  sdr->fine_freq_shift = (double)ffs;
+  static thread_local std::vector<uint8_t> bits(230400);
+  if (dabgpu_demod_frame_debug(sdr->buffer, nullptr, nullptr, bits.data())) {
+    report("sdr_demod");
+    return 0;
+  }
+  memcpy(tf->fic_symbols_demapped, bits.data(), 9216);
+  memcpy(tf->msc_symbols_demapped, bits.data() + 9216, 221184);
+  tf->has_fic = 1;
+  return 1;
+}
+
+// struct sizes, for tests/test_abi_layout.py (compared with the compiled reference)
+DABGPU_EXPORT int dabgpu_sizeof_dab_state(void) { return (int)sizeof(struct dab_state_t); }
+DABGPU_EXPORT int dabgpu_sizeof_sdr_state(void) { return (int)sizeof(struct sdr_state_t); }
+DABGPU_EXPORT int dabgpu_sizeof_tf(void) { return (int)sizeof(struct demapped_transmission_frame_t); }
+DABGPU_EXPORT void dabgpu_abi_offsets(int32_t *out) {
+  int i = 0;
+  out[i++] = (int)offsetof(struct dab_state_t, tfs);
+  out[i++] = (int)offsetof(struct dab_state_t, tf_info);
+  out[i++] = (int)offsetof(struct dab_state_t, ens_info);
+  out[i++] = (int)offsetof(struct dab_state_t, cifs_msc);
+  out[i++] = (int)offsetof(struct dab_state_t, ncifs);
+  out[i++] = (int)offsetof(struct dab_state_t, eti_callback);
+  out[i++] = (int)offsetof(struct sdr_state_t, input_buffer_len);
+  out[i++] = (int)offsetof(struct sdr_state_t, buffer);
+  out[i++] = (int)offsetof(struct sdr_state_t, fine_freq_shift);
+  out[i++] = (int)offsetof(struct sdr_state_t, fifo);
+  out[i++] = (int)offsetof(struct sdr_state_t, symbols);
+  out[i++] = (int)offsetof(struct sdr_state_t, startup_delay);
+  out[i++] = (int)offsetof(struct sdr_state_t, p_e_after_vitdec);
+  out[i++] = (int)offsetof(struct demapped_transmission_frame_t, fibs);
+  out[i++] = (int)offsetof(struct demapped_transmission_frame_t, msc_symbols_demapped);
+}

@@ -129,6 +129,12 @@ uint64_t dabgpu_engine_trellis_steps(dabgpu_engine *e);
 int dabgpu_engine_enable_timing(dabgpu_engine *e, int on);
 int dabgpu_engine_kernel_times(dabgpu_engine *e, double *ms_total, uint64_t *launches, int n);
 
+/* ---- ABI self-description (sizeof / offsetof of include/dabgpu_ref_abi.h's structs) -------- */
+int dabgpu_sizeof_dab_state(void);
+int dabgpu_sizeof_sdr_state(void);
+int dabgpu_sizeof_tf(void);
+void dabgpu_abi_offsets(int32_t *out15);
+
 #ifdef __cplusplus
 }
 #endif

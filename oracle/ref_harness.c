@@ -238,3 +238,23 @@ extern int Syms[];
 int ref_sizeof_dab_state(void) { return (int)sizeof(struct dab_state_t); }
 int ref_sizeof_sdr_state(void) { return (int)sizeof(struct sdr_state_t); }
 int ref_sizeof_tf(void) { return (int)sizeof(struct demapped_transmission_frame_t); }
+
+#include <stddef.h>
+void ref_abi_offsets(int32_t *out) {
+  int i = 0;
+  out[i++] = (int)offsetof(struct dab_state_t, tfs);
+  out[i++] = (int)offsetof(struct dab_state_t, tf_info);
+  out[i++] = (int)offsetof(struct dab_state_t, ens_info);
+  out[i++] = (int)offsetof(struct dab_state_t, cifs_msc);
+  out[i++] = (int)offsetof(struct dab_state_t, ncifs);
+  out[i++] = (int)offsetof(struct dab_state_t, eti_callback);
+  out[i++] = (int)offsetof(struct sdr_state_t, input_buffer_len);
+  out[i++] = (int)offsetof(struct sdr_state_t, buffer);
+  out[i++] = (int)offsetof(struct sdr_state_t, fine_freq_shift);
+  out[i++] = (int)offsetof(struct sdr_state_t, fifo);
+  out[i++] = (int)offsetof(struct sdr_state_t, symbols);
+  out[i++] = (int)offsetof(struct sdr_state_t, startup_delay);
+  out[i++] = (int)offsetof(struct sdr_state_t, p_e_after_vitdec);
+  out[i++] = (int)offsetof(struct demapped_transmission_frame_t, fibs);
+  out[i++] = (int)offsetof(struct demapped_transmission_frame_t, msc_symbols_demapped);
+}
