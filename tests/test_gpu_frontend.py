@@ -133,13 +133,14 @@ def test_virtual_tuner_converges_like_the_reference(gpu, port, cfo):
     """carrier offset: the tuner feedback (virtual NCO) must pull both receivers to lock; ETI payload
     equal wherever both produce frames (estimates are float vs double, so only statistical parity)."""
     ens = synth.small_ensemble()
-    g = synth.ModeITransmitter(ens).generate(1, 30, seed=10, snr_db=28, cfo_hz=cfo, tail_samples=262144)
+    g = synth.ModeITransmitter(ens).generate(1, 60, seed=10, snr_db=28, cfo_hz=cfo, tail_samples=262144)
     iq = g["iq"][0].numpy()[2 * 50000:]
     n = iq.size // 262144 * 262144
     got, trace = _run_engine_iq(gpu, iq[None, :n], flags=gpu.ENGINE_VIRTUAL_TUNER)
     want = port.run_iq(iq[:n])
-    assert want["eti"].shape[0] > 0 and got[0].shape[0] > 0
-    assert abs(got[0].shape[0] - want["eti"].shape[0]) <= 8
+    assert want["eti"].shape[0] >= 60 and got[0].shape[0] >= 60
+    # acquisition involves a random dither and float-vs-double estimates: allow a few TFs of slack
+    assert abs(got[0].shape[0] - want["eti"].shape[0]) <= 24
     # final tuner frequency within 60 Hz of the true offset for both
     assert abs((trace[0][-1][6] - 200_000_000) - cfo) < 60
     assert abs((int(want["trace"][-1]["frequency"]) - 200_000_000) - cfo) < 60
