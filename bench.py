@@ -212,6 +212,7 @@ def run_ours(args, rank, world, local_rank):
         n = step_device(eng, setup_steps + i)
     assert n == S * TFS_PER_STEP * FRAMES_PER_TF, f"steady state not reached: {n} frames in a step"
     launches0 = lib.launch_count()
+    host_t0 = eng.host_times()
     sampler = ClockSampler(local_rank)
     barrier()
     if rank == 0:
@@ -227,6 +228,7 @@ def run_ours(args, rank, world, local_rank):
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = lib.launch_count() - launches0
+    host_t = eng.host_times()
 
     # ---------------- per-kernel timing pass (same engine, next K steps) ----------------
     eng.enable_timing(True)
@@ -342,6 +344,7 @@ def run_ours(args, rank, world, local_rank):
             "acs_per_s": 64.0 * msc_steps_per_launch / (vit_ms * 1e-3) if vit_ms > 0 else 0.0,
             "decoded_mbit_s": msc_bits_per_launch / (vit_ms * 1e-3) / 1e6 if vit_ms > 0 else 0.0,
         },
+        "host_ms_per_step": {k: (host_t[k] - host_t0[k]) / 1e3 / K for k in host_t},
         "kernel_ms_per_launch": {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in kt.items()},
     }
     return out

@@ -1,9 +1,14 @@
 // engine.cu -- batched receiver (see engine.cuh) and its C ABI (include/dabgpu.h).
 #include "engine.cuh"
 
+#include <chrono>
 #include <cmath>
 
 namespace dabgpu {
+
+static inline double now_us() {
+  return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
 
 enum { FIC_ROW = 784 /* vit_row_bytes(774) */, FIBS_PER_TF = 384, TF_SLOTS = 5, CIF_SLOTS = 20 };
 
@@ -213,7 +218,10 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   if ((rc = launch_fib_crc(d_fib_c, d_crc_c, 12 * na, st))) return rc;
   if ((rc = launch_scatter_rows(d_fib_c, FIBS_PER_TF, d_dst, d_fibs.as<uint8_t>(), na, st))) return rc;
   CUDA_TRY(cudaMemcpyAsync(h_fic_out.p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), cudaMemcpyDeviceToHost, st));
+  double tw = now_us();
   CUDA_TRY(cudaStreamSynchronize(st));
+  host_us[H_WAIT] += now_us() - tw;
+  tw = now_us();
 
   // ---- host: per-stream sdr_demod epilogue + dab_process_frame ----
   const uint8_t *h_fibs = h_fic_out.as<uint8_t>();
@@ -279,7 +287,9 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
     }
     stats[s].eti_frames += work.n_eti;
   }
+  host_us[H_FSM] += now_us() - tw;
   if (!n_eti) return DABGPU_OK;
+  tw = now_us();
 
   // ---- MSC: time de-interleave + depuncture gather -> Viterbi + descramble -> ETI ----
   if ((rc = upload_tables(st))) return rc;
@@ -297,6 +307,7 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   const CifJob *dj = d_cifjobs.as<CifJob>();
   const SubJob *ds = reinterpret_cast<const SubJob *>(d_cifjobs.as<uint8_t>() + b_cif);
   const EtiJob *de = reinterpret_cast<const EtiJob *>(d_cifjobs.as<uint8_t>() + b_cif + b_sub);
+  host_us[H_JOBS] += now_us() - tw;
   t0(K_MSC_GATHER, st);
   if ((rc = launch_msc_gather(d_cifs.as<uint8_t>(), dj, ds, d_shapes.as<ShapeDev>(), d_steps_msc.as<uint8_t>(),
                               n_eti, st)))
@@ -395,6 +406,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     return DABGPU_ERR_ARG;
   }
   if ((rc = ensure_frontend())) return rc;
+  const double t_pre = now_us();
   cudaStream_t st = current_stream();
   StepCtl *ctl = h_ctl.as<StepCtl>();
   active.clear();
@@ -460,6 +472,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     active.push_back(s);
   }
   CUDA_TRY(cudaMemcpyAsync(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), cudaMemcpyHostToDevice, st));
+  host_us[H_PRE] += now_us() - t_pre;
   const uint8_t *d_src = iq;
   if (!on_device) {
     if ((rc = d_chunk.reserve((size_t)S * chunk_len))) return rc;
@@ -588,4 +601,8 @@ DABGPU_EXPORT int dabgpu_engine_kernel_times(dabgpu_engine *h, double *ms_total,
     launches[k] = h->e.n_total[k];
   }
   return Engine::K_COUNT;
+}
+
+DABGPU_EXPORT void dabgpu_engine_host_times(dabgpu_engine *h, double *us4) {
+  for (int i = 0; i < Engine::H_COUNT; i++) us4[i] = h->e.host_us[i];
 }

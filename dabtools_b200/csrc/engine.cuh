@@ -90,6 +90,9 @@ struct Engine {
       ev_used[k] = true;
     }
   }
+  // host-side wall-clock breakdown of a step (always on; microseconds, cumulative)
+  enum HostPhase { H_PRE, H_WAIT, H_FSM, H_JOBS, H_COUNT };
+  double host_us[H_COUNT] = {};
   int collect_timing(cudaStream_t st);
   int enable_timing(bool on);
 

@@ -111,22 +111,10 @@ __device__ __forceinline__ uint32_t decision_bit(uint2 d, uint32_t s) {
   return (w >> ((((s >> 1) & 3u) << 3) + (s >> 3))) & 1u;
 }
 
-__global__ void __launch_bounds__(32) viterbi_kernel(const uint8_t *__restrict__ steps,
-                                                     uint8_t *__restrict__ out,
-                                                     uint2 *__restrict__ dec,
-                                                     const VitJob *__restrict__ jobs,
-                                                     const VitGroup *__restrict__ groups) {
-  __shared__ uint2 lut[256];  // step byte -> {D, Dc}: per-class distances and complements
-  const int lane = threadIdx.x;
-  for (int sb = lane; sb < 256; sb += 32) {
-    const uint32_t r = sb & 15, e = sb >> 4;
-    uint32_t D = 0;
-    for (int c = 0; c < 4; c++) D |= (uint32_t)__popc(((2u * c) ^ r) & e) << (8 * c);
-    lut[sb] = make_uint2(D, (uint32_t)__popc(e) * 0x01010101u - D);
-  }
-  __syncwarp();
-
-  const VitGroup g = groups[blockIdx.x];
+// Decode one group (up to 32 equal-length codewords, one per lane): forward pass + traceback.
+__device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut,
+                                             const uint8_t *__restrict__ steps, uint8_t *__restrict__ out,
+                                             uint2 *__restrict__ dec, const VitJob *__restrict__ jobs, int lane) {
   const bool active = lane < (int)g.nlanes;
   const VitJob job = jobs[g.job0 + (active ? lane : 0)];
   const uint4 *row = reinterpret_cast<const uint4 *>(steps + job.in_off);
@@ -207,12 +195,47 @@ __global__ void __launch_bounds__(32) viterbi_kernel(const uint8_t *__restrict__
   }
 }
 
+// Persistent decoder: one CTA per SM, VIT_WARPS warps per CTA.  Warp w of CTA b owns work list
+// `bin = b * VIT_WARPS + w` (groups bin_start[bin] .. bin_start[bin+1]), filled on the host by
+// longest-processing-time-first packing over the 4 * num_SMs warp schedulers (warp w runs on
+// scheduler w % 4), so that every scheduler gets the same number of trellis steps.
+__global__ void __launch_bounds__(32 * VIT_WARPS, 1) viterbi_kernel(const uint8_t *__restrict__ steps,
+                                                                    uint8_t *__restrict__ out,
+                                                                    uint2 *__restrict__ dec,
+                                                                    const VitJob *__restrict__ jobs,
+                                                                    const VitGroup *__restrict__ groups,
+                                                                    const uint32_t *__restrict__ bin_start) {
+  __shared__ uint2 lut[256];  // step byte -> {D, Dc}: per-class distances and complements
+  for (int sb = threadIdx.x; sb < 256; sb += blockDim.x) {
+    const uint32_t r = sb & 15, e = sb >> 4;
+    uint32_t D = 0;
+    for (int c = 0; c < 4; c++) D |= (uint32_t)__popc(((2u * c) ^ r) & e) << (8 * c);
+    lut[sb] = make_uint2(D, (uint32_t)__popc(e) * 0x01010101u - D);
+  }
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const uint32_t bin = blockIdx.x * VIT_WARPS + (threadIdx.x >> 5);
+  const uint32_t g0 = bin_start[bin], g1 = bin_start[bin + 1];
+  for (uint32_t gi = g0; gi < g1; gi++) decode_group(groups[gi], lut, steps, out, dec, jobs, lane);
+}
+
 int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
-                   const VitGroup *d_groups, int ngroups, cudaStream_t st) {
-  if (ngroups <= 0) return DABGPU_OK;
-  viterbi_kernel<<<ngroups, 32, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups);
+                   const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, cudaStream_t st) {
+  if (n_ctas <= 0) return DABGPU_OK;
+  viterbi_kernel<<<n_ctas, 32 * VIT_WARPS, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups, d_bin_start);
   LAUNCH_CHECK();
   return DABGPU_OK;
+}
+
+int device_sm_count() {
+  static int n = 0;
+  if (!n) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
 }
 
 // ---- producers ---------------------------------------------------------------------------

@@ -240,3 +240,13 @@ def _engine_kernel_times(self) -> dict:
 
 Engine.enable_timing = _engine_enable_timing
 Engine.kernel_times = _engine_kernel_times
+
+
+def _engine_host_times(self) -> dict:
+    us = (C.c_double * 4)()
+    self._lib.dabgpu_engine_host_times.argtypes = [C.c_void_p, C.c_void_p]
+    self._lib.dabgpu_engine_host_times(self._h, us)
+    return dict(zip(("pre", "wait_gpu", "fsm", "jobs"), (float(x) for x in us)))
+
+
+Engine.host_times = _engine_host_times

@@ -128,6 +128,9 @@ uint64_t dabgpu_engine_trellis_steps(dabgpu_engine *e);
 #define DABGPU_ENGINE_KERNELS 9
 int dabgpu_engine_enable_timing(dabgpu_engine *e, int on);
 int dabgpu_engine_kernel_times(dabgpu_engine *e, double *ms_total, uint64_t *launches, int n);
+/* cumulative host wall-clock microseconds: control build, waiting for the GPU, state machines,
+ * job construction */
+void dabgpu_engine_host_times(dabgpu_engine *e, double *us4);
 
 /* ---- ABI self-description (sizeof / offsetof of include/dabgpu_ref_abi.h's structs) -------- */
 int dabgpu_sizeof_dab_state(void);
