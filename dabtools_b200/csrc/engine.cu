@@ -10,7 +10,68 @@ static inline double now_us() {
   return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
-enum { FIC_ROW = 784 /* vit_row_bytes(774) */, FIBS_PER_TF = 384, TF_SLOTS = 5, CIF_SLOTS = 20 };
+enum { FIC_ROW = 784 /* vit_row_bytes(774) */, FIBS_PER_TF = 384, TF_SLOTS = PHYS_TF_SLOTS, CIF_SLOTS = 4 * PHYS_TF_SLOTS };
+
+// ---- HostPool ---------------------------------------------------------------------------------
+void HostPool::start(int n_threads) {
+  for (int i = 0; i < n_threads; i++) th_.emplace_back([this] { worker(); });
+}
+void HostPool::stop() {
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    quit_ = true;
+  }
+  cv_.notify_all();
+  for (auto &t : th_) t.join();
+  th_.clear();
+  quit_ = false;
+}
+void HostPool::worker() {
+  int seen = 0;
+  for (;;) {
+    const std::function<void(int)> *fn;
+    int n;
+    {
+      std::unique_lock<std::mutex> lk(mu_);
+      cv_.wait(lk, [&] { return quit_ || gen_ != seen; });
+      if (quit_) return;
+      seen = gen_;
+      fn = fn_;
+      n = n_;
+    }
+    for (;;) {
+      const int i0 = next_.fetch_add(16);
+      if (i0 >= n) break;
+      for (int i = i0; i < std::min(n, i0 + 16); i++) (*fn)(i);
+    }
+    {
+      std::lock_guard<std::mutex> lk(mu_);
+      if (--busy_ == 0) done_.notify_one();
+    }
+  }
+}
+void HostPool::run(int n, const std::function<void(int)> &fn) {
+  if (th_.empty() || n < 64) {
+    for (int i = 0; i < n; i++) fn(i);
+    return;
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu_);
+    fn_ = &fn;
+    n_ = n;
+    next_.store(0);
+    busy_ = (int)th_.size();
+    gen_++;
+  }
+  cv_.notify_all();
+  for (;;) {
+    const int i0 = next_.fetch_add(16);
+    if (i0 >= n) break;
+    for (int i = i0; i < std::min(n, i0 + 16); i++) fn(i);
+  }
+  std::unique_lock<std::mutex> lk(mu_);
+  done_.wait(lk, [&] { return busy_ == 0; });
+}
 
 int Engine::shape_index(const dabgpu_cw_shape &s) {
   for (size_t i = 0; i < shapes.size(); i++)
@@ -40,11 +101,18 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
     front[s].rng.seed(1);
     back[s].reset();
   }
+  {
+    const char *env = getenv("DABGPU_HOST_THREADS");
+    int nt = env ? atoi(env) : 4;
+    const int hw = (int)std::thread::hardware_concurrency();
+    if (hw > 0) nt = std::min(nt, std::max(0, hw - 1));
+    if (S >= 64 && nt > 0) pool.start(nt);
+  }
   if ((rc = d_cifs.reserve((size_t)S * CIF_SLOTS * CIF_BYTES))) return rc;
   if ((rc = d_fibs.reserve((size_t)S * TF_SLOTS * FIBS_PER_TF))) return rc;
   if ((rc = d_ficbits.reserve((size_t)S * 9216))) return rc;
   if ((rc = d_steps_fic.reserve((size_t)S * 4 * FIC_ROW))) return rc;
-  if ((rc = d_eti.reserve((size_t)S * 4 * DABGPU_ETI_BYTES))) return rc;
+  if ((rc = d_eti.reserve((size_t)S * 4 * 4 * DABGPU_ETI_BYTES))) return rc;  // up to 4 TFs per flush
   if ((rc = d_ens.reserve((size_t)S * sizeof(EnsDev)))) return rc;
   if ((rc = d_gather_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
   if ((rc = h_fic_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
@@ -88,6 +156,7 @@ int Engine::collect_timing(cudaStream_t st) {
 }
 
 void Engine::destroy() {
+  pool.stop();
   if (ev[0][0])
     for (int k = 0; k < K_COUNT; k++)
       for (int j = 0; j < 2; j++) cudaEventDestroy(ev[k][j]);
@@ -95,7 +164,7 @@ void Engine::destroy() {
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
                   &d_subjobs, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
   for (DevBuf *b : db) b->release();
-  PinBuf *pb[] = {&h_ctl, &h_sync, &h_fic_out, &h_jobs, &h_eti, &h_chunk};
+  PinBuf *pb[] = {&h_ctl, &h_sync, &h_fic_out, &h_jobs, &h_msc, &h_eti, &h_chunk};
   for (PinBuf *b : pb) b->release();
   vb_fic.release();
   vb_msc.release();
@@ -179,8 +248,6 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
                             const SyncOut *sync) {
   int rc;
   const int na = (int)active.size();
-  n_eti = 0;
-  eti_stream.clear();
   if (na == 0) return DABGPU_OK;
 
   // ---- FIC: 4 groups per frame -> compact [na][384] FIBs + [na][12] CRC flags ----
@@ -196,7 +263,7 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   for (int a = 0; a < na; a++) {
     const int s = active[a];
     h_idx[a] = (uint32_t)s;
-    h_dst[a] = ((uint64_t)s * TF_SLOTS + (uint64_t)back[s].tfidx) * FIBS_PER_TF;
+    h_dst[a] = ((uint64_t)s * TF_SLOTS + (uint64_t)back[s].phys) * FIBS_PER_TF;
     for (int k = 0; k < 4; k++)
       vb_fic.add(((uint64_t)a * 4 + k) * FIC_ROW, (uint64_t)a * FIBS_PER_TF + 96 * k, 768, VIT_DESCRAMBLE);
   }
@@ -223,17 +290,15 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   host_us[H_WAIT] += now_us() - tw;
   tw = now_us();
 
-  // ---- host: per-stream sdr_demod epilogue + dab_process_frame ----
+  // ---- host: per-stream sdr_demod epilogue + dab_process_frame (streams are independent) ----
   const uint8_t *h_fibs = h_fic_out.as<uint8_t>();
   const uint8_t *h_crc = h_fibs + (size_t)na * FIBS_PER_TF;
-  cifjobs.clear();
-  subjobs.clear();
-  etijobs.clear();
-  vb_msc.clear();
-  uint64_t row_base = 0;
-  for (int a = 0; a < na; a++) {
+  works.resize(na);
+  pool.run(na, [&](int a) {
     const int s = active[a];
     FrontState &fr = front[s];
+    FrameWork &work = works[a];
+    work.n_eti = 0;
     fr.pending = false;
     if (sync) {
       // input_sdr.c:65-112: the order in which sdr_demod updates its state and bails out
@@ -241,26 +306,36 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
       fr.coarse_timeshift = so.coarse_timeshift;
       fr.force_timesync = 0;
       fr.last_ok = 0;
-      if (so.coarse_timeshift) continue;
+      if (so.coarse_timeshift) return;
       fr.fine_timeshift = so.fine_timeshift;
       fr.coarse_freq_shift = so.coarse_freq_shift;
       if (std::abs(so.coarse_freq_shift) > 1) {
         fr.force_timesync = 1;
-        continue;
+        return;
       }
       fr.fine_freq_shift = (double)so.fine_freq_shift;
       fr.last_ok = 1;
     }
     stats[s].frames_demodulated++;
     for (int i = 0; i < 12; i++) stats[s].fib_crc_errors += h_crc[12 * a + i] ? 0 : 1;
-    FrameWork work;
     host_process_frame(back[s], h_fibs + (size_t)a * FIBS_PER_TF, h_crc + 12 * a, &work, quiet);
+    stats[s].eti_frames += work.n_eti;
+  });
+  host_us[H_FSM] += now_us() - tw;
+  tw = now_us();
+
+  // ---- queue the ETI frames of this call (sequential: offsets are prefix sums) ----
+  bool any = false;
+  for (int a = 0; a < na; a++) {
+    const FrameWork &work = works[a];
     if (!work.n_eti) continue;
+    const int s = active[a];
     if ((rc = refresh_layout(s))) return rc;
     const EnsLayout &L = layout[s];
+    any = true;
     for (int k = 0; k < work.n_eti; k++) {
-      const int f = n_eti++;
-      eti_stream.push_back(s);
+      const int f = (int)etijobs.size();
+      pend_stream.push_back(s);
       CifJob cj;
       for (int j = 0; j < 16; j++)
         cj.slot_off[j] = ((uint64_t)s * CIF_SLOTS + (uint64_t)work.win[k][j]) * CIF_BYTES;
@@ -285,21 +360,33 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
       ej.pad[0] = ej.pad[1] = 0;
       etijobs.push_back(ej);
     }
-    stats[s].eti_frames += work.n_eti;
   }
-  host_us[H_FSM] += now_us() - tw;
-  if (!n_eti) return DABGPU_OK;
-  tw = now_us();
+  if (any) pend_calls++;
+  host_us[H_JOBS] += now_us() - tw;
+  if (pend_calls >= msc_batch) return flush_msc(st);
+  return DABGPU_OK;
+}
 
-  // ---- MSC: time de-interleave + depuncture gather -> Viterbi + descramble -> ETI ----
+// MSC of everything queued: time de-interleave + depuncture gather -> Viterbi + descramble -> ETI
+int Engine::flush_msc(cudaStream_t st) {
+  int rc;
+  if (etijobs.empty()) {
+    pend_calls = 0;
+    return DABGPU_OK;
+  }
+  const double tw = now_us();
+  n_eti = (int)etijobs.size();
+  eti_stream.assign(pend_stream.begin(), pend_stream.end());
   if ((rc = upload_tables(st))) return rc;
   const size_t b_cif = cifjobs.size() * sizeof(CifJob), b_sub = subjobs.size() * sizeof(SubJob),
                b_eti = etijobs.size() * sizeof(EtiJob);
-  if ((rc = h_jobs.reserve(b_cif + b_sub + b_eti))) return rc;
+  // the pinned staging area may still be read by the copy of the previous flush
+  CUDA_TRY(cudaStreamSynchronize(st));
+  if ((rc = h_msc.reserve(b_cif + b_sub + b_eti))) return rc;
   if ((rc = d_cifjobs.reserve(b_cif + b_sub + b_eti))) return rc;
   if ((rc = d_steps_msc.reserve(row_base + 64))) return rc;
   if ((rc = d_eti.reserve((size_t)n_eti * DABGPU_ETI_BYTES))) return rc;
-  uint8_t *hp = h_jobs.as<uint8_t>();
+  uint8_t *hp = h_msc.as<uint8_t>();
   memcpy(hp, cifjobs.data(), b_cif);
   memcpy(hp + b_cif, subjobs.data(), b_sub);
   memcpy(hp + b_cif + b_sub, etijobs.data(), b_eti);
@@ -321,6 +408,13 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   if ((rc = launch_eti_pack(de, d_ens.as<EnsDev>(), d_fibs.as<uint8_t>(), d_eti.as<uint8_t>(), n_eti, st)))
     return rc;
   t1(K_ETI, st);
+  cifjobs.clear();
+  subjobs.clear();
+  etijobs.clear();
+  pend_stream.clear();
+  vb_msc.clear();
+  row_base = 0;
+  pend_calls = 0;
   return DABGPU_OK;
 }
 
@@ -340,7 +434,7 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
     CUDA_TRY(cudaMemcpyAsync(d_tfbytes.p, tfs, (size_t)S * pitch, cudaMemcpyHostToDevice, st));
     d_tf = d_tfbytes.as<uint8_t>();
   }
-  // MSC bytes -> planes in the slot of the stream's current tfidx (dab.c:35: tfs[tfidx])
+  // MSC bytes -> planes in the physical slot that stands for tfs[tfidx] (dab.c:35)
   const int na = (int)active.size();
   n_eti = 0;
   eti_stream.clear();
@@ -350,7 +444,7 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
     if ((rc = d_planeoff.reserve((size_t)S * 4 * sizeof(uint64_t)))) return rc;
     uint64_t *off = h_ctl.as<uint64_t>();
     for (int s = 0; s < S; s++)
-      for (int k = 0; k < 4; k++) off[4 * s + k] = ((uint64_t)s * CIF_SLOTS + back[s].tfidx * 4 + k) * CIF_BYTES;
+      for (int k = 0; k < 4; k++) off[4 * s + k] = ((uint64_t)s * CIF_SLOTS + back[s].phys * 4 + k) * CIF_BYTES;
     CUDA_TRY(cudaMemcpyAsync(d_planeoff.p, off, (size_t)S * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if ((rc = launch_pack_planes(d_tf + 9216, pitch, d_planeoff.as<uint64_t>(), d_cifs.as<uint8_t>(), S, st)))
       return rc;
@@ -361,7 +455,7 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
     uint64_t *off = h_ctl.as<uint64_t>();
     for (int a = 0; a < na; a++)
       for (int k = 0; k < 4; k++)
-        off[4 * a + k] = ((uint64_t)active[a] * CIF_SLOTS + back[active[a]].tfidx * 4 + k) * CIF_BYTES;
+        off[4 * a + k] = ((uint64_t)active[a] * CIF_SLOTS + back[active[a]].phys * 4 + k) * CIF_BYTES;
     CUDA_TRY(cudaMemcpyAsync(d_planeoff.p, off, 4 * sizeof(uint64_t) * (size_t)na, cudaMemcpyHostToDevice, st));
     for (int a = 0; a < na; a++)
       if ((rc = launch_pack_planes(d_tf + (size_t)active[a] * pitch + 9216, pitch,
@@ -467,7 +561,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     c.run = 1;
     c.force_timesync = fr.force_timesync;
     for (int k = 0; k < 4; k++)
-      c.cif_off[k] = ((uint64_t)s * CIF_SLOTS + (uint64_t)back[s].tfidx * 4 + k) * CIF_BYTES;
+      c.cif_off[k] = ((uint64_t)s * CIF_SLOTS + (uint64_t)back[s].phys * 4 + k) * CIF_BYTES;
     fr.pending = true;
     active.push_back(s);
   }
@@ -605,4 +699,20 @@ DABGPU_EXPORT int dabgpu_engine_kernel_times(dabgpu_engine *h, double *ms_total,
 
 DABGPU_EXPORT void dabgpu_engine_host_times(dabgpu_engine *h, double *us4) {
   for (int i = 0; i < Engine::H_COUNT; i++) us4[i] = h->e.host_us[i];
+}
+
+DABGPU_EXPORT int dabgpu_engine_set_msc_batch(dabgpu_engine *h, int calls) {
+  if (calls < 1 || calls > PHYS_TF_SLOTS - 5 + 1) {
+    set_error(DABGPU_ERR_ARG, "msc batch depth must be 1..%d transmission frames", PHYS_TF_SLOTS - 5 + 1);
+    return DABGPU_ERR_ARG;
+  }
+  h->e.msc_batch = calls;
+  return DABGPU_OK;
+}
+DABGPU_EXPORT int dabgpu_engine_flush(dabgpu_engine *h) {
+  h->e.n_eti = 0;
+  h->e.eti_stream.clear();
+  int rc = h->e.flush_msc(current_stream());
+  if (rc) return rc;
+  return h->e.collect_timing(current_stream());
 }

@@ -3,6 +3,11 @@
 //      sdr_demod -> dab_process_frame -> tuner feedback
 // with the sample/bit arithmetic on the GPU and the per-stream control state on the host.
 #pragma once
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <vector>
 
 #include "hostlogic.cuh"
@@ -11,6 +16,26 @@
 #include "vitbatch.cuh"
 
 namespace dabgpu {
+
+// a few helper threads for the per-stream host state machines (streams are independent)
+class HostPool {
+ public:
+  ~HostPool() { stop(); }
+  void start(int n_threads);
+  void stop();
+  // fn(i) for i in [0, n); returns when all are done.  The calling thread takes part.
+  void run(int n, const std::function<void(int)> &fn);
+
+ private:
+  void worker();
+  std::vector<std::thread> th_;
+  std::mutex mu_;
+  std::condition_variable cv_, done_;
+  const std::function<void(int)> *fn_ = nullptr;
+  int n_ = 0, gen_ = 0, busy_ = 0;
+  std::atomic<int> next_{0};
+  bool quit_ = false;
+};
 
 // derived from a stream's ens_info whenever its sub-channel table changes
 struct EnsLayout {
@@ -69,7 +94,15 @@ struct Engine {
   DevBuf d_ens;       // EnsDev[S]
   DevBuf d_shapes, d_fic_shape;
   DevBuf d_cifjobs, d_subjobs, d_etijobs, d_planeoff, d_gather_idx, d_gather_out;
-  PinBuf h_ctl, h_sync, h_fic_out, h_jobs, h_eti, h_chunk;
+  PinBuf h_ctl, h_sync, h_fic_out, h_jobs, h_msc, h_eti, h_chunk;
+  HostPool pool;
+  std::vector<FrameWork> works;
+  // MSC decoding may lag by up to msc_batch calls so that one Viterbi launch covers several
+  // transmission frames per stream (more, better balanced work per launch)
+  int msc_batch = 1, pend_calls = 0;
+  uint64_t row_base = 0;
+  std::vector<int32_t> pend_stream;
+  int flush_msc(cudaStream_t st);
   VitBatch vb_fic, vb_msc;
 
   // optional per-kernel device timing (CUDA events on the launch stream), for bench.py's roofline

@@ -112,19 +112,28 @@ void BackendState::reset() {
   host_init_ens(&ens_info);
   memset(win, 0, sizeof win);
   ncifs = tfidx = locked = okcount = ens_info_shown = 0;
+  phys = 0;
   ens_version = 1;
 }
 
-static bool same_layout(const ens_info_t &a, const ens_info_t &b) {
+// misc.c:14-27, additionally reporting whether the sub-channel table changed
+static bool merge_and_diff(ens_info_t *ei, const tf_info_t *info) {
+  bool changed = false;
   for (int i = 0; i < 64; i++) {
-    const subchannel_info_t &x = a.subchans[i], &y = b.subchans[i];
-    if (x.id != y.id) return false;
-    if (x.id < 0) continue;
-    if (x.eepprot != y.eepprot || x.slForm != y.slForm || x.uep_index != y.uep_index ||
+    const subchannel_info_t &y = info->subchans[i];
+    if (y.id < 0) continue;
+    subchannel_info_t &x = ei->subchans[i];
+    if (x.id != y.id || x.eepprot != y.eepprot || x.slForm != y.slForm || x.uep_index != y.uep_index ||
         x.start_cu != y.start_cu || x.size != y.size || x.bitrate != y.bitrate || x.protlev != y.protlev)
-      return false;
+      changed = true;
+    x = y;
   }
-  return true;
+  ei->EId = info->EId;
+  if (ei->CIFCount_hi == 0xff) {
+    ei->CIFCount_hi = info->CIFCount_hi;
+    ei->CIFCount_lo = info->CIFCount_lo;
+  }
+  return changed;
 }
 
 // dab.c:35-99
@@ -152,12 +161,10 @@ void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *cr
   }
   if (!st.locked) return;
 
-  const ens_info_t before = st.ens_info;
-  host_merge_info(&st.ens_info, &st.tf_info);
-  if (!same_layout(before, st.ens_info)) st.ens_version++;
+  if (merge_and_diff(&st.ens_info, &st.tf_info)) st.ens_version++;
 
   if (st.ncifs < 16) {
-    for (int k = 0; k < 4; k++) st.win[st.ncifs++] = st.tfidx * 4 + k;
+    for (int k = 0; k < 4; k++) st.win[st.ncifs++] = st.phys * 4 + k;
   } else {
     if (!st.ens_info_shown) {
       if (!quiet) dump_ens_info(&st.ens_info);
@@ -174,10 +181,11 @@ void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *cr
         if (++st.ens_info.CIFCount_hi == 20) st.ens_info.CIFCount_hi = 0;
       }
       memmove(st.win, st.win + 1, 15 * sizeof(int));
-      st.win[15] = st.tfidx * 4 + k;
+      st.win[15] = st.phys * 4 + k;
     }
   }
   st.tfidx = (st.tfidx + 1) % 5;
+  st.phys = (st.phys + 1) % PHYS_TF_SLOTS;
 }
 
 }  // namespace dabgpu

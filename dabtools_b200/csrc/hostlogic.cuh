@@ -24,13 +24,17 @@ struct GlibcRand {
   int next();
 };
 
+enum { PHYS_TF_SLOTS = 8 };  // 5 referenced by the window + 3 of slack for deferred MSC batches
+
 // per-stream back-end state: dab_state_t without the 1.2 MB of frame buffers, which
 // live on the device (dab.h:70-89)
 struct BackendState {
   tf_info_t tf_info;
   ens_info_t ens_info;
-  int win[16];      // CIF store slots (tf*4+cif) of the 16-CIF window, [0] oldest
+  int win[16];      // physical CIF store slots (phys_tf*4+cif) of the 16-CIF window, [0] oldest
   int ncifs, tfidx, locked, okcount, ens_info_shown;
+  int phys;         // physical TF slot the incoming frame is written to; advances with tfidx but
+                    // over a deeper ring (PHYS_TF_SLOTS) so that MSC decoding can lag behind
   uint64_t ens_version;  // bumped whenever ens_info's sub-channel table changes
   void reset();
 };

@@ -175,19 +175,33 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut
       acc = 0;
     }
   }
+  // main loop: 32 bits per iteration in two halves of 16; the decision words of the next half are
+  // loaded while the current ones are walked (their addresses do not depend on the survivor state)
+  uint2 d[16];
+  if (i >= 31) {
+#pragma unroll
+    for (int j = 0; j < 16; j++) d[j] = decp[(size_t)(i - j + 6) * 32];
+  }
   for (; i >= 31; i -= 32) {
-    uint2 d[8];
+    uint2 n[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++) n[j] = decp[(size_t)(i - 16 - j + 6) * 32];
     acc = 0;
 #pragma unroll
-    for (int blk = 0; blk < 4; blk++) {
+    for (int j = 0; j < 16; j++) {
+      const uint32_t bit = decision_bit(d[j], state);
+      acc |= bit << j;  // bit index (i - j) & 31 = 31 - j
+      state = (state >> 1) | (bit << 5);
+    }
+    if (i >= 63) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) d[j] = decp[(size_t)(i - 8 * blk - j + 6) * 32];
+      for (int j = 0; j < 16; j++) d[j] = decp[(size_t)(i - 32 - j + 6) * 32];
+    }
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        const uint32_t bit = decision_bit(d[j], state);
-        acc |= bit << (8 * blk + j);  // bit index (i - 8blk - j) & 31 = 31 - (8blk+j)
-        state = (state >> 1) | (bit << 5);
-      }
+    for (int j = 0; j < 16; j++) {
+      const uint32_t bit = decision_bit(n[j], state);
+      acc |= bit << (16 + j);
+      state = (state >> 1) | (bit << 5);
     }
     uint32_t w = prmt(acc, 0u, 0x0123u);
     if (scr) w ^= c_prbs_le[i >> 5];

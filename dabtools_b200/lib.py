@@ -250,3 +250,18 @@ def _engine_host_times(self) -> dict:
 
 
 Engine.host_times = _engine_host_times
+
+
+def _engine_set_msc_batch(self, calls: int):
+    self._lib.dabgpu_engine_set_msc_batch.argtypes = [C.c_void_p, C.c_int]
+    check(self._lib.dabgpu_engine_set_msc_batch(self._h, calls))
+
+
+def _engine_flush(self) -> int:
+    self._lib.dabgpu_engine_flush.argtypes = [C.c_void_p]
+    check(self._lib.dabgpu_engine_flush(self._h))
+    return self._lib.dabgpu_engine_eti_count(self._h)
+
+
+Engine.set_msc_batch = _engine_set_msc_batch
+Engine.flush = _engine_flush

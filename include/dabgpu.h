@@ -113,7 +113,13 @@ int dabgpu_engine_feed_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int
  * equivalent to dab_process_frame per stream. */
 int dabgpu_engine_process_demapped(dabgpu_engine *e, const uint8_t *tfs, size_t pitch, const uint8_t *mask,
                                    int on_device);
-/* ETI frames produced by the last feed/process call (0 or 4 per stream), in stream order. */
+/* Let the MSC decoding (time de-interleave -> Viterbi -> ETI) lag so that one launch covers the
+ * frames of `calls` (1..4) frame-producing feed/process calls: more, better balanced work per
+ * launch; frames then come out in bursts.  dabgpu_engine_flush() decodes whatever is queued (call
+ * it at the end of a capture); its frames are then reported by eti_count()/fetch_eti(). */
+int dabgpu_engine_set_msc_batch(dabgpu_engine *e, int calls);
+int dabgpu_engine_flush(dabgpu_engine *e);
+/* ETI frames produced by the last feed/process/flush call, in call order, then stream order. */
 int dabgpu_engine_eti_count(dabgpu_engine *e);
 const uint8_t *dabgpu_engine_eti_device(dabgpu_engine *e);
 /* copies up to max_frames frames (6144 bytes each) and their stream indices to the host;

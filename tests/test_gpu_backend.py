@@ -11,13 +11,14 @@ from dabtools_b200 import synth
 pytestmark = pytest.mark.gpu
 
 
-def _run_engine(gpu, bits):
+def _run_engine(gpu, bits, msc_batch=1):
     """bits: [S][n_tf][230400] -> list of per-stream ETI arrays"""
     S, n_tf = bits.shape[0], bits.shape[1]
     eng = gpu.Engine(S)
+    eng.set_msc_batch(msc_batch)
     out = [[] for _ in range(S)]
-    for t in range(n_tf):
-        n = eng.process_demapped(bits[:, t])
+    for t in range(n_tf + 1):
+        n = eng.process_demapped(bits[:, t]) if t < n_tf else eng.flush()
         eti, ids = eng.fetch_eti()
         assert eti.shape[0] == n
         for f, s in zip(eti, ids):
@@ -50,6 +51,23 @@ def test_backend_eti_matches_oracle(gpu, port, ens_name, flip):
         off = 12 + 4 * nst + 96
         body = got[0][0][off: off + ens.bytes_per_cif].tobytes()
         assert body == synth.expected_eti_payload(ens, g["payload"], 0, 36)
+
+
+@pytest.mark.parametrize("batch", [2, 3, 4])
+def test_deferred_msc_batches_give_identical_frames(gpu, port, batch):
+    """MSC decoding lagging by up to 4 TFs (one Viterbi launch per batch) must not change a byte,
+    including across a lock loss while frames are still queued."""
+    ens = synth.reference_ensemble()
+    S, n_tf = 2, 24
+    g = synth.ModeITransmitter(ens).generate(S, n_tf, seed=31, want_iq=False)
+    bits = g["bits"].numpy().copy()
+    rng = np.random.default_rng(2)
+    bits ^= (rng.random(bits.shape) < 0.03).astype(np.uint8)
+    bits[1, 17, :9216] ^= (rng.random(9216) < 0.3).astype(np.uint8)
+    got, _ = _run_engine(gpu, bits, msc_batch=batch)
+    for s in range(S):
+        want, _, _ = port.run_backend(bits[s])
+        assert got[s].shape == want.shape and np.array_equal(got[s], want), (batch, s)
 
 
 def test_backend_golden(gpu):

@@ -18,6 +18,7 @@ lib.use_torch_stream()
 setup = bench.SETUP_TFS // 2
 data, ens = bench.generate_dataset(S, 2 * (setup + 1 + NPROF), torch.device("cuda", 0), seed=1)
 eng = lib.Engine(S)
+eng.set_msc_batch(2)
 step_bytes = 3 * bench.CALL_BYTES
 
 
