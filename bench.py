@@ -224,6 +224,7 @@ def run_ours(args, rank, world, local_rank):
     base = setup_steps + W
     for i in range(K):
         frames += step_device(eng, base + i)
+    eng.join()   # the MSC stream's last batch belongs to the timed region
     e1.record()
     barrier()
     clocks = sampler.stop() if rank == 0 else None

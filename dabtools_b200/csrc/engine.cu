@@ -116,6 +116,10 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   if ((rc = d_ens.reserve((size_t)S * sizeof(EnsDev)))) return rc;
   if ((rc = d_gather_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
   if ((rc = h_fic_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
+  CUDA_TRY(cudaStreamCreateWithFlags(&st_msc, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_up[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_up[1], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_msc_done, cudaEventDisableTiming));
   CUDA_TRY(cudaMemset(d_cifs.p, 0, (size_t)S * CIF_SLOTS * CIF_BYTES));
   CUDA_TRY(cudaMemset(d_fibs.p, 0, (size_t)S * TF_SLOTS * FIBS_PER_TF));
   dabgpu_cw_shape fs;
@@ -144,6 +148,7 @@ int Engine::enable_timing(bool on) {
 int Engine::collect_timing(cudaStream_t st) {
   if (!timing) return DABGPU_OK;
   CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaStreamSynchronize(st_msc));
   for (int k = 0; k < K_COUNT; k++) {
     if (!ev_used[k]) continue;
     float ms = 0;
@@ -155,8 +160,22 @@ int Engine::collect_timing(cudaStream_t st) {
   return DABGPU_OK;
 }
 
+int Engine::join_msc(cudaStream_t user) {
+  if (!msc_inflight) return DABGPU_OK;
+  CUDA_TRY(cudaStreamWaitEvent(user, ev_msc_done, 0));
+  return DABGPU_OK;
+}
+
 void Engine::destroy() {
   pool.stop();
+  if (st_msc) {
+    cudaStreamSynchronize(st_msc);
+    cudaStreamDestroy(st_msc);
+    st_msc = nullptr;
+    cudaEventDestroy(ev_up[0]);
+    cudaEventDestroy(ev_up[1]);
+    cudaEventDestroy(ev_msc_done);
+  }
   if (ev[0][0])
     for (int k = 0; k < K_COUNT; k++)
       for (int j = 0; j < 2; j++) cudaEventDestroy(ev[k][j]);
@@ -164,7 +183,7 @@ void Engine::destroy() {
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
                   &d_subjobs, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
   for (DevBuf *b : db) b->release();
-  PinBuf *pb[] = {&h_ctl, &h_sync, &h_fic_out, &h_jobs, &h_msc, &h_eti, &h_chunk};
+  PinBuf *pb[] = {&h_ctl, &h_sync, &h_fic_out, &h_jobs, &h_msc[0], &h_msc[1], &h_eti, &h_chunk};
   for (PinBuf *b : pb) b->release();
   vb_fic.release();
   vb_msc.release();
@@ -223,9 +242,9 @@ int Engine::refresh_layout(int s) {
   L.dev.nst = nst;
   L.dev.fl = fl + nst + 1 + 24;
   L.dev.payload = payload;
-  CUDA_TRY(cudaMemcpyAsync(d_ens.as<EnsDev>() + s, &L.dev, sizeof(EnsDev), cudaMemcpyHostToDevice,
-                           current_stream()));
-  // L.dev lives in this object, and is not modified again before the next sync of the step
+  // consumed by eti_pack on the MSC stream; L.dev lives in this object and only changes here
+  CUDA_TRY(cudaStreamSynchronize(st_msc));
+  CUDA_TRY(cudaMemcpyAsync(d_ens.as<EnsDev>() + s, &L.dev, sizeof(EnsDev), cudaMemcpyHostToDevice, st_msc));
   return DABGPU_OK;
 }
 
@@ -324,32 +343,25 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   host_us[H_FSM] += now_us() - tw;
   tw = now_us();
 
-  // ---- queue the ETI frames of this call (sequential: offsets are prefix sums) ----
+  // ---- queue the ETI frames of this call ----
   bool any = false;
   for (int a = 0; a < na; a++) {
     const FrameWork &work = works[a];
     if (!work.n_eti) continue;
     const int s = active[a];
-    if ((rc = refresh_layout(s))) return rc;
-    const EnsLayout &L = layout[s];
+    if (layout[s].version != back[s].ens_version) {
+      // the multiplex description changed: frames already queued use the old layout
+      if (!etijobs.empty() && (rc = flush_msc(st))) return rc;
+      if ((rc = refresh_layout(s))) return rc;
+    }
     any = true;
     for (int k = 0; k < work.n_eti; k++) {
-      const int f = (int)etijobs.size();
       pend_stream.push_back(s);
+      pend_sig = (pend_sig ^ (uint64_t)(uint32_t)s ^ (layout[s].version << 32)) * 0x100000001b3ull;
       CifJob cj;
       for (int j = 0; j < 16; j++)
         cj.slot_off[j] = ((uint64_t)s * CIF_SLOTS + (uint64_t)work.win[k][j]) * CIF_BYTES;
-      cj.sub0 = (uint32_t)subjobs.size();
-      cj.nsub = (uint32_t)L.nsub;
-      for (int u = 0; u < L.nsub; u++) {
-        SubJob sj;
-        sj.row_off = row_base + L.sub[u].row_off;
-        sj.in_bit0 = L.sub[u].in_bit0;
-        sj.shape = L.sub[u].shape;
-        subjobs.push_back(sj);
-        vb_msc.add(sj.row_off, (uint64_t)f * DABGPU_ETI_BYTES + L.sub[u].eti_off, L.sub[u].nbits, VIT_DESCRAMBLE);
-      }
-      row_base += L.rows_bytes;
+      cj.sub0 = cj.nsub = 0;  // filled in at flush time
       cifjobs.push_back(cj);
       EtiJob ej;
       const int w0 = work.win[k][0];
@@ -368,32 +380,72 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
 }
 
 // MSC of everything queued: time de-interleave + depuncture gather -> Viterbi + descramble -> ETI
-int Engine::flush_msc(cudaStream_t st) {
+int Engine::flush_msc(cudaStream_t user) {
   int rc;
+  (void)user;
   if (etijobs.empty()) {
     pend_calls = 0;
     return DABGPU_OK;
   }
   const double tw = now_us();
+  cudaStream_t st = st_msc;
+  // bound the lag of the MSC stream: the previous batch must be done before the next one is
+  // queued, which keeps every CIF/FIB slot a queued batch references out of the front-end's reach
+  if (msc_inflight) CUDA_TRY(cudaEventSynchronize(ev_msc_done));
   n_eti = (int)etijobs.size();
   eti_stream.assign(pend_stream.begin(), pend_stream.end());
+  // The per-sub-channel job lists only depend on which streams produced frames and on their
+  // multiplex layouts: in the steady state of locked receivers they repeat from flush to flush and
+  // the device copies (and the Viterbi plan) are reused as they are.
+  const bool reuse = pend_sig == cached_sig && (size_t)n_eti == frame_sub0.size() && !subjobs.empty();
+  if (!reuse) {
+    subjobs.clear();
+    frame_sub0.clear();
+    vb_msc.clear();
+    row_base = 0;
+    for (int f = 0; f < n_eti; f++) {
+      const EnsLayout &L = layout[pend_stream[f]];
+      frame_sub0.push_back((uint32_t)subjobs.size());
+      for (int u = 0; u < L.nsub; u++) {
+        SubJob sj;
+        sj.row_off = row_base + L.sub[u].row_off;
+        sj.in_bit0 = L.sub[u].in_bit0;
+        sj.shape = L.sub[u].shape;
+        subjobs.push_back(sj);
+        vb_msc.add(sj.row_off, (uint64_t)f * DABGPU_ETI_BYTES + L.sub[u].eti_off, L.sub[u].nbits, VIT_DESCRAMBLE);
+      }
+      row_base += L.rows_bytes;
+    }
+    cached_sig = pend_sig;
+  }
+  for (int f = 0; f < n_eti; f++) {
+    cifjobs[f].sub0 = frame_sub0[f];
+    cifjobs[f].nsub = (uint32_t)layout[pend_stream[f]].nsub;
+  }
   if ((rc = upload_tables(st))) return rc;
-  const size_t b_cif = cifjobs.size() * sizeof(CifJob), b_sub = subjobs.size() * sizeof(SubJob),
-               b_eti = etijobs.size() * sizeof(EtiJob);
-  // the pinned staging area may still be read by the copy of the previous flush
-  CUDA_TRY(cudaStreamSynchronize(st));
-  if ((rc = h_msc.reserve(b_cif + b_sub + b_eti))) return rc;
-  if ((rc = d_cifjobs.reserve(b_cif + b_sub + b_eti))) return rc;
+  const size_t b_cif = cifjobs.size() * sizeof(CifJob), b_eti = etijobs.size() * sizeof(EtiJob),
+               b_sub = subjobs.size() * sizeof(SubJob);
+  // two pinned staging areas alternate; each is free again once its upload has completed
+  PinBuf &hm = h_msc[msc_buf];
+  CUDA_TRY(cudaEventSynchronize(ev_up[msc_buf]));
+  if ((rc = hm.reserve(b_cif + b_eti + (reuse ? 0 : b_sub)))) return rc;
+  if ((rc = d_cifjobs.reserve(b_cif + b_eti))) return rc;
+  if ((rc = d_subjobs.reserve(b_sub))) return rc;
   if ((rc = d_steps_msc.reserve(row_base + 64))) return rc;
   if ((rc = d_eti.reserve((size_t)n_eti * DABGPU_ETI_BYTES))) return rc;
-  uint8_t *hp = h_msc.as<uint8_t>();
+  uint8_t *hp = hm.as<uint8_t>();
   memcpy(hp, cifjobs.data(), b_cif);
-  memcpy(hp + b_cif, subjobs.data(), b_sub);
-  memcpy(hp + b_cif + b_sub, etijobs.data(), b_eti);
-  CUDA_TRY(cudaMemcpyAsync(d_cifjobs.p, hp, b_cif + b_sub + b_eti, cudaMemcpyHostToDevice, st));
+  memcpy(hp + b_cif, etijobs.data(), b_eti);
+  CUDA_TRY(cudaMemcpyAsync(d_cifjobs.p, hp, b_cif + b_eti, cudaMemcpyHostToDevice, st));
+  if (!reuse) {
+    memcpy(hp + b_cif + b_eti, subjobs.data(), b_sub);
+    CUDA_TRY(cudaMemcpyAsync(d_subjobs.p, hp + b_cif + b_eti, b_sub, cudaMemcpyHostToDevice, st));
+  }
+  CUDA_TRY(cudaEventRecord(ev_up[msc_buf], st));
+  msc_buf ^= 1;
   const CifJob *dj = d_cifjobs.as<CifJob>();
-  const SubJob *ds = reinterpret_cast<const SubJob *>(d_cifjobs.as<uint8_t>() + b_cif);
-  const EtiJob *de = reinterpret_cast<const EtiJob *>(d_cifjobs.as<uint8_t>() + b_cif + b_sub);
+  const SubJob *ds = d_subjobs.as<SubJob>();
+  const EtiJob *de = reinterpret_cast<const EtiJob *>(d_cifjobs.as<uint8_t>() + b_cif);
   host_us[H_JOBS] += now_us() - tw;
   t0(K_MSC_GATHER, st);
   if ((rc = launch_msc_gather(d_cifs.as<uint8_t>(), dj, ds, d_shapes.as<ShapeDev>(), d_steps_msc.as<uint8_t>(),
@@ -401,19 +453,21 @@ int Engine::flush_msc(cudaStream_t st) {
     return rc;
   t1(K_MSC_GATHER, st);
   t0(K_MSC_VIT, st);
-  if ((rc = vb_msc.run(d_steps_msc.as<uint8_t>(), d_eti.as<uint8_t>(), st))) return rc;
+  if ((rc = reuse ? vb_msc.relaunch(d_steps_msc.as<uint8_t>(), d_eti.as<uint8_t>(), st)
+                  : vb_msc.run(d_steps_msc.as<uint8_t>(), d_eti.as<uint8_t>(), st)))
+    return rc;
   t1(K_MSC_VIT, st);
   trellis_steps += vb_msc.total_steps;
   t0(K_ETI, st);
   if ((rc = launch_eti_pack(de, d_ens.as<EnsDev>(), d_fibs.as<uint8_t>(), d_eti.as<uint8_t>(), n_eti, st)))
     return rc;
   t1(K_ETI, st);
+  CUDA_TRY(cudaEventRecord(ev_msc_done, st));
+  msc_inflight = true;
   cifjobs.clear();
-  subjobs.clear();
   etijobs.clear();
   pend_stream.clear();
-  vb_msc.clear();
-  row_base = 0;
+  pend_sig = 0xcbf29ce484222325ull;
   pend_calls = 0;
   return DABGPU_OK;
 }
@@ -644,7 +698,7 @@ DABGPU_EXPORT int dabgpu_engine_fetch_eti(dabgpu_engine *h, uint8_t *eti, int32_
   Engine &e = h->e;
   const int n = std::min(e.n_eti, max_frames);
   if (n <= 0) return 0;
-  cudaStream_t st = current_stream();
+  cudaStream_t st = e.st_msc;
   if (eti) {
     cudaError_t err = cudaMemcpyAsync(eti, e.d_eti.p, (size_t)n * DABGPU_ETI_BYTES, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
@@ -702,8 +756,8 @@ DABGPU_EXPORT void dabgpu_engine_host_times(dabgpu_engine *h, double *us4) {
 }
 
 DABGPU_EXPORT int dabgpu_engine_set_msc_batch(dabgpu_engine *h, int calls) {
-  if (calls < 1 || calls > PHYS_TF_SLOTS - 5 + 1) {
-    set_error(DABGPU_ERR_ARG, "msc batch depth must be 1..%d transmission frames", PHYS_TF_SLOTS - 5 + 1);
+  if (calls < 1 || calls > MAX_MSC_BATCH) {
+    set_error(DABGPU_ERR_ARG, "msc batch depth must be 1..%d transmission frames", MAX_MSC_BATCH);
     return DABGPU_ERR_ARG;
   }
   h->e.msc_batch = calls;
@@ -716,3 +770,7 @@ DABGPU_EXPORT int dabgpu_engine_flush(dabgpu_engine *h) {
   if (rc) return rc;
   return h->e.collect_timing(current_stream());
 }
+
+/* make the caller's stream (dabgpu_set_stream) wait for the MSC/ETI work issued so far, e.g.
+ * before recording an event that should cover it or before reading dabgpu_engine_eti_device() */
+DABGPU_EXPORT int dabgpu_engine_join(dabgpu_engine *h) { return h->e.join_msc(current_stream()); }

@@ -94,7 +94,13 @@ struct Engine {
   DevBuf d_ens;       // EnsDev[S]
   DevBuf d_shapes, d_fic_shape;
   DevBuf d_cifjobs, d_subjobs, d_etijobs, d_planeoff, d_gather_idx, d_gather_out;
-  PinBuf h_ctl, h_sync, h_fic_out, h_jobs, h_msc, h_eti, h_chunk;
+  PinBuf h_ctl, h_sync, h_fic_out, h_jobs, h_msc[2], h_eti, h_chunk;
+  // MSC work runs on its own stream so that it overlaps the next frames' front-end kernels
+  cudaStream_t st_msc = nullptr;
+  cudaEvent_t ev_up[2] = {}, ev_msc_done = nullptr;
+  int msc_buf = 0;
+  bool msc_inflight = false;
+  int join_msc(cudaStream_t user);  // make `user` wait for all MSC work issued so far
   HostPool pool;
   std::vector<FrameWork> works;
   // MSC decoding may lag by up to msc_batch calls so that one Viterbi launch covers several
@@ -102,6 +108,8 @@ struct Engine {
   int msc_batch = 1, pend_calls = 0;
   uint64_t row_base = 0;
   std::vector<int32_t> pend_stream;
+  std::vector<uint32_t> frame_sub0;  // first SubJob of every frame of the cached job list
+  uint64_t pend_sig = 0xcbf29ce484222325ull, cached_sig = 0;
   int flush_msc(cudaStream_t st);
   VitBatch vb_fic, vb_msc;
 

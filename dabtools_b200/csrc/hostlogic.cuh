@@ -24,7 +24,10 @@ struct GlibcRand {
   int next();
 };
 
-enum { PHYS_TF_SLOTS = 8 };  // 5 referenced by the window + 3 of slack for deferred MSC batches
+// The reference keeps 5 TF buffers (4 in the window + the incoming one).  The device store is a
+// deeper ring because MSC decoding is batched over up to D = 4 TFs and runs asynchronously to the
+// front-end: a batch references D + 4 slots while up to D newer frames are being written.
+enum { PHYS_TF_SLOTS = 12, MAX_MSC_BATCH = 4 };
 
 // per-stream back-end state: dab_state_t without the 1.2 MB of frame buffers, which
 // live on the device (dab.h:70-89)

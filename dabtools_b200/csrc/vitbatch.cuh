@@ -115,6 +115,11 @@ struct VitBatch {
     return launch_viterbi(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
                           d_bins.as<uint32_t>(), n_ctas, st);
   }
+  // launch again with the descriptors of the last run() (identical job list by construction)
+  int relaunch(const uint8_t *d_steps, uint8_t *d_out, cudaStream_t st) {
+    return launch_viterbi(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
+                          d_bins.as<uint32_t>(), n_ctas, st);
+  }
   void release() {
     d_jobs.release();
     d_groups.release();

@@ -265,3 +265,11 @@ def _engine_flush(self) -> int:
 
 Engine.set_msc_batch = _engine_set_msc_batch
 Engine.flush = _engine_flush
+
+
+def _engine_join(self):
+    self._lib.dabgpu_engine_join.argtypes = [C.c_void_p]
+    check(self._lib.dabgpu_engine_join(self._h))
+
+
+Engine.join = _engine_join

@@ -119,6 +119,11 @@ int dabgpu_engine_process_demapped(dabgpu_engine *e, const uint8_t *tfs, size_t 
  * it at the end of a capture); its frames are then reported by eti_count()/fetch_eti(). */
 int dabgpu_engine_set_msc_batch(dabgpu_engine *e, int calls);
 int dabgpu_engine_flush(dabgpu_engine *e);
+/* MSC decoding and ETI assembly run on an internal stream so that they overlap the next frames'
+ * front-end kernels.  dabgpu_engine_join() makes the caller's stream (dabgpu_set_stream) wait for
+ * everything issued so far -- needed before reading dabgpu_engine_eti_device() from that stream or
+ * before recording an event that should cover the work; dabgpu_engine_fetch_eti() waits by itself. */
+int dabgpu_engine_join(dabgpu_engine *e);
 /* ETI frames produced by the last feed/process/flush call, in call order, then stream order. */
 int dabgpu_engine_eti_count(dabgpu_engine *e);
 const uint8_t *dabgpu_engine_eti_device(dabgpu_engine *e);
