@@ -112,7 +112,10 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   if ((rc = d_fibs.reserve((size_t)S * TF_SLOTS * FIBS_PER_TF))) return rc;
   if ((rc = d_ficbits.reserve((size_t)S * 9216))) return rc;
   if ((rc = d_steps_fic.reserve((size_t)S * 4 * FIC_ROW))) return rc;
-  if ((rc = d_eti.reserve((size_t)S * 4 * 4 * DABGPU_ETI_BYTES))) return rc;  // up to 4 TFs per flush
+  // ETI output of one call: up to MAX_MSC_BATCH TFs per flush, plus one extra TF for the rare
+  // call that has to flush twice
+  if ((rc = d_eti.reserve((size_t)S * 4 * (MAX_MSC_BATCH + 1) * DABGPU_ETI_BYTES))) return rc;
+  pend_of_stream.assign(S, 0);
   if ((rc = d_ens.reserve((size_t)S * sizeof(EnsDev)))) return rc;
   if ((rc = d_gather_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
   if ((rc = h_fic_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
@@ -350,13 +353,15 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
     if (!work.n_eti) continue;
     const int s = active[a];
     if (layout[s].version != back[s].ens_version) {
-      // the multiplex description changed: frames already queued use the old layout
-      if (!etijobs.empty() && (rc = flush_msc(st))) return rc;
+      // the multiplex description changed: frames of this stream that are still queued were
+      // produced under the old layout and must be decoded first
+      if (pend_of_stream[s] && (rc = flush_msc(st))) return rc;
       if ((rc = refresh_layout(s))) return rc;
     }
     any = true;
     for (int k = 0; k < work.n_eti; k++) {
       pend_stream.push_back(s);
+      pend_of_stream[s]++;
       pend_sig = (pend_sig ^ (uint64_t)(uint32_t)s ^ (layout[s].version << 32)) * 0x100000001b3ull;
       CifJob cj;
       for (int j = 0; j < 16; j++)
@@ -392,18 +397,21 @@ int Engine::flush_msc(cudaStream_t user) {
   // bound the lag of the MSC stream: the previous batch must be done before the next one is
   // queued, which keeps every CIF/FIB slot a queued batch references out of the front-end's reach
   if (msc_inflight) CUDA_TRY(cudaEventSynchronize(ev_msc_done));
-  n_eti = (int)etijobs.size();
-  eti_stream.assign(pend_stream.begin(), pend_stream.end());
+  // several flushes inside one call (rare: a multiplex change) append to the call's output
+  const int base = n_eti, n_new = (int)etijobs.size();
+  n_eti = base + n_new;
+  eti_stream.insert(eti_stream.end(), pend_stream.begin(), pend_stream.end());
+  pend_sig = (pend_sig ^ (uint64_t)base) * 0x100000001b3ull;
   // The per-sub-channel job lists only depend on which streams produced frames and on their
   // multiplex layouts: in the steady state of locked receivers they repeat from flush to flush and
   // the device copies (and the Viterbi plan) are reused as they are.
-  const bool reuse = pend_sig == cached_sig && (size_t)n_eti == frame_sub0.size() && !subjobs.empty();
+  const bool reuse = pend_sig == cached_sig && (size_t)n_new == frame_sub0.size() && !subjobs.empty();
   if (!reuse) {
     subjobs.clear();
     frame_sub0.clear();
     vb_msc.clear();
     row_base = 0;
-    for (int f = 0; f < n_eti; f++) {
+    for (int f = 0; f < n_new; f++) {
       const EnsLayout &L = layout[pend_stream[f]];
       frame_sub0.push_back((uint32_t)subjobs.size());
       for (int u = 0; u < L.nsub; u++) {
@@ -412,13 +420,14 @@ int Engine::flush_msc(cudaStream_t user) {
         sj.in_bit0 = L.sub[u].in_bit0;
         sj.shape = L.sub[u].shape;
         subjobs.push_back(sj);
-        vb_msc.add(sj.row_off, (uint64_t)f * DABGPU_ETI_BYTES + L.sub[u].eti_off, L.sub[u].nbits, VIT_DESCRAMBLE);
+        vb_msc.add(sj.row_off, (uint64_t)(base + f) * DABGPU_ETI_BYTES + L.sub[u].eti_off, L.sub[u].nbits,
+                   VIT_DESCRAMBLE);
       }
       row_base += L.rows_bytes;
     }
     cached_sig = pend_sig;
   }
-  for (int f = 0; f < n_eti; f++) {
+  for (int f = 0; f < n_new; f++) {
     cifjobs[f].sub0 = frame_sub0[f];
     cifjobs[f].nsub = (uint32_t)layout[pend_stream[f]].nsub;
   }
@@ -432,7 +441,10 @@ int Engine::flush_msc(cudaStream_t user) {
   if ((rc = d_cifjobs.reserve(b_cif + b_eti))) return rc;
   if ((rc = d_subjobs.reserve(b_sub))) return rc;
   if ((rc = d_steps_msc.reserve(row_base + 64))) return rc;
-  if ((rc = d_eti.reserve((size_t)n_eti * DABGPU_ETI_BYTES))) return rc;
+  if ((size_t)n_eti * DABGPU_ETI_BYTES > d_eti.cap) {
+    set_error(DABGPU_ERR_STATE, "engine: more ETI frames in one call than the output store holds");
+    return DABGPU_ERR_STATE;
+  }
   uint8_t *hp = hm.as<uint8_t>();
   memcpy(hp, cifjobs.data(), b_cif);
   memcpy(hp + b_cif, etijobs.data(), b_eti);
@@ -449,7 +461,7 @@ int Engine::flush_msc(cudaStream_t user) {
   host_us[H_JOBS] += now_us() - tw;
   t0(K_MSC_GATHER, st);
   if ((rc = launch_msc_gather(d_cifs.as<uint8_t>(), dj, ds, d_shapes.as<ShapeDev>(), d_steps_msc.as<uint8_t>(),
-                              n_eti, st)))
+                              n_new, st)))
     return rc;
   t1(K_MSC_GATHER, st);
   t0(K_MSC_VIT, st);
@@ -459,13 +471,15 @@ int Engine::flush_msc(cudaStream_t user) {
   t1(K_MSC_VIT, st);
   trellis_steps += vb_msc.total_steps;
   t0(K_ETI, st);
-  if ((rc = launch_eti_pack(de, d_ens.as<EnsDev>(), d_fibs.as<uint8_t>(), d_eti.as<uint8_t>(), n_eti, st)))
+  if ((rc = launch_eti_pack(de, d_ens.as<EnsDev>(), d_fibs.as<uint8_t>(),
+                            d_eti.as<uint8_t>() + (size_t)base * DABGPU_ETI_BYTES, n_new, st)))
     return rc;
   t1(K_ETI, st);
   CUDA_TRY(cudaEventRecord(ev_msc_done, st));
   msc_inflight = true;
   cifjobs.clear();
   etijobs.clear();
+  for (int32_t ps : pend_stream) pend_of_stream[ps] = 0;
   pend_stream.clear();
   pend_sig = 0xcbf29ce484222325ull;
   pend_calls = 0;

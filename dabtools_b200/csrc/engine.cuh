@@ -108,6 +108,7 @@ struct Engine {
   int msc_batch = 1, pend_calls = 0;
   uint64_t row_base = 0;
   std::vector<int32_t> pend_stream;
+  std::vector<int> pend_of_stream;   // queued frames per stream
   std::vector<uint32_t> frame_sub0;  // first SubJob of every frame of the cached job list
   uint64_t pend_sig = 0xcbf29ce484222325ull, cached_sig = 0;
   int flush_msc(cudaStream_t st);
