@@ -28,6 +28,8 @@
 // symbols occur) come from a 256-entry shared-memory table indexed by the step byte.
 #include "viterbi.cuh"
 
+#include <algorithm>
+
 namespace dabgpu {
 
 __constant__ uint32_t c_prbs_le[288];  // 1152 PRBS bytes as little-endian words
@@ -175,50 +177,60 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut
       acc = 0;
     }
   }
-  // main loop: 32 bits per iteration in two halves of 16; the decision words of the next half are
-  // loaded while the current ones are walked (their addresses do not depend on the survivor state)
-  uint2 d[16];
-  if (i >= 31) {
+  // main loop: 16 bits per half-iteration; the decision words are fetched two half-iterations
+  // ahead (their addresses do not depend on the survivor state), so ~32 loads per lane are in
+  // flight while 16 are being walked
+  if (i < 31) return;
+  const uint2 *dp = decp + (size_t)6 * 32;  // dp[step * 32] = decisions of trellis step `step`+6
+  uint2 b0[16], b1[16];
 #pragma unroll
-    for (int j = 0; j < 16; j++) d[j] = decp[(size_t)(i - j + 6) * 32];
-  }
+  for (int j = 0; j < 16; j++) b0[j] = dp[(size_t)(i - j) * 32];
+#pragma unroll
+  for (int j = 0; j < 16; j++) b1[j] = dp[(size_t)(i - 16 - j) * 32];
   for (; i >= 31; i -= 32) {
-    uint2 n[16];
+    uint2 b2[16];
+    if (i >= 63) {
 #pragma unroll
-    for (int j = 0; j < 16; j++) n[j] = decp[(size_t)(i - 16 - j + 6) * 32];
+      for (int j = 0; j < 16; j++) b2[j] = dp[(size_t)(i - 32 - j) * 32];
+    }
     acc = 0;
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      const uint32_t bit = decision_bit(d[j], state);
+      const uint32_t bit = decision_bit(b0[j], state);
       acc |= bit << j;  // bit index (i - j) & 31 = 31 - j
       state = (state >> 1) | (bit << 5);
     }
     if (i >= 63) {
 #pragma unroll
-      for (int j = 0; j < 16; j++) d[j] = decp[(size_t)(i - 32 - j + 6) * 32];
+      for (int j = 0; j < 16; j++) b0[j] = dp[(size_t)(i - 48 - j) * 32];
     }
 #pragma unroll
     for (int j = 0; j < 16; j++) {
-      const uint32_t bit = decision_bit(n[j], state);
+      const uint32_t bit = decision_bit(b1[j], state);
       acc |= bit << (16 + j);
       state = (state >> 1) | (bit << 5);
     }
     uint32_t w = prmt(acc, 0u, 0x0123u);
     if (scr) w ^= c_prbs_le[i >> 5];
     *reinterpret_cast<uint32_t *>(dst + 4 * (i >> 5)) = w;
+    // rotate: next iteration walks b2 (steps i-32..i-47) then the freshly requested b0 (i-48..)
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      b1[j] = b0[j];
+      b0[j] = b2[j];
+    }
   }
 }
 
-// Persistent decoder: one CTA per SM, VIT_WARPS warps per CTA.  Warp w of CTA b owns work list
-// `bin = b * VIT_WARPS + w` (groups bin_start[bin] .. bin_start[bin+1]), filled on the host by
-// longest-processing-time-first packing over the 4 * num_SMs warp schedulers (warp w runs on
-// scheduler w % 4), so that every scheduler gets the same number of trellis steps.
+// Persistent decoder: one CTA per SM, VIT_WARPS warps per CTA.  Groups are sorted longest first on
+// the host; every warp pulls the next group from a global counter when it is done with its
+// current one (list scheduling: the tail of the launch is at most one short group long).
 __global__ void __launch_bounds__(32 * VIT_WARPS, 1) viterbi_kernel(const uint8_t *__restrict__ steps,
                                                                     uint8_t *__restrict__ out,
                                                                     uint2 *__restrict__ dec,
                                                                     const VitJob *__restrict__ jobs,
                                                                     const VitGroup *__restrict__ groups,
-                                                                    const uint32_t *__restrict__ bin_start) {
+                                                                    uint32_t n_groups, uint32_t *__restrict__ queue) {
   __shared__ uint2 lut[256];  // step byte -> {D, Dc}: per-class distances and complements
   for (int sb = threadIdx.x; sb < 256; sb += blockDim.x) {
     const uint32_t r = sb & 15, e = sb >> 4;
@@ -228,15 +240,23 @@ __global__ void __launch_bounds__(32 * VIT_WARPS, 1) viterbi_kernel(const uint8_
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const uint32_t bin = blockIdx.x * VIT_WARPS + (threadIdx.x >> 5);
-  const uint32_t g0 = bin_start[bin], g1 = bin_start[bin + 1];
-  for (uint32_t gi = g0; gi < g1; gi++) decode_group(groups[gi], lut, steps, out, dec, jobs, lane);
+  for (;;) {
+    uint32_t gi = 0;
+    if (lane == 0) gi = atomicAdd(queue, 1u);
+    gi = __shfl_sync(0xffffffffu, gi, 0);
+    if (gi >= n_groups) break;
+    decode_group(groups[gi], lut, steps, out, dec, jobs, lane);
+  }
 }
 
 int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
-                   const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, cudaStream_t st) {
-  if (n_ctas <= 0) return DABGPU_OK;
-  viterbi_kernel<<<n_ctas, 32 * VIT_WARPS, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups, d_bin_start);
+                   const VitGroup *d_groups, int n_groups, uint32_t *d_queue, cudaStream_t st) {
+  if (n_groups <= 0) return DABGPU_OK;
+  // enough CTAs to give every group a warp, at most one CTA per SM
+  const int n_ctas = std::min(device_sm_count(), (n_groups + VIT_WARPS - 1) / VIT_WARPS);
+  CUDA_TRY(cudaMemsetAsync(d_queue, 0, sizeof(uint32_t), st));
+  viterbi_kernel<<<n_ctas, 32 * VIT_WARPS, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups, (uint32_t)n_groups,
+                                                   d_queue);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }
