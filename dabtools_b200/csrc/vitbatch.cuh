@@ -2,25 +2,28 @@
 // per-warp-scheduler work lists for the persistent decoder kernel.
 #pragma once
 #include <algorithm>
+#include <queue>
 #include <vector>
 
 #include "viterbi.cuh"
 
 namespace dabgpu {
 
-// Collects codewords, packs them 32 per warp by length (longest first: the persistent kernel's
-// warps pull groups in that order, which is list scheduling with the shortest jobs last), uploads
-// the descriptors and launches.  The plan is cached: an identical job list
+// Collects codewords, packs them 32 per warp by length, distributes the groups over the GPU's
+// warp schedulers with longest-processing-time-first (so every scheduler sees the same number of
+// trellis steps), uploads the descriptors and launches.  The plan is cached: an identical job list
 // (the steady state of a locked receiver) re-launches without any host work or upload.
 struct VitBatch {
   std::vector<VitJob> jobs;
   std::vector<VitJob> sorted;
   std::vector<VitJob> planned;  // the job list the device descriptors were built from
   std::vector<VitGroup> groups;
-  DevBuf d_jobs, d_groups, d_queue, d_dec;
+  std::vector<uint32_t> bin_start;
+  DevBuf d_jobs, d_groups, d_bins, d_dec;
   PinBuf h_stage;
   uint64_t dec_words = 0;
   uint64_t total_steps = 0;  // sum over codewords of nbits+6 (for ACS/s accounting)
+  int n_ctas = 0;
 
   void clear() {
     jobs.clear();
@@ -51,7 +54,44 @@ struct VitBatch {
       g0.push_back(g);
       i = j;
     }
-    groups.swap(g0);  // longest first: the order in which the kernel's warps pull them
+    // LPT over the warp schedulers (4 per SM); a scheduler's groups are then dealt round-robin to
+    // its VIT_WARPS/4 resident warps so that they overlap each other's latencies
+    const int n_sm = device_sm_count();
+    const int per_sched = VIT_WARPS / 4;
+    const int n_sched = std::min<int>(n_sm * 4, std::max<size_t>(1, g0.size()));
+    n_ctas = std::min(n_sm, n_sched);  // small batches spread over SMs before doubling up
+    typedef std::pair<uint64_t, int> Load;  // (steps so far, scheduler)
+    std::priority_queue<Load, std::vector<Load>, std::greater<Load>> pq;
+    for (int s = 0; s < n_sched; s++) pq.push(Load(0, s));
+    std::vector<std::vector<uint32_t>> sched(n_sched);
+    for (size_t i = 0; i < g0.size(); i++) {  // g0 is already longest-first
+      Load l = pq.top();
+      pq.pop();
+      sched[l.second].push_back((uint32_t)i);
+      pq.push(Load(l.first + g0[i].nsteps, l.second));
+    }
+    const int n_bins = n_ctas * VIT_WARPS;
+    std::vector<std::vector<uint32_t>> bins(n_bins);
+    for (int s = 0; s < n_sched; s++) {
+      // scheduler s = CTA (s % n_ctas), partition (s / n_ctas); its warps are w = part + 4 k.
+      // LPT again over those warps (the list is already longest-first)
+      const int cta = s % n_ctas, part = s / n_ctas;
+      uint64_t load[VIT_WARPS / 4] = {};
+      for (uint32_t gi : sched[s]) {
+        int k = 0;
+        for (int q = 1; q < per_sched; q++)
+          if (load[q] < load[k]) k = q;
+        load[k] += g0[gi].nsteps;
+        bins[cta * VIT_WARPS + part + 4 * k].push_back(gi);
+      }
+    }
+    groups.clear();
+    bin_start.assign(n_bins + 1, 0);
+    for (int b = 0; b < n_bins; b++) {
+      bin_start[b] = (uint32_t)groups.size();
+      for (uint32_t gi : bins[b]) groups.push_back(g0[gi]);
+    }
+    bin_start[n_bins] = (uint32_t)groups.size();
   }
 
   // upload descriptors (pinned staging, async) and launch on `st`
@@ -63,30 +103,34 @@ struct VitBatch {
       plan();
       planned = jobs;
       int rc;
-      const size_t jb = sorted.size() * sizeof(VitJob), gb = groups.size() * sizeof(VitGroup);
+      const size_t jb = sorted.size() * sizeof(VitJob), gb = groups.size() * sizeof(VitGroup),
+                   bb = bin_start.size() * sizeof(uint32_t);
       if ((rc = d_jobs.reserve(jb))) return rc;
       if ((rc = d_groups.reserve(gb))) return rc;
-      if ((rc = d_queue.reserve(64))) return rc;
+      if ((rc = d_bins.reserve(bb))) return rc;
       if ((rc = d_dec.reserve(dec_words * sizeof(uint2)))) return rc;
       // the staging buffer may still be in flight from the previous upload on this stream
       CUDA_TRY(cudaStreamSynchronize(st));
-      if ((rc = h_stage.reserve(jb + gb))) return rc;
+      if ((rc = h_stage.reserve(jb + gb + bb))) return rc;
       memcpy(h_stage.p, sorted.data(), jb);
       memcpy((char *)h_stage.p + jb, groups.data(), gb);
+      memcpy((char *)h_stage.p + jb + gb, bin_start.data(), bb);
       CUDA_TRY(cudaMemcpyAsync(d_jobs.p, h_stage.p, jb, cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaMemcpyAsync(d_groups.p, (char *)h_stage.p + jb, gb, cudaMemcpyHostToDevice, st));
+      CUDA_TRY(cudaMemcpyAsync(d_bins.p, (char *)h_stage.p + jb + gb, bb, cudaMemcpyHostToDevice, st));
     }
-    return relaunch(d_steps, d_out, st);
+    return launch_viterbi(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
+                          d_bins.as<uint32_t>(), n_ctas, st);
   }
   // launch again with the descriptors of the last run() (identical job list by construction)
   int relaunch(const uint8_t *d_steps, uint8_t *d_out, cudaStream_t st) {
     return launch_viterbi(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
-                          (int)groups.size(), d_queue.as<uint32_t>(), st);
+                          d_bins.as<uint32_t>(), n_ctas, st);
   }
   void release() {
     d_jobs.release();
     d_groups.release();
-    d_queue.release();
+    d_bins.release();
     d_dec.release();
     h_stage.release();
     planned.clear();

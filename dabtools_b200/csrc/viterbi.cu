@@ -222,15 +222,17 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut
   }
 }
 
-// Persistent decoder: one CTA per SM, VIT_WARPS warps per CTA.  Groups are sorted longest first on
-// the host; every warp pulls the next group from a global counter when it is done with its
-// current one (list scheduling: the tail of the launch is at most one short group long).
+// Persistent decoder: one CTA per SM, VIT_WARPS warps per CTA.  Warp w of CTA b owns work list
+// `bin = b * VIT_WARPS + w` (groups bin_start[bin] .. bin_start[bin+1]).  The host packs the
+// groups longest-processing-time-first, first over the warp schedulers (warp w runs on scheduler
+// w % 4) so that every scheduler gets the same number of trellis steps, then over the scheduler's
+// VIT_WARPS/4 warps so that they all stay busy until the end of the launch.
 __global__ void __launch_bounds__(32 * VIT_WARPS, 1) viterbi_kernel(const uint8_t *__restrict__ steps,
                                                                     uint8_t *__restrict__ out,
                                                                     uint2 *__restrict__ dec,
                                                                     const VitJob *__restrict__ jobs,
                                                                     const VitGroup *__restrict__ groups,
-                                                                    uint32_t n_groups, uint32_t *__restrict__ queue) {
+                                                                    const uint32_t *__restrict__ bin_start) {
   __shared__ uint2 lut[256];  // step byte -> {D, Dc}: per-class distances and complements
   for (int sb = threadIdx.x; sb < 256; sb += blockDim.x) {
     const uint32_t r = sb & 15, e = sb >> 4;
@@ -240,23 +242,15 @@ __global__ void __launch_bounds__(32 * VIT_WARPS, 1) viterbi_kernel(const uint8_
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  for (;;) {
-    uint32_t gi = 0;
-    if (lane == 0) gi = atomicAdd(queue, 1u);
-    gi = __shfl_sync(0xffffffffu, gi, 0);
-    if (gi >= n_groups) break;
-    decode_group(groups[gi], lut, steps, out, dec, jobs, lane);
-  }
+  const uint32_t bin = blockIdx.x * VIT_WARPS + (threadIdx.x >> 5);
+  const uint32_t g0 = bin_start[bin], g1 = bin_start[bin + 1];
+  for (uint32_t gi = g0; gi < g1; gi++) decode_group(groups[gi], lut, steps, out, dec, jobs, lane);
 }
 
 int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
-                   const VitGroup *d_groups, int n_groups, uint32_t *d_queue, cudaStream_t st) {
-  if (n_groups <= 0) return DABGPU_OK;
-  // enough CTAs to give every group a warp, at most one CTA per SM
-  const int n_ctas = std::min(device_sm_count(), (n_groups + VIT_WARPS - 1) / VIT_WARPS);
-  CUDA_TRY(cudaMemsetAsync(d_queue, 0, sizeof(uint32_t), st));
-  viterbi_kernel<<<n_ctas, 32 * VIT_WARPS, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups, (uint32_t)n_groups,
-                                                   d_queue);
+                   const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, cudaStream_t st) {
+  if (n_ctas <= 0) return DABGPU_OK;
+  viterbi_kernel<<<n_ctas, 32 * VIT_WARPS, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups, d_bin_start);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }

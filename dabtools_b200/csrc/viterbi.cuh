@@ -34,12 +34,13 @@ struct VitGroup {
 __host__ __device__ static inline uint64_t vit_group_dec_words(uint32_t nsteps) { return (uint64_t)nsteps * 32u; }
 __host__ __device__ static inline uint32_t vit_row_bytes(uint32_t nsteps) { return (nsteps + 15u) & ~15u; }
 
-// warps per persistent CTA (one CTA per SM): 4 schedulers x 4 concurrently decoded groups
-enum { VIT_WARPS = 16 };
+// warps per persistent CTA (one CTA per SM): 4 schedulers x 3 concurrent work lists
+enum { VIT_WARPS = 12 };
 int device_sm_count();
-// persistent launch; d_groups sorted longest first, d_queue = one uint32 work counter
+// persistent launch: n_ctas CTAs of VIT_WARPS warps; warp-bin b owns groups
+// d_bin_start[b] .. d_bin_start[b+1] (n_ctas * VIT_WARPS + 1 entries)
 int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
-                   const VitGroup *d_groups, int n_groups, uint32_t *d_queue, cudaStream_t st);
+                   const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, cudaStream_t st);
 
 // step-byte producers -------------------------------------------------------------------
 // (a) from the reference's soft-symbol bytes (4 per step; <128 -> 0, 128 -> erasure, >128 -> 1)
