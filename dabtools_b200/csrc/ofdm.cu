@@ -48,10 +48,17 @@ int ofdm_init_constants() {
   return DABGPU_OK;
 }
 
-// uint8 sample -> the reference's int8 (input_sdr.c:61-62: buffer-127 stored in int8_t, 255 -> -128)
+// uint8 sample -> the reference's int8 (input_sdr.c:61-62: buffer-127 stored in int8_t, so 255 wraps
+// to -128): (b - 127) mod 256 == (b + 129) mod 256, read back as a signed byte.
 __device__ __forceinline__ float u8_to_sample(uint32_t b) {
-  int v = (int)b - 127;
-  return (float)(v == 128 ? -128 : v);
+  return (float)(int)(int8_t)((b + 129u) & 0xffu);
+}
+// one I/Q pair (I in bits 0..7, Q in bits 8..15): add 129 to each byte in its own copy (the carry of
+// the low byte must not reach the high one), then prmt sign-extends the byte of interest
+__device__ __forceinline__ float2 iq_to_sample(uint32_t w) {
+  const int re = (int)prmt(w + 0x81u, 0u, 0x8880u);    // byte 0, sign-replicated above
+  const int im = (int)prmt(w + 0x8100u, 0u, 0x9991u);  // byte 1, sign-replicated above
+  return make_float2((float)re, (float)im);
 }
 
 // =================================================================================================
@@ -237,7 +244,7 @@ __device__ __forceinline__ void dft16(float2 *v) {
 // result: thread p holds bins p + 128 m, m = 0..15  (m = 2 k3 for q = p, 2 k3 + 1 for q = p + 128)
 // `xch` is a 2080-element float2 exchange buffer.
 // =================================================================================================
-enum { FFT_THREADS = 128, XCH_ELEMS = 16 * 130 };
+enum { FFT_THREADS = 128, XCH_PAD = 129, XCH_ELEMS = 16 * XCH_PAD };  // 129: both half-warps conflict-free
 
 struct FftTwiddles {  // per-thread twiddles, constant over symbols
   float2 s1[15];      // W2048^(t*k1), k1 = 1..15
@@ -258,11 +265,11 @@ __device__ __forceinline__ void fft2048_from_regs(float2 *v, const FftTwiddles &
 #pragma unroll
   for (int k = 1; k < 16; k++) v[k] = cmul(v[k], tw.s1[k - 1]);
 #pragma unroll
-  for (int k = 0; k < 16; k++) xch[k * 130 + p] = v[k];
+  for (int k = 0; k < 16; k++) xch[k * XCH_PAD + p] = v[k];
   __syncthreads();
   const int u = p >> 4, k1 = p & 15;
 #pragma unroll
-  for (int j = 0; j < 16; j++) v[j] = xch[k1 * 130 + u + 8 * j];
+  for (int j = 0; j < 16; j++) v[j] = xch[k1 * XCH_PAD + u + 8 * j];
   __syncthreads();
   // stage 2
   dft16(v);
@@ -293,8 +300,7 @@ __device__ __forceinline__ void load_symbol(float2 *v, const uint8_t *sym, int p
   const uint16_t *h = reinterpret_cast<const uint16_t *>(sym);
 #pragma unroll
   for (int j = 0; j < 16; j++) {
-    const uint32_t w = h[p + 128 * j];
-    v[j] = make_float2(u8_to_sample(w & 0xffu), u8_to_sample(w >> 8));
+    v[j] = iq_to_sample(h[p + 128 * j]);
   }
 }
 
@@ -376,14 +382,23 @@ __global__ void __launch_bounds__(FFT_THREADS) demod_kernel(const uint8_t *__res
   }
   FftTwiddles tw;
   load_twiddles(tw, p);
-  // destination of this thread's bins p + 128 m (constant over symbols)
-  uint16_t dst[16];
+  // Thread p ends every FFT with bins p + 128 m.  Carriers are bins 1..768 and 1280..2047, so
+  // m = 0..5 and 10..15 are always carriers (except bin 0 = DC for p = 0), m = 6 only for p = 0
+  // (bin 768), m = 7..9 never.  Slot k = 0..11 <-> m = k (k < 6) or k + 4; slot 12 = bin 768.
+  // The byte position of each carrier's first bit in sm.bits is constant over symbols.
+  const bool plane_order = !(seg == 0 || DEBUG);
+  uint16_t pos[13];
 #pragma unroll
-  for (int m = 0; m < 16; m++) dst[m] = g_bin_dst[p + 128 * m];
+  for (int k = 0; k < 13; k++) {
+    const int m = k < 6 ? k : (k < 12 ? k + 4 : 6);
+    const uint32_t n = g_bin_dst[p + 128 * m];  // 0xffff on the two non-carrier cases
+    pos[k] = (uint16_t)(n == 0xffffu ? 0xffffu : (plane_order ? (n & 15u) * 192u + (n >> 4) : n));
+  }
+  const uint32_t second = plane_order ? 96u : 1536u;  // distance from a carrier's bit 0 to its bit 1
 
-  float2 prev[16];
+  float2 prev[13];
 #pragma unroll
-  for (int m = 0; m < 16; m++) prev[m] = make_float2(0.f, 0.f);
+  for (int k = 0; k < 13; k++) prev[k] = make_float2(0.f, 0.f);
 
   for (int i = 0; i < nsym; i++) {
     const int l = l0 + i, st = i % N_STAGES;
@@ -401,30 +416,33 @@ __global__ void __launch_bounds__(FFT_THREADS) demod_kernel(const uint8_t *__res
 #pragma unroll
       for (int m = 0; m < 16; m++) dbg_sym[(size_t)l * 2048 + ((p + 128 * m + 1024) & 2047)] = v[m];
     }
+    float2 cur[13];
+#pragma unroll
+    for (int k = 0; k < 13; k++) cur[k] = v[k < 6 ? k : (k < 12 ? k + 4 : 6)];
     if (i > 0) {
       // DQPSK against the previous symbol and hard slicing (input_sdr.c:132-158):
       //   re = Re(s_l conj(s_l-1)) / |s_l-1|^2 ,  im' = -Im(s_l conj(s_l-1)) / |s_l-1|^2
       //   bit0 = !(re > 0) ; bit1 = (im' > 0)      (division by a positive number dropped)
+      if (DEBUG) {
+        // the reference computes the quotient on all 2048 bins; only the carriers are compared
 #pragma unroll
-      for (int m = 0; m < 16; m++) {
-        const float re = v[m].x * prev[m].x + v[m].y * prev[m].y;
-        const float imn = v[m].x * prev[m].y - v[m].y * prev[m].x;
-        if (DEBUG) {
-          const float den = prev[m].x * prev[m].x + prev[m].y * prev[m].y;
+        for (int k = 0; k < 13; k++) {
+          const int m = k < 6 ? k : (k < 12 ? k + 4 : 6);
+          const float re = cur[k].x * prev[k].x + cur[k].y * prev[k].y;
+          const float imn = cur[k].x * prev[k].y - cur[k].y * prev[k].x;
+          const float den = prev[k].x * prev[k].x + prev[k].y * prev[k].y;
           dbg_symd[(size_t)l * 2048 + ((p + 128 * m + 1024) & 2047)] = make_float2(re / den, imn / den);
         }
-        const uint32_t n = dst[m];
-        if (n != 0xffffu) {
-          const uint8_t b0 = re > 0.f ? 0 : 1, b1 = imn > 0.f ? 1 : 0;
-          if (seg == 0 || DEBUG) {
-            sm.bits[n] = b0;
-            sm.bits[1536 + n] = b1;
-          } else {
-            const uint32_t idx = (n & 15u) * 192u + (n >> 4);
-            sm.bits[idx] = b0;
-            sm.bits[idx + 96] = b1;
-          }
-        }
+      }
+#pragma unroll
+      for (int k = 0; k < 13; k++) {
+        if (k == 12 && p != 0) continue;  // bin 768 belongs to thread 0 only
+        const float re = cur[k].x * prev[k].x + cur[k].y * prev[k].y;
+        const float imn = cur[k].x * prev[k].y - cur[k].y * prev[k].x;
+        const uint32_t a = pos[k];
+        if (k == 0 && a == 0xffffu) continue;  // bin 0 (DC) of thread 0
+        sm.bits[a] = re > 0.f ? 0 : 1;
+        sm.bits[a + second] = imn > 0.f ? 1 : 0;
       }
       __syncthreads();
       if (DEBUG) {
@@ -442,10 +460,10 @@ __global__ void __launch_bounds__(FFT_THREADS) demod_kernel(const uint8_t *__res
         sm.planes[p / 6][(i - 1) * 6 + p % 6] = word;
       }
       // the next symbol's slicing must not overwrite sm.bits before it has been read: the
-      // three barriers inside fft2048_from_regs of the next iteration order that
+      // barriers inside fft2048_from_regs of the next iteration order that
     }
 #pragma unroll
-    for (int m = 0; m < 16; m++) prev[m] = v[m];
+    for (int k = 0; k < 13; k++) prev[k] = cur[k];
   }
   if (!DEBUG && seg > 0) {
     __syncthreads();
@@ -538,8 +556,7 @@ struct SrcU8 {
   const uint8_t *f;
   __device__ __forceinline__ float real(int n) const { return u8_to_sample(f[2 * n]); }
   __device__ __forceinline__ float2 at(int n) const {
-    const uint32_t w = reinterpret_cast<const uint16_t *>(f)[n];
-    return make_float2(u8_to_sample(w & 0xffu), u8_to_sample(w >> 8));
+    return iq_to_sample(reinterpret_cast<const uint16_t *>(f)[n]);
   }
 };
 struct SrcI8 {
