@@ -120,6 +120,11 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   if ((rc = d_gather_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
   if ((rc = h_fic_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
   CUDA_TRY(cudaStreamCreateWithFlags(&st_msc, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
+  }
   CUDA_TRY(cudaEventCreateWithFlags(&ev_up[0], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_up[1], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_msc_done, cudaEventDisableTiming));
@@ -171,6 +176,16 @@ int Engine::join_msc(cudaStream_t user) {
 
 void Engine::destroy() {
   pool.stop();
+  if (st_copy) {
+    cudaStreamSynchronize(st_copy);
+    cudaStreamDestroy(st_copy);
+    st_copy = nullptr;
+    for (int i = 0; i < 2; i++) {
+      cudaEventDestroy(ev_copied[i]);
+      cudaEventDestroy(ev_consumed[i]);
+      d_stage[i].release();
+    }
+  }
   if (st_msc) {
     cudaStreamSynchronize(st_msc);
     cudaStreamDestroy(st_msc);
@@ -561,8 +576,50 @@ static void tuner_feedback(FrontState &fr) {
     fr.frequency = (uint32_t)((double)fr.frequency + fr.fine_freq_shift / 3);
 }
 
+// upload one callback's worth of host IQ for every stream; returns immediately
+int Engine::submit_iq(const uint8_t *iq, size_t pitch, int chunk_len) {
+  int rc;
+  if (chunk_len <= 0 || chunk_len > 262144 || (chunk_len & 15) || pitch < (size_t)chunk_len) {
+    set_error(DABGPU_ERR_ARG, "submit_iq: chunk_len must be a multiple of 16 in (0, 262144], pitch >= chunk_len");
+    return DABGPU_ERR_ARG;
+  }
+  if (stage_count >= 2) {
+    set_error(DABGPU_ERR_STATE, "submit_iq: two chunks are already queued; call dabgpu_engine_feed_submitted");
+    return DABGPU_ERR_STATE;
+  }
+  const int b = (stage_head + stage_count) & 1;
+  if ((rc = d_stage[b].reserve((size_t)S * chunk_len))) return rc;
+  // the buffer is free once the ingest kernel that read it last has run
+  CUDA_TRY(cudaStreamWaitEvent(st_copy, ev_consumed[b], 0));
+  CUDA_TRY(cudaMemcpy2DAsync(d_stage[b].p, chunk_len, iq, pitch, chunk_len, S, cudaMemcpyHostToDevice, st_copy));
+  CUDA_TRY(cudaEventRecord(ev_copied[b], st_copy));
+  stage_len[b] = chunk_len;
+  stage_count++;
+  return DABGPU_OK;
+}
+
+int Engine::feed_submitted() {
+  if (stage_count <= 0) {
+    set_error(DABGPU_ERR_STATE, "feed_submitted: nothing was submitted");
+    return DABGPU_ERR_STATE;
+  }
+  const int b = stage_head;
+  CUDA_TRY(cudaStreamWaitEvent(current_stream(), ev_copied[b], 0));
+  consuming_stage = b;
+  const int rc = feed_iq(d_stage[b].as<uint8_t>(), (size_t)stage_len[b], stage_len[b], true);
+  consuming_stage = -1;
+  stage_head ^= 1;
+  stage_count--;
+  return rc;
+}
+
 int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_device) {
   int rc;
+  if (!on_device) {
+    if ((rc = submit_iq(iq, pitch, chunk_len))) return rc;
+    // chunks submitted earlier are consumed first (FIFO); this call consumes exactly one
+    return feed_submitted();
+  }
   if (chunk_len <= 0 || chunk_len > 262144 || (chunk_len & 15) || pitch < (size_t)chunk_len) {
     set_error(DABGPU_ERR_ARG, "feed_iq: chunk_len must be a multiple of 16 in (0, 262144], pitch >= chunk_len");
     return DABGPU_ERR_ARG;
@@ -636,16 +693,11 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   CUDA_TRY(cudaMemcpyAsync(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), cudaMemcpyHostToDevice, st));
   host_us[H_PRE] += now_us() - t_pre;
   const uint8_t *d_src = iq;
-  if (!on_device) {
-    if ((rc = d_chunk.reserve((size_t)S * chunk_len))) return rc;
-    CUDA_TRY(cudaMemcpy2DAsync(d_chunk.p, chunk_len, iq, pitch, chunk_len, S, cudaMemcpyHostToDevice, st));
-    d_src = d_chunk.as<uint8_t>();
-    pitch = chunk_len;
-  }
   t0(K_INGEST, st);
   if ((rc = launch_ingest(d_src, pitch, (uint32_t)chunk_len, d_ring.as<uint8_t>(), d_ctl.as<StepCtl>(), S, st)))
     return rc;
   t1(K_INGEST, st);
+  if (consuming_stage >= 0) CUDA_TRY(cudaEventRecord(ev_consumed[consuming_stage], st));
   n_eti = 0;
   eti_stream.clear();
   if (any_read) {
@@ -702,6 +754,10 @@ DABGPU_EXPORT int dabgpu_engine_feed_iq(dabgpu_engine *h, const uint8_t *iq, siz
                                         int on_device) {
   return h->e.feed_iq(iq, pitch, chunk_len, on_device != 0);
 }
+DABGPU_EXPORT int dabgpu_engine_submit_iq(dabgpu_engine *h, const uint8_t *iq, size_t pitch, int chunk_len) {
+  return h->e.submit_iq(iq, pitch, chunk_len);
+}
+DABGPU_EXPORT int dabgpu_engine_feed_submitted(dabgpu_engine *h) { return h->e.feed_submitted(); }
 DABGPU_EXPORT int dabgpu_engine_process_demapped(dabgpu_engine *h, const uint8_t *tfs, size_t pitch,
                                                  const uint8_t *mask, int on_device) {
   return h->e.process_demapped(tfs, pitch, mask, on_device != 0);

@@ -101,6 +101,16 @@ struct Engine {
   int msc_buf = 0;
   bool msc_inflight = false;
   int join_msc(cudaStream_t user);  // make `user` wait for all MSC work issued so far
+  // host IQ is staged through two device buffers on a copy stream, so that the upload of the
+  // next callback overlaps the processing of the current one
+  cudaStream_t st_copy = nullptr;
+  DevBuf d_stage[2];
+  cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
+  int stage_len[2] = {0, 0};
+  int stage_head = 0, stage_count = 0;  // FIFO of submitted chunks (at most 2)
+  int consuming_stage = -1;
+  int submit_iq(const uint8_t *iq, size_t pitch, int chunk_len);
+  int feed_submitted();
   HostPool pool;
   std::vector<FrameWork> works;
   // MSC decoding may lag by up to msc_batch calls so that one Viterbi launch covers several

@@ -273,3 +273,20 @@ def _engine_join(self):
 
 
 Engine.join = _engine_join
+
+
+def _engine_submit_iq(self, iq: np.ndarray):
+    """start the upload of one callback's worth of host IQ ([n_streams][chunk_len], ideally pinned)"""
+    assert iq.dtype == np.uint8 and iq.flags.c_contiguous and iq.shape[0] == self.n_streams
+    self._lib.dabgpu_engine_submit_iq.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_int]
+    check(self._lib.dabgpu_engine_submit_iq(self._h, _np_ptr(iq), iq.shape[1], iq.shape[1]))
+
+
+def _engine_feed_submitted(self) -> int:
+    self._lib.dabgpu_engine_feed_submitted.argtypes = [C.c_void_p]
+    check(self._lib.dabgpu_engine_feed_submitted(self._h))
+    return self._lib.dabgpu_engine_eti_count(self._h)
+
+
+Engine.submit_iq = _engine_submit_iq
+Engine.feed_submitted = _engine_feed_submitted

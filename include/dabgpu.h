@@ -108,6 +108,12 @@ void dabgpu_engine_destroy(dabgpu_engine *e);
 /* One rtlsdr callback for every stream: iq + s*pitch holds chunk_len bytes (<= 262144, multiple
  * of 16) for stream s.  Equivalent to one demod_thread_fn iteration per stream. */
 int dabgpu_engine_feed_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int chunk_len, int on_device);
+/* The same in two halves, so that the host->device copy of the next callback overlaps the
+ * processing of the current one: submit_iq() starts the upload of a host chunk (pinned memory
+ * makes it asynchronous) and returns; feed_submitted() processes the oldest submitted chunk.  At
+ * most two chunks may be in flight.  feed_iq(host pointer) == submit_iq + feed_submitted. */
+int dabgpu_engine_submit_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int chunk_len);
+int dabgpu_engine_feed_submitted(dabgpu_engine *e);
 /* Back-end only: one demapped transmission frame (fic 9216 + msc 221184 bytes of 0/1, i.e. the
  * payload of demapped_transmission_frame_t) for every stream with mask[s] != 0 (mask NULL = all);
  * equivalent to dab_process_frame per stream. */
