@@ -152,6 +152,28 @@ def cpu_reference_rate(n_procs: int, reps: int = 1, n1: int = 18, n2: int = 40):
 
 
 # ------------------------------------------------------------------------------------------------
+def shard_streams(total_streams: int, world: int, rank: int):
+    """Streams are independent end to end: rank r decodes the contiguous block
+    [r*total/world, (r+1)*total/world) and nothing is exchanged between ranks."""
+    per = total_streams // world
+    rem = total_streams % world
+    lo = rank * per + min(rank, rem)
+    return lo, lo + per + (1 if rank < rem else 0)
+
+
+def reduce_over_ranks(times_ms, frames, device, world):
+    """timing = MAX over ranks, work = SUM over ranks (the only collectives of the benchmark; the
+    data path has none).  Works on any backend (nccl on the GPU box, gloo in the CPU tests)."""
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor(list(times_ms), dtype=torch.float64, device=device)
+    f = torch.tensor(list(frames), dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(f, op=dist.ReduceOp.SUM)
+    return [float(x) for x in t], [float(x) for x in f]
+
+
 def generate_dataset(S, n_tf, device, seed):
     """[S][n_tf*393216 + pad] uint8 I/Q on `device`, distinct payload and noise per stream"""
     import torch
@@ -288,13 +310,8 @@ def run_ours(args, rank, world, local_rank):
     eng.close()
 
     # ---------------- reduce over ranks ----------------
-    t = torch.tensor([ms, e2e_ms], dtype=torch.float64, device=dev)
-    fr = torch.tensor([float(frames), float(e2e_frames)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(fr, op=dist.ReduceOp.SUM)
-    ms_max, e2e_ms_max = float(t[0]), float(t[1])
-    frames_all, e2e_frames_all = float(fr[0]), float(fr[1])
+    (ms_max, e2e_ms_max), (frames_all, e2e_frames_all) = reduce_over_ranks(
+        [ms, e2e_ms], [frames, e2e_frames], dev, world)
     if rank != 0:
         return None
 
