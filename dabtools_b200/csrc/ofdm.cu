@@ -350,7 +350,7 @@ struct DemodSmem {
 __device__ __forceinline__ uint32_t sym_byte_off(int l) { return 2u * (2656u + 2552u * (uint32_t)l + 504u); }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(FFT_THREADS) demod_kernel(const uint8_t *__restrict__ frames,
+__global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__restrict__ frames,
                                                             const StepCtl *__restrict__ ctl,
                                                             const SyncOut *__restrict__ sync,
                                                             uint8_t *__restrict__ fic_bits,
@@ -509,24 +509,26 @@ int launch_demod_debug(const uint8_t *d_frame, float2 *d_symbols, float2 *d_symb
 // =================================================================================================
 // synchronisers: one CTA of 128 threads per stream
 // =================================================================================================
-// generic in-place radix-2 FFT of n = 2^logn points in shared memory by the whole CTA;
-// sign = -1 forward, +1 backward; unnormalised
-__device__ void block_fft_pow2(float2 *d, int logn, int sign) {
+// `batch` independent in-place radix-2 FFTs of n = 2^logn points, stored back to back in shared
+// memory, by the whole CTA; sign = -1 forward, +1 backward; unnormalised
+__device__ void block_fft_pow2(float2 *d, int logn, int sign, int batch) {
   const int n = 1 << logn;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    const int j = (int)(__brev((unsigned)i) >> (32 - logn));
-    if (i < j) {
-      const float2 t = d[i];
-      d[i] = d[j];
-      d[j] = t;
+  for (int i = threadIdx.x; i < batch * n; i += blockDim.x) {
+    const int base = i & ~(n - 1), ii = i & (n - 1);
+    const int j = (int)(__brev((unsigned)ii) >> (32 - logn));
+    if (ii < j) {
+      const float2 t = d[base + ii];
+      d[base + ii] = d[base + j];
+      d[base + j] = t;
     }
   }
   __syncthreads();
   for (int len = 2; len <= n; len <<= 1) {
     const int half = len >> 1;
-    for (int b = threadIdx.x; b < n / 2; b += blockDim.x) {
+    for (int bb = threadIdx.x; bb < batch * (n / 2); bb += blockDim.x) {
+      const int base = (bb >> (logn - 1)) << logn, b = bb & (n / 2 - 1);
       const int k = b & (half - 1);
-      const int i0 = ((b - k) << 1) + k, i1 = i0 + half;
+      const int i0 = base + ((b - k) << 1) + k, i1 = i0 + half;
       float2 w = g_tw2048[(k * (2048 / len)) & 2047];
       if (sign > 0) w.y = -w.y;
       const float2 x = d[i0], y = cmul(d[i1], w);
@@ -534,6 +536,32 @@ __device__ void block_fft_pow2(float2 *d, int logn, int sign) {
       d[i1] = csub(x, y);
     }
     __syncthreads();
+  }
+}
+
+// in-place 128-point backward FFT of shared-memory data by ONE warp (no CTA barriers)
+__device__ void warp_ifft128(float2 *d, int lane) {
+  for (int i = lane; i < 128; i += 32) {
+    const int j = (int)(__brev((unsigned)i) >> 25);
+    if (i < j) {
+      const float2 t = d[i];
+      d[i] = d[j];
+      d[j] = t;
+    }
+  }
+  __syncwarp();
+  for (int len = 2; len <= 128; len <<= 1) {
+    const int half = len >> 1;
+    for (int b = lane; b < 64; b += 32) {
+      const int k = b & (half - 1);
+      const int i0 = ((b - k) << 1) + k, i1 = i0 + half;
+      float2 w = g_tw2048[(k * (2048 / len)) & 2047];
+      w.y = -w.y;
+      const float2 x = d[i0], y = cmul(d[i1], w);
+      d[i0] = cadd(x, y);
+      d[i1] = csub(x, y);
+    }
+    __syncwarp();
   }
 }
 
@@ -659,7 +687,7 @@ __device__ int fine_time_from_spec(SyncSmem &sm) {
     sm.work[(i % 3) * 512 + i / 3] = cmulc(sm.spec[bin], prs_value(i));
   }
   __syncthreads();
-  for (int b = 0; b < 3; b++) block_fft_pow2(sm.work + 512 * b, 9, +1);
+  block_fft_pow2(sm.work, 9, +1, 3);
   float best = -99999.f;
   int best_i = 0x7fffffff;
   for (int k = p; k < 1536; k += FFT_THREADS) {
@@ -683,25 +711,33 @@ __device__ int fine_time_from_spec(SyncSmem &sm) {
 }
 
 // sdr_sync.c:205-258 on the spectrum in sm.spec (natural order; the reference's fftshifted
-// index i is bin (i + 1024) mod 2048)
+// index i is bin (i + 1024) mod 2048).  The 29 hypotheses are independent: each warp takes every
+// fourth one and runs its 128-point inverse FFT on its own; the reference keeps the first k whose
+// peak is strictly larger, i.e. the largest peak with the smallest k on ties.
 __device__ int coarse_freq_from_spec(SyncSmem &sm) {
-  const int p = threadIdx.x;
-  float gbest = -99999.f;
-  int gk = 0;
-  for (int k = -14; k <= 14; k++) {
-    if (p < 128) sm.work[p] = cmulc(sm.spec[(14 + k + 256 + p + 1024) & 2047], prs_value(14 + p));
-    __syncthreads();
-    block_fft_pow2(sm.work, 7, +1);
-    const float mag = sqrtf(sm.work[p].x * sm.work[p].x + sm.work[p].y * sm.work[p].y);
-    float bv;
-    int bi;
-    block_arg_reduce(sm, mag, p, true, &bv, &bi);
-    if (bv > gbest) {
-      gbest = bv;
-      gk = k;
+  const int p = threadIdx.x, lane = p & 31, warp = p >> 5;
+  float2 *buf = sm.work + 128 * warp;
+  float best = -99999.f;
+  int best_k = 99;
+  for (int k = -14 + warp; k <= 14; k += 4) {
+    for (int s = lane; s < 128; s += 32)
+      buf[s] = cmulc(sm.spec[(14 + k + 256 + s + 1024) & 2047], prs_value(14 + s));
+    __syncwarp();
+    warp_ifft128(buf, lane);
+    float mag = -99999.f;
+    for (int s = lane; s < 128; s += 32) mag = fmaxf(mag, sqrtf(buf[s].x * buf[s].x + buf[s].y * buf[s].y));
+#pragma unroll
+    for (int o = 16; o; o >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, o));
+    if (mag > best) {  // ascending k within the warp
+      best = mag;
+      best_k = k;
     }
+    __syncwarp();
   }
-  return gk;
+  float bv;
+  int bi;
+  block_arg_reduce(sm, best, best_k + 14, true, &bv, &bi);  // ties -> lowest k
+  return bi - 14;
 }
 
 // sdr_sync.c:259-302: mean phase of x[n+2048] conj(x[n]) over the PRS guard interval, in Hz
