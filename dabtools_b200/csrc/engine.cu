@@ -197,7 +197,7 @@ void Engine::destroy() {
   if (ev[0][0])
     for (int k = 0; k < K_COUNT; k++)
       for (int j = 0; j < 2; j++) cudaEventDestroy(ev[k][j]);
-  DevBuf *db[] = {&d_ring, &d_frames, &d_chunk, &d_ctl, &d_sync, &d_cifs, &d_fibs, &d_crc, &d_ficbits,
+  DevBuf *db[] = {&d_ring, &d_frames, &d_tails, &d_chunk, &d_ctl, &d_sync, &d_cifs, &d_fibs, &d_crc, &d_ficbits,
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
                   &d_subjobs, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
   for (DevBuf *b : db) b->release();
@@ -554,12 +554,14 @@ int Engine::ensure_frontend() {
   if (d_ring.p) return DABGPU_OK;
   if ((rc = d_ring.reserve((size_t)S * IQ_RING_BYTES))) return rc;
   if ((rc = d_frames.reserve((size_t)S * DABGPU_TF_BYTES))) return rc;
+  if ((rc = d_tails.reserve((size_t)S * TAIL_BYTES))) return rc;
   if ((rc = d_ctl.reserve((size_t)S * sizeof(StepCtl)))) return rc;
   if ((rc = d_sync.reserve((size_t)S * sizeof(SyncOut)))) return rc;
   if ((rc = h_ctl.reserve((size_t)S * sizeof(StepCtl)))) return rc;
   if ((rc = h_sync.reserve((size_t)S * sizeof(SyncOut)))) return rc;
   CUDA_TRY(cudaMemset(d_ring.p, 0, (size_t)S * IQ_RING_BYTES));
   CUDA_TRY(cudaMemset(d_frames.p, 0, (size_t)S * DABGPU_TF_BYTES));
+  CUDA_TRY(cudaMemset(d_tails.p, 0, (size_t)S * TAIL_BYTES));
   CUDA_TRY(cudaMemset(d_sync.p, 0, (size_t)S * sizeof(SyncOut)));
   return DABGPU_OK;
 }
@@ -629,7 +631,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   cudaStream_t st = current_stream();
   StepCtl *ctl = h_ctl.as<StepCtl>();
   active.clear();
-  bool any_read = false;
+  bool any_read = false, any_copy = false, any_mat = false;
   for (int s = 0; s < S; s++) {
     FrontState &fr = front[s];
     StepCtl &c = ctl[s];
@@ -677,6 +679,22 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       fr.fifo_count -= n;
     }
     any_read = true;
+    // a plain window is used in place; anything else goes through the frame buffer
+    if (c.rd_bytes[1] == 0 && c.rd_dst[0] == 0 && c.rd_bytes[0] >= TAIL_OFF) {
+      c.src_ring = 1;
+      c.src_pos = c.rd_pos[0];
+      fr.prev_ring = true;
+      fr.prev_pos = c.rd_pos[0];
+    } else {
+      c.src_ring = 0;
+      if (fr.prev_ring) {
+        c.mat = 1;
+        c.mat_pos = fr.prev_pos;
+        any_mat = true;
+      }
+      fr.prev_ring = false;
+      any_copy = true;
+    }
     if (fr.startup_delay <= 0) {  // GAIN_SETTLE_TIME == 0: the first frame is read and dropped
       fr.startup_delay++;
       if (!quiet) fprintf(stderr, "startup_delay=%i\n", fr.startup_delay);
@@ -702,15 +720,25 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   eti_stream.clear();
   if (any_read) {
     t0(K_FIFO, st);
-    if ((rc = launch_fifo_read(d_ring.as<uint8_t>(), d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), S, st)))
+    if (any_mat && (rc = launch_fifo_read(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+                                          d_ctl.as<StepCtl>(), S, true, st)))
+      return rc;
+    if (any_copy && (rc = launch_fifo_read(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+                                           d_ctl.as<StepCtl>(), S, false, st)))
+      return rc;
+    if ((rc = launch_tail_update(d_ring.as<uint8_t>(), d_frames.as<uint8_t>(), d_tails.as<uint8_t>(),
+                                 d_ctl.as<StepCtl>(), S, st)))
       return rc;
     t1(K_FIFO, st);
     if (!active.empty()) {
       t0(K_SYNC, st);
-      if ((rc = launch_sync(d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), S, st))) return rc;
+      if ((rc = launch_sync(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+                            d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), S, st)))
+        return rc;
       t1(K_SYNC, st);
       t0(K_DEMOD, st);
-      if ((rc = launch_demod(d_frames.as<uint8_t>(), d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(),
+      if ((rc = launch_demod(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+                             d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(),
                              d_ficbits.as<uint8_t>(), d_cifs.as<uint8_t>(), S, st)))
         return rc;
       t1(K_DEMOD, st);

@@ -60,6 +60,8 @@ struct FrontState {
   uint64_t samples_in = 0;  // samples ingested so far (virtual-tuner phase reference)
   int last_ok = 0;
   bool pending = false;     // a frame of this stream is in flight in the current step
+  bool prev_ring = false;   // the previous frame was used in place from the ring (never copied)
+  uint32_t prev_pos = 0;    // ... and started at this ring offset
   GlibcRand rng;
 };
 
@@ -83,7 +85,7 @@ struct Engine {
   int shape_index(const dabgpu_cw_shape &s);
 
   // device stores
-  DevBuf d_ring, d_frames, d_chunk, d_ctl, d_sync;
+  DevBuf d_ring, d_frames, d_tails, d_chunk, d_ctl, d_sync;
   DevBuf d_cifs;      // [S][20][CIF_BYTES]
   DevBuf d_fibs;      // [S][5][384]
   DevBuf d_crc;       // [S][5][12]

@@ -113,7 +113,19 @@ int launch_ingest(const uint8_t *d_src, uint64_t src_pitch, uint32_t chunk_len, 
 // =================================================================================================
 // FIFO read into the persistent per-stream frame buffer
 // =================================================================================================
+// 16 bytes of a ring window starting at the even offset `p` (wraps at word granularity)
+__device__ __forceinline__ uint4 ring_load16(const uint8_t *rs, uint32_t p) {
+  const uint32_t sh = (p & 3u) * 8u;
+  uint32_t w[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) w[k] = *reinterpret_cast<const uint32_t *>(rs + (((p & ~3u) + 4u * k) % IQ_RING_BYTES));
+  return make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh),
+                    __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
+}
+
+template <bool MATERIALISE>
 __global__ void __launch_bounds__(256) fifo_read_kernel(const uint8_t *__restrict__ ring,
+                                                        const uint8_t *__restrict__ tails,
                                                         uint8_t *__restrict__ frames,
                                                         const StepCtl *__restrict__ ctl) {
   const int s = blockIdx.y;
@@ -121,21 +133,29 @@ __global__ void __launch_bounds__(256) fifo_read_kernel(const uint8_t *__restric
   const uint8_t *rs = ring + (uint64_t)s * IQ_RING_BYTES;
   uint8_t *fs = frames + (uint64_t)s * DABGPU_TF_BYTES;
   const uint32_t vec = blockIdx.x * blockDim.x + threadIdx.x;
+  if (MATERIALISE) {
+    // the previous frame was never copied (ring mode): rebuild sdr->buffer as it stood, because a
+    // short read below leaves part of it in place
+    if (!c->mat) return;
+    const uint32_t b = 16u * vec;
+    uint4 v;
+    if (b < TAIL_OFF)
+      v = ring_load16(rs, c->mat_pos + b);
+    else
+      v = *reinterpret_cast<const uint4 *>(tails + (uint64_t)s * TAIL_BYTES + (b - TAIL_OFF));
+    *reinterpret_cast<uint4 *>(fs + b) = v;
+    return;
+  }
+  if (c->src_ring) return;
   // segment 0 always lands at offset 0: 16 destination bytes per thread from an even, possibly
   // unaligned ring position (all shifts are even byte counts)
   const uint32_t n0 = c->rd_bytes[0];
   if (16u * vec < n0) {
-    const uint32_t p = c->rd_pos[0] + 16u * vec;
-    const uint32_t sh = (p & 3u) * 8u;
-    uint32_t w[5];
-#pragma unroll
-    for (int k = 0; k < 5; k++) w[k] = *reinterpret_cast<const uint32_t *>(rs + (((p & ~3u) + 4u * k) % IQ_RING_BYTES));
-    uint32_t o[4];
-#pragma unroll
-    for (int k = 0; k < 4; k++) o[k] = __funnelshift_r(w[k], w[k + 1], sh);
+    const uint4 o4 = ring_load16(rs, c->rd_pos[0] + 16u * vec);
     if (16u * vec + 16u <= n0) {
-      *reinterpret_cast<uint4 *>(fs + 16u * vec) = make_uint4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<uint4 *>(fs + 16u * vec) = o4;
     } else {
+      const uint32_t o[4] = {o4.x, o4.y, o4.z, o4.w};
       for (uint32_t b = 0; 16u * vec + b < n0; b++) fs[16u * vec + b] = (uint8_t)(o[b >> 2] >> (8 * (b & 3)));
     }
   }
@@ -145,11 +165,49 @@ __global__ void __launch_bounds__(256) fifo_read_kernel(const uint8_t *__restric
     fs[c->rd_dst[1] + b] = rs[(c->rd_pos[1] + b) % IQ_RING_BYTES];
 }
 
-int launch_fifo_read(const uint8_t *d_ring, uint8_t *d_frames, const StepCtl *d_ctl, int n_streams,
-                     cudaStream_t st) {
+int launch_fifo_read(const uint8_t *d_ring, const uint8_t *d_tails, uint8_t *d_frames, const StepCtl *d_ctl,
+                     int n_streams, bool materialise, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
   dim3 grid(DABGPU_TF_BYTES / 16 / 256, n_streams);
-  fifo_read_kernel<<<grid, 256, 0, st>>>(d_ring, d_frames, d_ctl);
+  if (materialise)
+    fifo_read_kernel<true><<<grid, 256, 0, st>>>(d_ring, d_tails, d_frames, d_ctl);
+  else
+    fifo_read_kernel<false><<<grid, 256, 0, st>>>(d_ring, d_tails, d_frames, d_ctl);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// tail[j] = byte TAIL_OFF + j of the stream's logical frame buffer after this step's read
+__global__ void __launch_bounds__(128) tail_update_kernel(const uint8_t *__restrict__ ring,
+                                                          const uint8_t *__restrict__ frames,
+                                                          uint8_t *__restrict__ tails,
+                                                          const StepCtl *__restrict__ ctl) {
+  const int s = blockIdx.x;
+  const StepCtl *c = &ctl[s];
+  if (!c->rd_bytes[0] && !c->rd_bytes[1]) return;  // no read this step
+  uint8_t *t = tails + (uint64_t)s * TAIL_BYTES;
+  const uint32_t j = 16u * threadIdx.x;  // 128 threads x 16 bytes
+  if (!c->src_ring) {
+    *reinterpret_cast<uint4 *>(t + j) =
+        *reinterpret_cast<const uint4 *>(frames + (uint64_t)s * DABGPU_TF_BYTES + TAIL_OFF + j);
+    return;
+  }
+  const uint32_t n0 = c->rd_bytes[0];  // fresh bytes; the rest of the buffer keeps its old content
+  const uint32_t b = TAIL_OFF + j;
+  if (b >= n0) return;
+  const uint4 v = ring_load16(ring + (uint64_t)s * IQ_RING_BYTES, c->src_pos + b);
+  if (b + 16u <= n0) {
+    *reinterpret_cast<uint4 *>(t + j) = v;
+  } else {
+    const uint32_t o[4] = {v.x, v.y, v.z, v.w};
+    for (uint32_t k = 0; b + k < n0; k++) t[j + k] = (uint8_t)(o[k >> 2] >> (8 * (k & 3)));
+  }
+}
+
+int launch_tail_update(const uint8_t *d_ring, const uint8_t *d_frames, uint8_t *d_tails, const StepCtl *d_ctl,
+                       int n_streams, cudaStream_t st) {
+  if (n_streams <= 0) return DABGPU_OK;
+  tail_update_kernel<<<n_streams, 128, 0, st>>>(d_ring, d_frames, d_tails, d_ctl);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }
@@ -336,11 +394,14 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-enum { SYM_BYTES = 4096, N_STAGES = 3 };
+enum { SYM_BYTES = 4096, STAGE_BYTES = SYM_BYTES + 16, N_STAGES = 3 };
 
 struct DemodSmem {
-  float2 xch[XCH_ELEMS];                       // 16640 B
-  __align__(16) uint8_t stage[N_STAGES][SYM_BYTES];
+  float2 xch[XCH_ELEMS];
+  // a symbol is fetched from the 16-byte aligned address below its first byte (TMA needs aligned
+  // sources; ring windows start at any even offset), hence 16 spare bytes per stage
+  __align__(16) uint8_t stage[N_STAGES][STAGE_BYTES];
+  __align__(16) uint8_t tailbuf[TAIL_BYTES];   // second half of symbol 75 in ring mode
   uint8_t bits[3072];                          // one symbol's sliced bits, one per byte
   uint32_t planes[16][CIF_PLANE_WORDS];        // the CIF being assembled
   uint64_t full[N_STAGES];
@@ -349,8 +410,34 @@ struct DemodSmem {
 // symbol l of a frame starts (useful part) at this byte offset (input_sdr.c:116)
 __device__ __forceinline__ uint32_t sym_byte_off(int l) { return 2u * (2656u + 2552u * (uint32_t)l + 504u); }
 
+// where a stream's frame lives this step (see StepCtl) and how one symbol is fetched from it
+struct FrameSrc {
+  const uint8_t *ring, *tail, *frame;
+  uint32_t ring_mode, pos, delta;
+};
+
+// thread 0: start the TMA copies of symbol l into stage buffer `st`
+__device__ __forceinline__ void issue_symbol_load(DemodSmem &sm, const FrameSrc &src, int l, int st) {
+  const uint32_t off = sym_byte_off(l);
+  if (!src.ring_mode) {
+    mbar_expect_tx(&sm.full[st], SYM_BYTES);
+    tma_load_1d(sm.stage[st], src.frame + off, SYM_BYTES, &sm.full[st]);
+    return;
+  }
+  const bool last = l == 75;  // its second half may be stale: it comes from the tail store
+  const uint32_t need = (last ? SYM_BYTES - TAIL_BYTES : SYM_BYTES) + 16u;
+  const uint32_t a0 = ((src.pos + off) % IQ_RING_BYTES) & ~15u;
+  mbar_expect_tx(&sm.full[st], need + (last ? TAIL_BYTES : 0u));
+  const uint32_t first = min(need, IQ_RING_BYTES - a0);
+  tma_load_1d(sm.stage[st], src.ring + a0, first, &sm.full[st]);
+  if (first < need) tma_load_1d(sm.stage[st] + first, src.ring, need - first, &sm.full[st]);
+  if (last) tma_load_1d(sm.tailbuf, src.tail, TAIL_BYTES, &sm.full[st]);
+}
+
 template <bool DEBUG>
-__global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__restrict__ frames,
+__global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__restrict__ ring,
+                                                            const uint8_t *__restrict__ tails,
+                                                            const uint8_t *__restrict__ frames,
                                                             const StepCtl *__restrict__ ctl,
                                                             const SyncOut *__restrict__ sync,
                                                             uint8_t *__restrict__ fic_bits,
@@ -365,7 +452,13 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__
   if (!DEBUG) {
     if (!ctl[s].run || sync[s].ok != 1) return;
   }
-  const uint8_t *frame = frames + (uint64_t)s * DABGPU_TF_BYTES;
+  FrameSrc src;
+  src.frame = frames + (uint64_t)s * DABGPU_TF_BYTES;
+  src.ring_mode = DEBUG ? 0u : ctl[s].src_ring;
+  src.pos = DEBUG ? 0u : ctl[s].src_pos;
+  src.delta = src.ring_mode ? (src.pos & 15u) : 0u;
+  src.ring = DEBUG ? nullptr : ring + (uint64_t)s * IQ_RING_BYTES;
+  src.tail = DEBUG ? nullptr : tails + (uint64_t)s * TAIL_BYTES;
   const int l0 = seg == 0 ? 0 : 3 + 18 * (seg - 1);
   const int nsym = seg == 0 ? 4 : 19;
 
@@ -375,10 +468,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__
   }
   __syncthreads();
   if (p == 0) {
-    for (int i = 0; i < N_STAGES && i < nsym; i++) {
-      mbar_expect_tx(&sm.full[i], SYM_BYTES);
-      tma_load_1d(sm.stage[i], frame + sym_byte_off(l0 + i), SYM_BYTES, &sm.full[i]);
-    }
+    for (int i = 0; i < N_STAGES && i < nsym; i++) issue_symbol_load(sm, src, l0 + i, i);
   }
   FftTwiddles tw;
   load_twiddles(tw, p);
@@ -404,12 +494,20 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__
     const int l = l0 + i, st = i % N_STAGES;
     float2 v[16];
     mbar_wait(&sm.full[st], (uint32_t)(i / N_STAGES) & 1u);
-    load_symbol(v, sm.stage[st], p);
+    if (src.ring_mode && l == 75) {
+      const uint16_t *h0 = reinterpret_cast<const uint16_t *>(sm.stage[st] + src.delta);
+      const uint16_t *h1 = reinterpret_cast<const uint16_t *>(sm.tailbuf);
+#pragma unroll
+      for (int j = 0; j < 8; j++) v[j] = iq_to_sample(h0[p + 128 * j]);
+#pragma unroll
+      for (int j = 8; j < 16; j++) v[j] = iq_to_sample(h1[p + 128 * (j - 8)]);
+    } else {
+      load_symbol(v, sm.stage[st] + src.delta, p);
+    }
     __syncthreads();  // everyone has consumed the staging buffer -> refill it
     if (p == 0 && i + N_STAGES < nsym) {
       fence_proxy_async();
-      mbar_expect_tx(&sm.full[st], SYM_BYTES);
-      tma_load_1d(sm.stage[st], frame + sym_byte_off(l + N_STAGES), SYM_BYTES, &sm.full[st]);
+      issue_symbol_load(sm, src, l + N_STAGES, st);
     }
     fft2048_from_regs(v, tw, sm.xch, p);
     if (DEBUG) {
@@ -473,8 +571,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__
   }
 }
 
-int launch_demod(const uint8_t *d_frames, const StepCtl *d_ctl, const SyncOut *d_sync, uint8_t *d_fic_bits,
-                 uint8_t *d_cifs, int n_streams, cudaStream_t st) {
+int launch_demod(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
+                 const SyncOut *d_sync, uint8_t *d_fic_bits, uint8_t *d_cifs, int n_streams, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
   static bool attr_set = false;
   if (!attr_set) {
@@ -483,8 +581,8 @@ int launch_demod(const uint8_t *d_frames, const StepCtl *d_ctl, const SyncOut *d
     attr_set = true;
   }
   dim3 grid(5, n_streams);
-  demod_kernel<false><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_frames, d_ctl, d_sync, d_fic_bits, d_cifs,
-                                                                   nullptr, nullptr, nullptr);
+  demod_kernel<false><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_ring, d_tails, d_frames, d_ctl, d_sync,
+                                                                   d_fic_bits, d_cifs, nullptr, nullptr, nullptr);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }
@@ -500,8 +598,8 @@ int launch_demod_debug(const uint8_t *d_frame, float2 *d_symbols, float2 *d_symb
   // one "segment" walking all 76 symbols is what the debug variant needs: reuse seg 0 semantics
   // by launching the five segments; each writes its own rows
   dim3 grid(5, 1);
-  demod_kernel<true><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_frame, nullptr, nullptr, nullptr, nullptr,
-                                                                  d_symbols, d_symbols_d, d_bits);
+  demod_kernel<true><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(nullptr, nullptr, d_frame, nullptr, nullptr,
+                                                                  nullptr, nullptr, d_symbols, d_symbols_d, d_bits);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }
@@ -585,6 +683,18 @@ struct SrcU8 {
   __device__ __forceinline__ float real(int n) const { return u8_to_sample(f[2 * n]); }
   __device__ __forceinline__ float2 at(int n) const {
     return iq_to_sample(reinterpret_cast<const uint16_t *>(f)[n]);
+  }
+};
+// the frame through the ring window + tail store (StepCtl.src_ring == 1)
+struct SrcRing {
+  const uint8_t *ring, *tail;
+  uint32_t pos;
+  __device__ __forceinline__ const uint8_t *byte_ptr(uint32_t b) const {
+    return b < TAIL_OFF ? ring + (pos + b) % IQ_RING_BYTES : tail + (b - TAIL_OFF);
+  }
+  __device__ __forceinline__ float real(int n) const { return u8_to_sample(*byte_ptr(2u * (uint32_t)n)); }
+  __device__ __forceinline__ float2 at(int n) const {
+    return iq_to_sample(*reinterpret_cast<const uint16_t *>(byte_ptr(2u * (uint32_t)n)));
   }
 };
 struct SrcI8 {
@@ -751,46 +861,57 @@ __device__ float fine_freq(SyncSmem &sm, const Src &src) {
   return block_sum(sm, acc) / 504.f / (2.f * 3.14159265358979323846f) * 1000.f;
 }
 
-// the synchroniser half of sdr_demod (input_sdr.c:65-112) for every stream with ctl.run
-__global__ void __launch_bounds__(FFT_THREADS) sync_kernel(const uint8_t *__restrict__ frames,
+// the synchroniser half of sdr_demod (input_sdr.c:65-112) on one frame
+template <typename Src>
+__device__ void sync_frame(SyncSmem &sm, const Src &src, bool force, SyncOut &r) {
+  r.ok = 0;
+  r.coarse_freq_shift = 0;
+  r.stage = 1;
+  r.coarse_timeshift = coarse_time_sync(sm, src, force, &r.null_energy);
+  if (r.coarse_timeshift != 0) return;
+  FftTwiddles tw;
+  load_twiddles(tw, threadIdx.x);
+  fft_window(sm, src, 2656 + 504, tw);
+  r.fine_timeshift = fine_time_from_spec(sm);
+  // input_sdr.c:91: the reference indexes the frame with the *byte* shift here
+  fft_window(sm, src, 2656 + 505 + r.fine_timeshift, tw);
+  r.coarse_freq_shift = coarse_freq_from_spec(sm);
+  r.stage = 2;
+  if (abs(r.coarse_freq_shift) > 1) return;
+  r.fine_freq_shift = fine_freq(sm, src);
+  r.ok = 1;
+  r.stage = 3;
+}
+
+// ... for every stream with ctl.run
+__global__ void __launch_bounds__(FFT_THREADS) sync_kernel(const uint8_t *__restrict__ ring,
+                                                           const uint8_t *__restrict__ tails,
+                                                           const uint8_t *__restrict__ frames,
                                                            const StepCtl *__restrict__ ctl,
                                                            SyncOut *__restrict__ out) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SyncSmem &sm = *reinterpret_cast<SyncSmem *>(smem_raw);
-  const int s = blockIdx.x, p = threadIdx.x;
+  const int s = blockIdx.x;
   if (!ctl[s].run) return;
-  const SrcU8 src{frames + (uint64_t)s * DABGPU_TF_BYTES};
   SyncOut r = out[s];  // fine_timeshift / fine_freq_shift persist across early exits (sdr_state_t)
-  r.ok = 0;
-  r.coarse_freq_shift = 0;
-  r.stage = 1;
-  r.coarse_timeshift = coarse_time_sync(sm, src, ctl[s].force_timesync != 0, &r.null_energy);
-  if (r.coarse_timeshift == 0) {
-    FftTwiddles tw;
-    load_twiddles(tw, p);
-    fft_window(sm, src, 2656 + 504, tw);
-    r.fine_timeshift = fine_time_from_spec(sm);
-    // input_sdr.c:91: the reference indexes the frame with the *byte* shift here
-    fft_window(sm, src, 2656 + 505 + r.fine_timeshift, tw);
-    r.coarse_freq_shift = coarse_freq_from_spec(sm);
-    r.stage = 2;
-    if (abs(r.coarse_freq_shift) <= 1) {
-      r.fine_freq_shift = fine_freq(sm, src);
-      r.ok = 1;
-      r.stage = 3;
-    }
-  }
-  if (p == 0) out[s] = r;
+  const bool force = ctl[s].force_timesync != 0;
+  if (ctl[s].src_ring)
+    sync_frame(sm, SrcRing{ring + (uint64_t)s * IQ_RING_BYTES, tails + (uint64_t)s * TAIL_BYTES, ctl[s].src_pos},
+               force, r);
+  else
+    sync_frame(sm, SrcU8{frames + (uint64_t)s * DABGPU_TF_BYTES}, force, r);
+  if (threadIdx.x == 0) out[s] = r;
 }
 
-int launch_sync(const uint8_t *d_frames, const StepCtl *d_ctl, SyncOut *d_out, int n_streams, cudaStream_t st) {
+int launch_sync(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
+                SyncOut *d_out, int n_streams, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(sync_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SyncSmem)));
     attr_set = true;
   }
-  sync_kernel<<<n_streams, FFT_THREADS, sizeof(SyncSmem), st>>>(d_frames, d_ctl, d_out);
+  sync_kernel<<<n_streams, FFT_THREADS, sizeof(SyncSmem), st>>>(d_ring, d_tails, d_frames, d_ctl, d_out);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }

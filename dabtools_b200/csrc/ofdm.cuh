@@ -6,7 +6,11 @@
 
 namespace dabgpu {
 
-enum : uint32_t { IQ_RING_BYTES = 196608u * 2u * 4u };  // input_sdr.c:170: FIFO of four frames
+enum : uint32_t {
+  IQ_RING_BYTES = 196608u * 2u * 4u,  // input_sdr.c:170: FIFO of four frames
+  TAIL_BYTES = 2048u,                 // >= the largest stale tail (negative fine time shift: 1536 bytes)
+  TAIL_OFF = 393216u - TAIL_BYTES
+};
 
 // Per-stream, per-step control block, written by the host FSM, read by the kernels.
 struct StepCtl {
@@ -18,6 +22,14 @@ struct StepCtl {
   uint32_t rd_pos[2];    // ring offsets
   uint32_t rd_dst[2];    // destination offsets inside the 393216-byte frame buffer
   uint32_t rd_bytes[2];  // 0 = nothing
+  // ---- where the kernels find the frame (sdr->buffer).  src_ring = 1: the read was one plain
+  //      window, so byte b of the frame is ring[(src_pos + b) % RING] for b < TAIL_OFF and
+  //      tail[b - TAIL_OFF] above (the tail store carries the stale bytes a negative shift leaves
+  //      behind); no copy is made.  src_ring = 0: the persistent frame buffer (rare: FIFO ran dry).
+  uint32_t src_ring;
+  uint32_t src_pos;
+  uint32_t mat;          // materialise the previous (ring-mode) frame into the frame buffer first
+  uint32_t mat_pos;
   // ---- sync + demod (sdr_demod, input_sdr.c:60-162)
   uint32_t run;             // frame goes through the synchronisers / demodulator
   uint32_t force_timesync;  // sdr->force_timesync on entry
@@ -38,12 +50,18 @@ struct SyncOut {
 
 int launch_ingest(const uint8_t *d_src, uint64_t src_pitch, uint32_t chunk_len, uint8_t *d_ring,
                   const StepCtl *d_ctl, int n_streams, cudaStream_t st);
-int launch_fifo_read(const uint8_t *d_ring, uint8_t *d_frames, const StepCtl *d_ctl, int n_streams,
-                     cudaStream_t st);
-int launch_sync(const uint8_t *d_frames, const StepCtl *d_ctl, SyncOut *d_out, int n_streams, cudaStream_t st);
+// fallback copy into the frame buffer for the streams with src_ring == 0 (materialise = true runs
+// the "previous frame" pass for the streams with mat == 1 instead)
+int launch_fifo_read(const uint8_t *d_ring, const uint8_t *d_tails, uint8_t *d_frames, const StepCtl *d_ctl,
+                     int n_streams, bool materialise, cudaStream_t st);
+// keep the tail store equal to the last TAIL_BYTES of every stream's logical frame buffer
+int launch_tail_update(const uint8_t *d_ring, const uint8_t *d_frames, uint8_t *d_tails, const StepCtl *d_ctl,
+                       int n_streams, cudaStream_t st);
+int launch_sync(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
+                SyncOut *d_out, int n_streams, cudaStream_t st);
 // fic_bits: [n_streams][9216] one byte per bit (reference layout); MSC goes to the CIF store as planes
-int launch_demod(const uint8_t *d_frames, const StepCtl *d_ctl, const SyncOut *d_sync, uint8_t *d_fic_bits,
-                 uint8_t *d_cifs, int n_streams, cudaStream_t st);
+int launch_demod(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
+                 const SyncOut *d_sync, uint8_t *d_fic_bits, uint8_t *d_cifs, int n_streams, cudaStream_t st);
 
 // debug / parity variants on a single frame buffer: raw spectra (fftshifted, 76x2048 complex
 // float), DQPSK products (rows 1..75) and the reference's byte-per-bit demapped output
