@@ -103,7 +103,7 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   }
   {
     const char *env = getenv("DABGPU_HOST_THREADS");
-    int nt = env ? atoi(env) : 4;
+    int nt = env ? atoi(env) : 6;
     const int hw = (int)std::thread::hardware_concurrency();
     if (hw > 0) nt = std::min(nt, std::max(0, hw - 1));
     if (S >= 64 && nt > 0) pool.start(nt);
