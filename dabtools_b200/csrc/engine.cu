@@ -121,6 +121,10 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   if ((rc = h_fic_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
   CUDA_TRY(cudaStreamCreateWithFlags(&st_msc, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithFlags(&st_fic, cudaStreamNonBlocking));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_fic_ready, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_demod_done, cudaEventDisableTiming));
+  vb_fic.small_ctas = true;
   for (int i = 0; i < 2; i++) {
     CUDA_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
@@ -156,6 +160,7 @@ int Engine::enable_timing(bool on) {
 int Engine::collect_timing(cudaStream_t st) {
   if (!timing) return DABGPU_OK;
   CUDA_TRY(cudaStreamSynchronize(st));
+  CUDA_TRY(cudaStreamSynchronize(st_fic));
   CUDA_TRY(cudaStreamSynchronize(st_msc));
   for (int k = 0; k < K_COUNT; k++) {
     if (!ev_used[k]) continue;
@@ -176,6 +181,13 @@ int Engine::join_msc(cudaStream_t user) {
 
 void Engine::destroy() {
   pool.stop();
+  if (st_fic) {
+    cudaStreamSynchronize(st_fic);
+    cudaStreamDestroy(st_fic);
+    st_fic = nullptr;
+    cudaEventDestroy(ev_fic_ready);
+    cudaEventDestroy(ev_demod_done);
+  }
   if (st_copy) {
     cudaStreamSynchronize(st_copy);
     cudaStreamDestroy(st_copy);
@@ -412,6 +424,11 @@ int Engine::flush_msc(cudaStream_t user) {
   // bound the lag of the MSC stream: the previous batch must be done before the next one is
   // queued, which keeps every CIF/FIB slot a queued batch references out of the front-end's reach
   if (msc_inflight) CUDA_TRY(cudaEventSynchronize(ev_msc_done));
+  // the CIF symbols of the newest frame may still be on their way into the CIF store
+  if (demod_pending) {
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_demod_done, 0));
+    demod_pending = false;
+  }
   // several flushes inside one call (rare: a multiplex change) append to the call's output
   const int base = n_eti, n_new = (int)etijobs.size();
   n_eti = base + n_new;
@@ -736,14 +753,23 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
                             d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), S, st)))
         return rc;
       t1(K_SYNC, st);
+      // FIC symbols first; their decoding then runs on st_fic next to the CIF symbols on `st`
       t0(K_DEMOD, st);
       if ((rc = launch_demod(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
-                             d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(),
-                             d_ficbits.as<uint8_t>(), d_cifs.as<uint8_t>(), S, st)))
+                             d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), d_ficbits.as<uint8_t>(),
+                             d_cifs.as<uint8_t>(), S, 0, 1, st)))
+        return rc;
+      CUDA_TRY(cudaEventRecord(ev_fic_ready, st));
+      if ((rc = launch_demod(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+                             d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), d_ficbits.as<uint8_t>(),
+                             d_cifs.as<uint8_t>(), S, 1, 4, st)))
         return rc;
       t1(K_DEMOD, st);
-      CUDA_TRY(cudaMemcpyAsync(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st));
-      if ((rc = fic_and_backend(st, d_ficbits.as<uint8_t>(), 9216, h_sync.as<SyncOut>()))) return rc;
+      CUDA_TRY(cudaEventRecord(ev_demod_done, st));
+      demod_pending = true;
+      CUDA_TRY(cudaStreamWaitEvent(st_fic, ev_fic_ready, 0));
+      CUDA_TRY(cudaMemcpyAsync(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st_fic));
+      if ((rc = fic_and_backend(st_fic, d_ficbits.as<uint8_t>(), 9216, h_sync.as<SyncOut>()))) return rc;
     }
   }
   for (int s = 0; s < S; s++) tuner_feedback(front[s]);

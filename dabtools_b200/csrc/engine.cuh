@@ -98,6 +98,11 @@ struct Engine {
   DevBuf d_cifjobs, d_subjobs, d_etijobs, d_planeoff, d_gather_idx, d_gather_out;
   PinBuf h_ctl, h_sync, h_fic_out, h_jobs, h_msc[2], h_eti, h_chunk;
   // MSC work runs on its own stream so that it overlaps the next frames' front-end kernels
+  // ... and the FIC chain (depuncture, Viterbi, CRC, copy back) on another one, so that the host
+  // gets the FIBs while the CIF symbols of the same frame are still being demodulated
+  cudaStream_t st_fic = nullptr;
+  cudaEvent_t ev_fic_ready = nullptr, ev_demod_done = nullptr;
+  bool demod_pending = false;
   cudaStream_t st_msc = nullptr;
   cudaEvent_t ev_up[2] = {}, ev_msc_done = nullptr;
   int msc_buf = 0;
@@ -172,6 +177,7 @@ struct Engine {
  private:
   int fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride,
                       const SyncOut *h_sync_or_null);
+  int after_fic(cudaStream_t st);
   int refresh_layout(int s);
   int upload_tables(cudaStream_t st);
 };

@@ -444,11 +444,11 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__
                                                             uint8_t *__restrict__ cifs,
                                                             float2 *__restrict__ dbg_sym,
                                                             float2 *__restrict__ dbg_symd,
-                                                            uint8_t *__restrict__ dbg_bits) {
+                                                            uint8_t *__restrict__ dbg_bits, int seg_first) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   DemodSmem &sm = *reinterpret_cast<DemodSmem *>(smem_raw);
   const int p = threadIdx.x;
-  const int s = blockIdx.y, seg = blockIdx.x;  // seg 0: PRS + FIC symbols, seg 1..4: CIF seg-1
+  const int s = blockIdx.y, seg = blockIdx.x + seg_first;  // seg 0: PRS + FIC symbols, seg 1..4: CIF seg-1
   if (!DEBUG) {
     if (!ctl[s].run || sync[s].ok != 1) return;
   }
@@ -572,7 +572,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__
 }
 
 int launch_demod(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
-                 const SyncOut *d_sync, uint8_t *d_fic_bits, uint8_t *d_cifs, int n_streams, cudaStream_t st) {
+                 const SyncOut *d_sync, uint8_t *d_fic_bits, uint8_t *d_cifs, int n_streams, int seg_first,
+                 int seg_count, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
   static bool attr_set = false;
   if (!attr_set) {
@@ -580,9 +581,10 @@ int launch_demod(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d
                                   (int)sizeof(DemodSmem)));
     attr_set = true;
   }
-  dim3 grid(5, n_streams);
+  dim3 grid(seg_count, n_streams);
   demod_kernel<false><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_ring, d_tails, d_frames, d_ctl, d_sync,
-                                                                   d_fic_bits, d_cifs, nullptr, nullptr, nullptr);
+                                                                   d_fic_bits, d_cifs, nullptr, nullptr, nullptr,
+                                                                   seg_first);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }
@@ -599,7 +601,7 @@ int launch_demod_debug(const uint8_t *d_frame, float2 *d_symbols, float2 *d_symb
   // by launching the five segments; each writes its own rows
   dim3 grid(5, 1);
   demod_kernel<true><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(nullptr, nullptr, d_frame, nullptr, nullptr,
-                                                                  nullptr, nullptr, d_symbols, d_symbols_d, d_bits);
+                                                                  nullptr, nullptr, d_symbols, d_symbols_d, d_bits, 0);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }

@@ -24,6 +24,7 @@ struct VitBatch {
   uint64_t dec_words = 0;
   uint64_t total_steps = 0;  // sum over codewords of nbits+6 (for ACS/s accounting)
   int n_ctas = 0;
+  bool small_ctas = false;  // one single-warp CTA per group instead of the persistent layout
 
   void clear() {
     jobs.clear();
@@ -53,6 +54,13 @@ struct VitBatch {
       dec_words += vit_group_dec_words(g.nsteps);
       g0.push_back(g);
       i = j;
+    }
+    if (small_ctas) {
+      groups.swap(g0);
+      n_ctas = (int)groups.size();
+      bin_start.resize(groups.size() + 1);
+      for (size_t i = 0; i <= groups.size(); i++) bin_start[i] = (uint32_t)i;
+      return;
     }
     // LPT over the warp schedulers (4 per SM); a scheduler's groups are then dealt round-robin to
     // its VIT_WARPS/4 resident warps so that they overlap each other's latencies
@@ -119,13 +127,12 @@ struct VitBatch {
       CUDA_TRY(cudaMemcpyAsync(d_groups.p, (char *)h_stage.p + jb, gb, cudaMemcpyHostToDevice, st));
       CUDA_TRY(cudaMemcpyAsync(d_bins.p, (char *)h_stage.p + jb + gb, bb, cudaMemcpyHostToDevice, st));
     }
-    return launch_viterbi(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
-                          d_bins.as<uint32_t>(), n_ctas, st);
+    return relaunch(d_steps, d_out, st);
   }
   // launch again with the descriptors of the last run() (identical job list by construction)
   int relaunch(const uint8_t *d_steps, uint8_t *d_out, cudaStream_t st) {
     return launch_viterbi(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
-                          d_bins.as<uint32_t>(), n_ctas, st);
+                          d_bins.as<uint32_t>(), n_ctas, small_ctas ? 1 : VIT_WARPS, st);
   }
   void release() {
     d_jobs.release();

@@ -247,12 +247,13 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut
 // groups longest-processing-time-first, first over the warp schedulers (warp w runs on scheduler
 // w % 4) so that every scheduler gets the same number of trellis steps, then over the scheduler's
 // VIT_WARPS/4 warps so that they all stay busy until the end of the launch.
-__global__ void __launch_bounds__(32 * VIT_WARPS, 1) viterbi_kernel(const uint8_t *__restrict__ steps,
-                                                                    uint8_t *__restrict__ out,
-                                                                    uint2 *__restrict__ dec,
-                                                                    const VitJob *__restrict__ jobs,
-                                                                    const VitGroup *__restrict__ groups,
-                                                                    const uint32_t *__restrict__ bin_start) {
+template <int WARPS>
+__global__ void __launch_bounds__(32 * WARPS, 1) viterbi_kernel(const uint8_t *__restrict__ steps,
+                                                                uint8_t *__restrict__ out,
+                                                                uint2 *__restrict__ dec,
+                                                                const VitJob *__restrict__ jobs,
+                                                                const VitGroup *__restrict__ groups,
+                                                                const uint32_t *__restrict__ bin_start) {
   __shared__ uint2 lut[256];  // step byte -> {D, Dc}: per-class distances and complements
   for (int sb = threadIdx.x; sb < 256; sb += blockDim.x) {
     const uint32_t r = sb & 15, e = sb >> 4;
@@ -262,15 +263,20 @@ __global__ void __launch_bounds__(32 * VIT_WARPS, 1) viterbi_kernel(const uint8_
   }
   __syncthreads();
   const int lane = threadIdx.x & 31;
-  const uint32_t bin = blockIdx.x * VIT_WARPS + (threadIdx.x >> 5);
+  const uint32_t bin = blockIdx.x * WARPS + (threadIdx.x >> 5);
   const uint32_t g0 = bin_start[bin], g1 = bin_start[bin + 1];
   for (uint32_t gi = g0; gi < g1; gi++) decode_group(groups[gi], lut, steps, out, dec, jobs, lane);
 }
 
 int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
-                   const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, cudaStream_t st) {
+                   const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, int warps_per_cta,
+                   cudaStream_t st) {
   if (n_ctas <= 0) return DABGPU_OK;
-  viterbi_kernel<<<n_ctas, 32 * VIT_WARPS, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups, d_bin_start);
+  if (warps_per_cta == 1)
+    viterbi_kernel<1><<<n_ctas, 32, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups, d_bin_start);
+  else
+    viterbi_kernel<VIT_WARPS><<<n_ctas, 32 * VIT_WARPS, 0, st>>>(d_steps, d_out, d_dec, d_jobs, d_groups,
+                                                                 d_bin_start);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }

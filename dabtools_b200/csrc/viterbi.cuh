@@ -39,8 +39,11 @@ enum { VIT_WARPS = 12 };
 int device_sm_count();
 // persistent launch: n_ctas CTAs of VIT_WARPS warps; warp-bin b owns groups
 // d_bin_start[b] .. d_bin_start[b+1] (n_ctas * VIT_WARPS + 1 entries)
+// warps_per_cta: VIT_WARPS (persistent, one CTA per SM) or 1 (one small CTA per work list: a
+// footprint that can share SMs with other kernels, used for the latency-critical FIC batches)
 int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
-                   const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, cudaStream_t st);
+                   const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, int warps_per_cta,
+                   cudaStream_t st);
 
 // step-byte producers -------------------------------------------------------------------
 // (a) from the reference's soft-symbol bytes (4 per step; <128 -> 0, 128 -> erasure, >128 -> 1)
