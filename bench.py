@@ -54,50 +54,120 @@ def peaks():
 
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md's clocks line).
 
+    NVML is queried in-process (pynvml) from a thread that is already running before the warm-up, so
+    that neither a process start-up nor NVML initialisation falls into the timed region; begin()/end()
+    mark the region and only samples taken inside it are reported.  Falls back to an `nvidia-smi -lms`
+    child started equally early."""
+
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, gpu_index: int):
+    def __init__(self, gpu_index: int, period_s: float = 0.004):
         self.gpu = gpu_index
+        self.period = period_s
+        self.samples = []          # (t, sm_mhz, reasons bitmask or set)
+        self.window = [None, None]
+        self.stop_flag = False
+        self.max_mhz = None
+        self.mode = None
+        self.thread = None
         self.proc = None
-        self.lines = []
 
     def start(self):
         try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates physical devices; honour CUDA_VISIBLE_DEVICES when it is a list of indices
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            idx = self.gpu
+            if vis:
+                try:
+                    idx = int(vis.split(",")[self.gpu])
+                except (ValueError, IndexError):
+                    idx = self.gpu
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+            self.nv = pynvml
+            self.mode = "nvml"
+            self.thread = threading.Thread(target=self._poll_nvml, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.mode = None
+        try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-i", str(self.gpu), "-lms", "100"], stdout=subprocess.PIPE, text=True)
-            self.t = threading.Thread(target=self._read, daemon=True)
-            self.t.start()
+                                          "-i", str(self.gpu), "-lms", "20"], stdout=subprocess.PIPE, text=True)
+            self.mode = "nvidia-smi"
+            self.thread = threading.Thread(target=self._read_smi, daemon=True)
+            self.thread.start()
         except Exception:
             self.proc = None
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.lines.append(line.strip())
+    def _poll_nvml(self):
+        nv = self.nv
+        while not self.stop_flag:
+            try:
+                mhz = float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    mask = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                self.samples.append((time.perf_counter(), mhz, mask))
+            except Exception:
+                pass
+            time.sleep(self.period)
 
-    def stop(self) -> dict:
-        if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
-        self.proc.terminate()
-        sm, mx, reasons = [], [], set()
-        for ln in self.lines:
-            f = [x.strip() for x in ln.split(",")]
+    def _read_smi(self):
+        for line in self.proc.stdout:
+            f = [x.strip() for x in line.split(",")]
             if len(f) < 8:
                 continue
             try:
-                sm.append(float(f[1]))
-                mx.append(float(f[2]))
+                mhz, mx = float(f[1]), float(f[2])
             except ValueError:
                 continue
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+            self.max_mhz = mx
+            mask = 0
+            for (name, bit), v in zip(self.REASONS, f[4:8]):
                 if v.lower().startswith("active"):
-                    reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                    mask |= bit
+            self.samples.append((time.perf_counter(), mhz, mask))
+
+    def begin(self):
+        self.window[0] = time.perf_counter()
+
+    def end(self):
+        self.window[1] = time.perf_counter()
+
+    def stop(self) -> dict:
+        self.stop_flag = True
+        if self.proc:
+            self.proc.terminate()
+        if self.thread:
+            self.thread.join(timeout=1.0)
+        if self.mode is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["NVML and nvidia-smi unavailable"], "samples": 0}
+        t0, t1 = self.window
+        inside = [x for x in self.samples if t0 is not None and t1 is not None and t0 <= x[0] <= t1]
+        note = None
+        if not inside and self.samples and t0 is not None:
+            # region shorter than the sampling period: take the samples nearest to it
+            inside = sorted(self.samples, key=lambda x: abs(x[0] - 0.5 * (t0 + t1)))[:3]
+            note = "nearest samples (region shorter than the sampling period)"
+        mask = 0
+        for x in inside:
+            mask |= x[2]
+        out = {"sm_mhz": float(np.median([x[1] for x in inside])) if inside else None, "sm_max_mhz": self.max_mhz,
+               "reasons": [name for name, bit in self.REASONS if mask & bit], "samples": len(inside),
+               "source": self.mode}
+        if note:
+            out["note"] = note
+        return out
 
 
 # ------------------------------------------------------------------------------------------------
@@ -231,16 +301,20 @@ def run_ours(args, rank, world, local_rank):
     locked = sum(eng.status(s).locked for s in range(S))
     if locked != S:
         raise RuntimeError(f"only {locked}/{S} streams locked after set-up")
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
     n = 0
     for i in range(W):
         n += step_device(eng, setup_steps + i)
     assert n >= S * TFS_PER_STEP * FRAMES_PER_TF * (W - 2), f"steady state not reached: {n} frames in warm-up"
+    # start from an empty pipeline so that the frames counted are exactly the frames fed
+    eng.flush()
+    eng.join()
     launches0 = lib.launch_count()
     host_t0 = eng.host_times()
-    sampler = ClockSampler(local_rank)
     barrier()
-    if rank == 0:
-        sampler.start()
+    sampler.begin()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     frames = 0
@@ -251,6 +325,7 @@ def run_ours(args, rank, world, local_rank):
     eng.join()              # ... and so does the MSC stream's last batch
     e1.record()
     barrier()
+    sampler.end()
     clocks = sampler.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = lib.launch_count() - launches0
@@ -271,37 +346,46 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- end to end: pinned host IQ in, ETI out to host ----------------
     eng = lib.Engine(S)
     eng.set_msc_batch(args.e2e_msc_batch)
-    for i in range(setup_steps + W):
+    for i in range(setup_steps):
         step_device(eng, i)
-    host_in = torch.empty((k_e2e, CALLS_PER_STEP, S, CALL_BYTES), dtype=torch.uint8, pin_memory=True)
-    for i in range(k_e2e):
+    w_e2e = 2   # warm-up steps through the host path (staging buffers, steady batching)
+    host_in = torch.empty((w_e2e + k_e2e, CALLS_PER_STEP, S, CALL_BYTES), dtype=torch.uint8, pin_memory=True)
+    for i in range(w_e2e + k_e2e):
         for c in range(CALLS_PER_STEP):
-            off = (setup_steps + W + i) * step_bytes + c * CALL_BYTES
+            off = (setup_steps + i) * step_bytes + c * CALL_BYTES
             host_in[i, c].copy_(data[:, off: off + CALL_BYTES])
-    host_out_t = torch.empty((S * FRAMES_PER_TF * args.e2e_msc_batch, 6144), dtype=torch.uint8, pin_memory=True)
+    host_out_t = torch.empty((S * FRAMES_PER_TF * (args.e2e_msc_batch + 1), 6144), dtype=torch.uint8,
+                             pin_memory=True)
     host_out = host_out_t.numpy()
+    calls = [host_in[i, c].numpy() for i in range(w_e2e + k_e2e) for c in range(CALLS_PER_STEP)]
+    AHEAD = 2   # uploads in flight ahead of the callback being processed
+
+    def run_calls(lo, hi):
+        """public API, software-pipelined: callbacks lo..hi-1; returns (frames, bytes copied back)"""
+        nf = nb = 0
+        for k in range(lo, min(lo + AHEAD, hi)):
+            eng.submit_iq(calls[k])
+        for k in range(lo, hi):
+            if k + AHEAD < hi:
+                eng.submit_iq(calls[k + AHEAD])
+            n = eng.feed_submitted()
+            if n:
+                eng.fetch_eti(host_out)
+                nf += n
+                nb += n * 6144
+        n = eng.flush()   # drain: frames still queued for a deferred MSC batch belong to these calls
+        if n:
+            eng.fetch_eti(host_out)
+            nf += n
+            nb += n * 6144
+        return nf, nb
+
+    run_calls(0, w_e2e * CALLS_PER_STEP)
     torch.cuda.synchronize()
     barrier()
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     f0.record()
-    e2e_frames = 0
-    d2h = 0
-    # public API, software-pipelined: the upload of callback k+1 overlaps the processing of k
-    calls = [host_in[i, c].numpy() for i in range(k_e2e) for c in range(CALLS_PER_STEP)]
-    eng.submit_iq(calls[0])
-    for k in range(len(calls)):
-        if k + 1 < len(calls):
-            eng.submit_iq(calls[k + 1])
-        n = eng.feed_submitted()
-        if n:
-            eti, ids = eng.fetch_eti(host_out)
-            e2e_frames += n
-            d2h += n * 6144
-    n = eng.flush()
-    if n:
-        eti, ids = eng.fetch_eti(host_out)
-        e2e_frames += n
-        d2h += n * 6144
+    e2e_frames, d2h = run_calls(w_e2e * CALLS_PER_STEP, len(calls))
     f1.record()
     barrier()
     e2e_ms = f0.elapsed_time(f1)
@@ -384,7 +468,7 @@ def run_ours(args, rank, world, local_rank):
             "d2h_bytes_per_step": int(d2h / max(k_e2e, 1)),
             "steps": k_e2e,
             "msc_batch_tf": args.e2e_msc_batch,
-            "api": "dabgpu_engine_submit_iq / feed_submitted / fetch_eti (upload of callback k+1 overlaps k)",
+            "api": "dabgpu_engine_submit_iq / feed_submitted / fetch_eti (uploads run two callbacks ahead)",
         },
         "roofline": {
             "kernel": "demod_kernel (FFT2048 x76 + DQPSK + freq de-interleave + slicing)",

@@ -118,17 +118,22 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   pend_of_stream.assign(S, 0);
   if ((rc = d_ens.reserve((size_t)S * sizeof(EnsDev)))) return rc;
   if ((rc = d_gather_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
-  if ((rc = h_fic_out.reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
+  for (int i = 0; i < 2; i++)
+    if ((rc = h_fic_out[i].reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
+  frame_slot.assign(S, 0);
   CUDA_TRY(cudaStreamCreateWithFlags(&st_msc, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
   CUDA_TRY(cudaStreamCreateWithFlags(&st_fic, cudaStreamNonBlocking));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_fic_ready, cudaEventDisableTiming));
-  CUDA_TRY(cudaEventCreateWithFlags(&ev_demod_done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_demod_done[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_demod_done[1], cudaEventDisableTiming));
   vb_fic.small_ctas = true;
-  for (int i = 0; i < 2; i++) {
+  for (int i = 0; i < N_STAGE; i++) {
     CUDA_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
   }
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_ctl[0], cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_ctl[1], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_up[0], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_up[1], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_msc_done, cudaEventDisableTiming));
@@ -186,13 +191,14 @@ void Engine::destroy() {
     cudaStreamDestroy(st_fic);
     st_fic = nullptr;
     cudaEventDestroy(ev_fic_ready);
-    cudaEventDestroy(ev_demod_done);
+    cudaEventDestroy(ev_demod_done[0]);
+    cudaEventDestroy(ev_demod_done[1]);
   }
   if (st_copy) {
     cudaStreamSynchronize(st_copy);
     cudaStreamDestroy(st_copy);
     st_copy = nullptr;
-    for (int i = 0; i < 2; i++) {
+    for (int i = 0; i < N_STAGE; i++) {
       cudaEventDestroy(ev_copied[i]);
       cudaEventDestroy(ev_consumed[i]);
       d_stage[i].release();
@@ -204,6 +210,8 @@ void Engine::destroy() {
     st_msc = nullptr;
     cudaEventDestroy(ev_up[0]);
     cudaEventDestroy(ev_up[1]);
+    cudaEventDestroy(ev_ctl[0]);
+    cudaEventDestroy(ev_ctl[1]);
     cudaEventDestroy(ev_msc_done);
   }
   if (ev[0][0])
@@ -213,7 +221,7 @@ void Engine::destroy() {
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
                   &d_subjobs, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
   for (DevBuf *b : db) b->release();
-  PinBuf *pb[] = {&h_ctl, &h_sync, &h_fic_out, &h_jobs, &h_msc[0], &h_msc[1], &h_eti, &h_chunk};
+  PinBuf *pb[] = {&h_ctl, &h_stepctl[0], &h_stepctl[1], &h_sync, &h_fic_out[0], &h_fic_out[1], &h_jobs, &h_msc[0], &h_msc[1], &h_eti, &h_chunk};
   for (PinBuf *b : pb) b->release();
   vb_fic.release();
   vb_msc.release();
@@ -290,38 +298,33 @@ int Engine::upload_tables(cudaStream_t st) {
   return DABGPU_OK;
 }
 
-// FIC decode of the `active` streams' frames, host state machines, MSC decode and ETI assembly.
+// FIC decode of the `active` streams' frames: depuncture, Viterbi, CRC, FIBs into the FIB store,
+// compact copy back to the host.  Nothing here waits for the GPU.
 // d_fic_src + s*fic_stride holds stream s' 9216 demapped FIC bits (one byte each).
-// sync: SyncOut per stream (front-end path) or null (demapped path: every active frame is "ok").
-int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride,
-                            const SyncOut *sync) {
+int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride) {
   int rc;
   const int na = (int)active.size();
   if (na == 0) return DABGPU_OK;
-
-  // ---- FIC: 4 groups per frame -> compact [na][384] FIBs + [na][12] CRC flags ----
+  // 4 groups per frame -> compact [na][384] FIBs + [na][12] CRC flags
   uint8_t *d_fib_c = d_gather_out.as<uint8_t>();
   uint8_t *d_crc_c = d_fib_c + (size_t)na * FIBS_PER_TF;
-  if ((rc = h_jobs.reserve((size_t)na * (sizeof(uint32_t) + sizeof(uint64_t))))) return rc;
+  const size_t idx_bytes = ((size_t)na * 4 + 7) & ~(size_t)7;
+  if ((rc = h_jobs.reserve((size_t)S * 12 + 8))) return rc;
   uint32_t *h_idx = h_jobs.as<uint32_t>();
-  uint64_t *h_dst = reinterpret_cast<uint64_t *>(h_jobs.as<uint8_t>() + (((size_t)na * 4 + 7) & ~(size_t)7));
-  if ((rc = h_jobs.reserve((((size_t)na * 4 + 7) & ~(size_t)7) + (size_t)na * 8))) return rc;
-  h_idx = h_jobs.as<uint32_t>();
-  h_dst = reinterpret_cast<uint64_t *>(h_jobs.as<uint8_t>() + (((size_t)na * 4 + 7) & ~(size_t)7));
+  uint64_t *h_dst = reinterpret_cast<uint64_t *>(h_jobs.as<uint8_t>() + idx_bytes);
   vb_fic.clear();
+  vb_fic.reserve_scale = std::max(1.0, (double)S / na);
   for (int a = 0; a < na; a++) {
     const int s = active[a];
     h_idx[a] = (uint32_t)s;
-    h_dst[a] = ((uint64_t)s * TF_SLOTS + (uint64_t)back[s].phys) * FIBS_PER_TF;
+    h_dst[a] = ((uint64_t)s * TF_SLOTS + (uint64_t)frame_slot[s]) * FIBS_PER_TF;
     for (int k = 0; k < 4; k++)
       vb_fic.add(((uint64_t)a * 4 + k) * FIC_ROW, (uint64_t)a * FIBS_PER_TF + 96 * k, 768, VIT_DESCRAMBLE);
   }
-  if ((rc = d_gather_idx.reserve((((size_t)na * 4 + 7) & ~(size_t)7) + (size_t)na * 8))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(d_gather_idx.p, h_jobs.p, (((size_t)na * 4 + 7) & ~(size_t)7) + (size_t)na * 8,
-                           cudaMemcpyHostToDevice, st));
+  if ((rc = d_gather_idx.reserve((size_t)S * 12 + 8))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(d_gather_idx.p, h_jobs.p, idx_bytes + (size_t)na * 8, cudaMemcpyHostToDevice, st));
   const uint32_t *d_idx = d_gather_idx.as<uint32_t>();
-  const uint64_t *d_dst = reinterpret_cast<const uint64_t *>(d_gather_idx.as<uint8_t>() +
-                                                             (((size_t)na * 4 + 7) & ~(size_t)7));
+  const uint64_t *d_dst = reinterpret_cast<const uint64_t *>(d_gather_idx.as<uint8_t>() + idx_bytes);
   t0(K_FIC_PREP, st);
   if ((rc = launch_prep_hard(d_fic_src, 2304, 4, fic_stride, d_idx, d_steps_fic.as<uint8_t>(), FIC_ROW, 4 * na,
                              d_fic_shape.as<ShapeDev>(), 774, st)))
@@ -333,52 +336,88 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
   trellis_steps += vb_fic.total_steps;
   if ((rc = launch_fib_crc(d_fib_c, d_crc_c, 12 * na, st))) return rc;
   if ((rc = launch_scatter_rows(d_fib_c, FIBS_PER_TF, d_dst, d_fibs.as<uint8_t>(), na, st))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(h_fic_out.p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(h_fic_out[fic_buf].p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), cudaMemcpyDeviceToHost,
+                           st));
+  return DABGPU_OK;
+}
+
+// Wait for the FIC results (and the synchroniser outputs) of the frames launched by this call, run
+// the part of sdr_demod that feeds back into the next FIFO read, and hand the frames that passed
+// to the back-end host logic (`lag`), which runs either right away or during the next call.
+// sync: SyncOut per stream (front-end path) or null (demapped path: every active frame is "ok").
+int Engine::fic_finish(cudaStream_t st, const SyncOut *sync, int demod_ev) {
+  const int na = (int)active.size();
+  if (na == 0) return DABGPU_OK;
   double tw = now_us();
   CUDA_TRY(cudaStreamSynchronize(st));
   host_us[H_WAIT] += now_us() - tw;
   tw = now_us();
-
-  // ---- host: per-stream sdr_demod epilogue + dab_process_frame (streams are independent) ----
-  const uint8_t *h_fibs = h_fic_out.as<uint8_t>();
-  const uint8_t *h_crc = h_fibs + (size_t)na * FIBS_PER_TF;
-  works.resize(na);
-  pool.run(na, [&](int a) {
-    const int s = active[a];
+  lag.valid = true;
+  lag.fic_buf = fic_buf;
+  lag.demod_ev = demod_ev;
+  lag.active.swap(active);
+  lag.proc.assign(na, 1);
+  lag.slot.resize(na);
+  for (int a = 0; a < na; a++) {
+    const int s = lag.active[a];
     FrontState &fr = front[s];
-    FrameWork &work = works[a];
-    work.n_eti = 0;
     fr.pending = false;
+    lag.slot[a] = frame_slot[s];
     if (sync) {
       // input_sdr.c:65-112: the order in which sdr_demod updates its state and bails out
       const SyncOut &so = sync[s];
+      lag.proc[a] = 0;
       fr.coarse_timeshift = so.coarse_timeshift;
       fr.force_timesync = 0;
       fr.last_ok = 0;
-      if (so.coarse_timeshift) return;
+      if (so.coarse_timeshift) continue;
       fr.fine_timeshift = so.fine_timeshift;
       fr.coarse_freq_shift = so.coarse_freq_shift;
       if (std::abs(so.coarse_freq_shift) > 1) {
         fr.force_timesync = 1;
-        return;
+        continue;
       }
       fr.fine_freq_shift = (double)so.fine_freq_shift;
       fr.last_ok = 1;
+      lag.proc[a] = 1;
     }
     stats[s].frames_demodulated++;
+  }
+  fic_buf ^= 1;
+  host_us[H_FSM] += now_us() - tw;
+  return DABGPU_OK;
+}
+
+// dab_process_frame of every frame in `lag` (FIG parsing, lock state machine, CIF window), queueing
+// of the resulting ETI frames and, once msc_batch frames per stream are queued, their MSC decode.
+int Engine::backend_host(cudaStream_t st) {
+  int rc;
+  if (!lag.valid) return DABGPU_OK;
+  lag.valid = false;
+  const int na = (int)lag.active.size();
+  double tw = now_us();
+  // ---- host: per-stream dab_process_frame (streams are independent) ----
+  const uint8_t *h_fibs = h_fic_out[lag.fic_buf].as<uint8_t>();
+  const uint8_t *h_crc = h_fibs + (size_t)na * FIBS_PER_TF;
+  works.resize(na);
+  pool.run(na, [&](int a) {
+    const int s = lag.active[a];
+    FrameWork &work = works[a];
+    work.n_eti = 0;
+    if (!lag.proc[a]) return;
     for (int i = 0; i < 12; i++) stats[s].fib_crc_errors += h_crc[12 * a + i] ? 0 : 1;
-    host_process_frame(back[s], h_fibs + (size_t)a * FIBS_PER_TF, h_crc + 12 * a, &work, quiet);
+    host_process_frame(back[s], h_fibs + (size_t)a * FIBS_PER_TF, h_crc + 12 * a, lag.slot[a], &work, quiet);
     stats[s].eti_frames += work.n_eti;
   });
   host_us[H_FSM] += now_us() - tw;
   tw = now_us();
 
-  // ---- queue the ETI frames of this call ----
+  // ---- queue the ETI frames of these transmission frames ----
   bool any = false;
   for (int a = 0; a < na; a++) {
     const FrameWork &work = works[a];
     if (!work.n_eti) continue;
-    const int s = active[a];
+    const int s = lag.active[a];
     if (layout[s].version != back[s].ens_version) {
       // the multiplex description changed: frames of this stream that are still queued were
       // produced under the old layout and must be decoded first
@@ -405,7 +444,10 @@ int Engine::fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t 
       etijobs.push_back(ej);
     }
   }
-  if (any) pend_calls++;
+  if (any) {
+    pend_calls++;
+    if (lag.demod_ev >= 0) msc_wait_ev = lag.demod_ev;  // the newest CIFs these frames reference
+  }
   host_us[H_JOBS] += now_us() - tw;
   if (pend_calls >= msc_batch) return flush_msc(st);
   return DABGPU_OK;
@@ -424,10 +466,10 @@ int Engine::flush_msc(cudaStream_t user) {
   // bound the lag of the MSC stream: the previous batch must be done before the next one is
   // queued, which keeps every CIF/FIB slot a queued batch references out of the front-end's reach
   if (msc_inflight) CUDA_TRY(cudaEventSynchronize(ev_msc_done));
-  // the CIF symbols of the newest frame may still be on their way into the CIF store
-  if (demod_pending) {
-    CUDA_TRY(cudaStreamWaitEvent(st, ev_demod_done, 0));
-    demod_pending = false;
+  // the CIF symbols of the newest queued frame may still be on their way into the CIF store
+  if (msc_wait_ev >= 0) {
+    CUDA_TRY(cudaStreamWaitEvent(st, ev_demod_done[msc_wait_ev], 0));
+    msc_wait_ev = -1;
   }
   // several flushes inside one call (rare: a multiplex change) append to the call's output
   const int base = n_eti, n_new = (int)etijobs.size();
@@ -466,13 +508,18 @@ int Engine::flush_msc(cudaStream_t user) {
   if ((rc = upload_tables(st))) return rc;
   const size_t b_cif = cifjobs.size() * sizeof(CifJob), b_eti = etijobs.size() * sizeof(EtiJob),
                b_sub = subjobs.size() * sizeof(SubJob);
-  // two pinned staging areas alternate; each is free again once its upload has completed
+  // two pinned staging areas alternate; each is free again once its upload has completed.
+  // Every store is sized for a full batch (S streams x msc_batch frames) the first time it is
+  // needed, so that no allocation ever happens in the steady state.
+  const double scale = std::max(1.0, (double)S * 4.0 * msc_batch / (double)n_new) * 1.02;
+  auto full = [scale](size_t bytes) { return (size_t)((double)bytes * scale) + 4096; };
   PinBuf &hm = h_msc[msc_buf];
   CUDA_TRY(cudaEventSynchronize(ev_up[msc_buf]));
-  if ((rc = hm.reserve(b_cif + b_eti + (reuse ? 0 : b_sub)))) return rc;
-  if ((rc = d_cifjobs.reserve(b_cif + b_eti))) return rc;
-  if ((rc = d_subjobs.reserve(b_sub))) return rc;
-  if ((rc = d_steps_msc.reserve(row_base + 64))) return rc;
+  if (hm.cap < b_cif + b_eti + b_sub && (rc = hm.reserve(full(b_cif + b_eti + b_sub)))) return rc;
+  if (d_cifjobs.cap < b_cif + b_eti && (rc = d_cifjobs.reserve(full(b_cif + b_eti)))) return rc;
+  if (d_subjobs.cap < b_sub && (rc = d_subjobs.reserve(full(b_sub)))) return rc;
+  if (d_steps_msc.cap < row_base + 64 && (rc = d_steps_msc.reserve(full(row_base + 64)))) return rc;
+  vb_msc.reserve_scale = scale;
   if ((size_t)n_eti * DABGPU_ETI_BYTES > d_eti.cap) {
     set_error(DABGPU_ERR_STATE, "engine: more ETI frames in one call than the output store holds");
     return DABGPU_ERR_STATE;
@@ -538,13 +585,15 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
   const int na = (int)active.size();
   n_eti = 0;
   eti_stream.clear();
+  if ((rc = backend_host(st))) return rc;  // a frame left over from a feed_iq call comes first
   if (!na) return DABGPU_OK;
+  for (int s : active) take_slot(s);
   if (na == S) {
     if ((rc = h_ctl.reserve((size_t)S * 4 * sizeof(uint64_t)))) return rc;
     if ((rc = d_planeoff.reserve((size_t)S * 4 * sizeof(uint64_t)))) return rc;
     uint64_t *off = h_ctl.as<uint64_t>();
     for (int s = 0; s < S; s++)
-      for (int k = 0; k < 4; k++) off[4 * s + k] = ((uint64_t)s * CIF_SLOTS + back[s].phys * 4 + k) * CIF_BYTES;
+      for (int k = 0; k < 4; k++) off[4 * s + k] = ((uint64_t)s * CIF_SLOTS + frame_slot[s] * 4 + k) * CIF_BYTES;
     CUDA_TRY(cudaMemcpyAsync(d_planeoff.p, off, (size_t)S * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
     if ((rc = launch_pack_planes(d_tf + 9216, pitch, d_planeoff.as<uint64_t>(), d_cifs.as<uint8_t>(), S, st)))
       return rc;
@@ -555,14 +604,16 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
     uint64_t *off = h_ctl.as<uint64_t>();
     for (int a = 0; a < na; a++)
       for (int k = 0; k < 4; k++)
-        off[4 * a + k] = ((uint64_t)active[a] * CIF_SLOTS + back[active[a]].phys * 4 + k) * CIF_BYTES;
+        off[4 * a + k] = ((uint64_t)active[a] * CIF_SLOTS + frame_slot[active[a]] * 4 + k) * CIF_BYTES;
     CUDA_TRY(cudaMemcpyAsync(d_planeoff.p, off, 4 * sizeof(uint64_t) * (size_t)na, cudaMemcpyHostToDevice, st));
     for (int a = 0; a < na; a++)
       if ((rc = launch_pack_planes(d_tf + (size_t)active[a] * pitch + 9216, pitch,
                                    d_planeoff.as<uint64_t>() + 4 * a, d_cifs.as<uint8_t>(), 1, st)))
         return rc;
   }
-  if ((rc = fic_and_backend(st, d_tf, pitch, nullptr))) return rc;
+  if ((rc = fic_launch(st, d_tf, pitch))) return rc;
+  if ((rc = fic_finish(st, nullptr, -1))) return rc;  // also covers the pack kernels on `st`
+  if ((rc = backend_host(st))) return rc;
   return collect_timing(st);
 }
 
@@ -574,7 +625,6 @@ int Engine::ensure_frontend() {
   if ((rc = d_tails.reserve((size_t)S * TAIL_BYTES))) return rc;
   if ((rc = d_ctl.reserve((size_t)S * sizeof(StepCtl)))) return rc;
   if ((rc = d_sync.reserve((size_t)S * sizeof(SyncOut)))) return rc;
-  if ((rc = h_ctl.reserve((size_t)S * sizeof(StepCtl)))) return rc;
   if ((rc = h_sync.reserve((size_t)S * sizeof(SyncOut)))) return rc;
   CUDA_TRY(cudaMemset(d_ring.p, 0, (size_t)S * IQ_RING_BYTES));
   CUDA_TRY(cudaMemset(d_frames.p, 0, (size_t)S * DABGPU_TF_BYTES));
@@ -602,15 +652,18 @@ int Engine::submit_iq(const uint8_t *iq, size_t pitch, int chunk_len) {
     set_error(DABGPU_ERR_ARG, "submit_iq: chunk_len must be a multiple of 16 in (0, 262144], pitch >= chunk_len");
     return DABGPU_ERR_ARG;
   }
-  if (stage_count >= 2) {
-    set_error(DABGPU_ERR_STATE, "submit_iq: two chunks are already queued; call dabgpu_engine_feed_submitted");
+  if (stage_count >= N_STAGE) {
+    set_error(DABGPU_ERR_STATE, "submit_iq: %d chunks are already queued; call dabgpu_engine_feed_submitted", N_STAGE);
     return DABGPU_ERR_STATE;
   }
-  const int b = (stage_head + stage_count) & 1;
-  if ((rc = d_stage[b].reserve((size_t)S * chunk_len))) return rc;
+  const int b = (stage_head + stage_count) % N_STAGE;
+  if ((rc = d_stage[b].reserve((size_t)S * 262144))) return rc;
   // the buffer is free once the ingest kernel that read it last has run
   CUDA_TRY(cudaStreamWaitEvent(st_copy, ev_consumed[b], 0));
-  CUDA_TRY(cudaMemcpy2DAsync(d_stage[b].p, chunk_len, iq, pitch, chunk_len, S, cudaMemcpyHostToDevice, st_copy));
+  if (pitch == (size_t)chunk_len)
+    CUDA_TRY(cudaMemcpyAsync(d_stage[b].p, iq, (size_t)S * chunk_len, cudaMemcpyHostToDevice, st_copy));
+  else
+    CUDA_TRY(cudaMemcpy2DAsync(d_stage[b].p, chunk_len, iq, pitch, chunk_len, S, cudaMemcpyHostToDevice, st_copy));
   CUDA_TRY(cudaEventRecord(ev_copied[b], st_copy));
   stage_len[b] = chunk_len;
   stage_count++;
@@ -627,7 +680,7 @@ int Engine::feed_submitted() {
   consuming_stage = b;
   const int rc = feed_iq(d_stage[b].as<uint8_t>(), (size_t)stage_len[b], stage_len[b], true);
   consuming_stage = -1;
-  stage_head ^= 1;
+  stage_head = (stage_head + 1) % N_STAGE;
   stage_count--;
   return rc;
 }
@@ -646,7 +699,11 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   if ((rc = ensure_frontend())) return rc;
   const double t_pre = now_us();
   cudaStream_t st = current_stream();
-  StepCtl *ctl = h_ctl.as<StepCtl>();
+  // the staging copy of the call before last has certainly been consumed; make sure anyway
+  PinBuf &hc = h_stepctl[ctl_buf];
+  CUDA_TRY(cudaEventSynchronize(ev_ctl[ctl_buf]));
+  if ((rc = hc.reserve((size_t)S * sizeof(StepCtl)))) return rc;
+  StepCtl *ctl = hc.as<StepCtl>();
   active.clear();
   bool any_read = false, any_copy = false, any_mat = false;
   for (int s = 0; s < S; s++) {
@@ -720,12 +777,15 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     fr.coarse_timeshift = 0;  // input_sdr.c:66
     c.run = 1;
     c.force_timesync = fr.force_timesync;
+    const int slot = take_slot(s);
     for (int k = 0; k < 4; k++)
-      c.cif_off[k] = ((uint64_t)s * CIF_SLOTS + (uint64_t)back[s].phys * 4 + k) * CIF_BYTES;
+      c.cif_off[k] = ((uint64_t)s * CIF_SLOTS + (uint64_t)slot * 4 + k) * CIF_BYTES;
     fr.pending = true;
     active.push_back(s);
   }
   CUDA_TRY(cudaMemcpyAsync(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaEventRecord(ev_ctl[ctl_buf], st));
+  ctl_buf ^= 1;
   host_us[H_PRE] += now_us() - t_pre;
   const uint8_t *d_src = iq;
   t0(K_INGEST, st);
@@ -735,6 +795,11 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   if (consuming_stage >= 0) CUDA_TRY(cudaEventRecord(ev_consumed[consuming_stage], st));
   n_eti = 0;
   eti_stream.clear();
+  // With deferred MSC batches the back-end host logic trails the front-end by one frame: it runs
+  // below, after this call's kernels have been queued, so the GPU is never waiting for it.
+  const bool trailing = msc_batch > 1;
+  bool launched = false;
+  int demod_ev = -1;
   if (any_read) {
     t0(K_FIFO, st);
     if (any_mat && (rc = launch_fifo_read(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
@@ -765,12 +830,19 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
                              d_cifs.as<uint8_t>(), S, 1, 4, st)))
         return rc;
       t1(K_DEMOD, st);
-      CUDA_TRY(cudaEventRecord(ev_demod_done, st));
-      demod_pending = true;
+      demod_ev = demod_ev_next;
+      demod_ev_next ^= 1;
+      CUDA_TRY(cudaEventRecord(ev_demod_done[demod_ev], st));
       CUDA_TRY(cudaStreamWaitEvent(st_fic, ev_fic_ready, 0));
       CUDA_TRY(cudaMemcpyAsync(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st_fic));
-      if ((rc = fic_and_backend(st_fic, d_ficbits.as<uint8_t>(), 9216, h_sync.as<SyncOut>()))) return rc;
+      if ((rc = fic_launch(st_fic, d_ficbits.as<uint8_t>(), 9216))) return rc;
+      launched = true;
     }
+  }
+  if ((rc = backend_host(st))) return rc;  // the previous frame's, overlapping the kernels above
+  if (launched) {
+    if ((rc = fic_finish(st_fic, h_sync.as<SyncOut>(), demod_ev))) return rc;
+    if (!trailing && (rc = backend_host(st))) return rc;
   }
   for (int s = 0; s < S; s++) tuner_feedback(front[s]);
   return collect_timing(st);
@@ -890,7 +962,9 @@ DABGPU_EXPORT int dabgpu_engine_set_msc_batch(dabgpu_engine *h, int calls) {
 DABGPU_EXPORT int dabgpu_engine_flush(dabgpu_engine *h) {
   h->e.n_eti = 0;
   h->e.eti_stream.clear();
-  int rc = h->e.flush_msc(current_stream());
+  int rc = h->e.backend_host(current_stream());  // a frame whose host logic is still outstanding
+  if (rc) return rc;
+  rc = h->e.flush_msc(current_stream());
   if (rc) return rc;
   return h->e.collect_timing(current_stream());
 }

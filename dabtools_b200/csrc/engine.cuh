@@ -96,30 +96,53 @@ struct Engine {
   DevBuf d_ens;       // EnsDev[S]
   DevBuf d_shapes, d_fic_shape;
   DevBuf d_cifjobs, d_subjobs, d_etijobs, d_planeoff, d_gather_idx, d_gather_out;
-  PinBuf h_ctl, h_sync, h_fic_out, h_jobs, h_msc[2], h_eti, h_chunk;
+  PinBuf h_ctl, h_stepctl[2], h_sync, h_fic_out[2], h_jobs, h_msc[2], h_eti, h_chunk;
   // MSC work runs on its own stream so that it overlaps the next frames' front-end kernels
   // ... and the FIC chain (depuncture, Viterbi, CRC, copy back) on another one, so that the host
   // gets the FIBs while the CIF symbols of the same frame are still being demodulated
   cudaStream_t st_fic = nullptr;
-  cudaEvent_t ev_fic_ready = nullptr, ev_demod_done = nullptr;
-  bool demod_pending = false;
+  cudaEvent_t ev_fic_ready = nullptr, ev_demod_done[2] = {};
+  int demod_ev_next = 0;  // the two events alternate from frame to frame
+  cudaEvent_t ev_ctl[2] = {};  // StepCtl staging buffers alternate; each is reusable once uploaded
+  int ctl_buf = 0;
+  int msc_wait_ev = -1;   // event the next MSC batch has to wait for (-1: its CIFs are in place)
   cudaStream_t st_msc = nullptr;
   cudaEvent_t ev_up[2] = {}, ev_msc_done = nullptr;
   int msc_buf = 0;
   bool msc_inflight = false;
   int join_msc(cudaStream_t user);  // make `user` wait for all MSC work issued so far
-  // host IQ is staged through two device buffers on a copy stream, so that the upload of the
-  // next callback overlaps the processing of the current one
+  // host IQ is staged through a small ring of device buffers on a copy stream, so that the
+  // uploads of the next callbacks overlap the processing of the current one
+  enum { N_STAGE = 3 };
   cudaStream_t st_copy = nullptr;
-  DevBuf d_stage[2];
-  cudaEvent_t ev_copied[2] = {}, ev_consumed[2] = {};
-  int stage_len[2] = {0, 0};
-  int stage_head = 0, stage_count = 0;  // FIFO of submitted chunks (at most 2)
+  DevBuf d_stage[N_STAGE];
+  cudaEvent_t ev_copied[N_STAGE] = {}, ev_consumed[N_STAGE] = {};
+  int stage_len[N_STAGE] = {};
+  int stage_head = 0, stage_count = 0;  // FIFO of submitted chunks (at most N_STAGE)
   int consuming_stage = -1;
   int submit_iq(const uint8_t *iq, size_t pitch, int chunk_len);
   int feed_submitted();
   HostPool pool;
   std::vector<FrameWork> works;
+  // Transmission frames whose FIC has been decoded but whose dab_process_frame is still to run.
+  // With msc_batch > 1 that happens during the next feed_iq call, after its kernels have been
+  // queued, so that the host state machines overlap GPU work instead of stalling it.
+  struct LagFrame {
+    bool valid = false;
+    std::vector<int> active;    // streams with a frame
+    std::vector<uint8_t> proc;  // frame passed the synchroniser checks of sdr_demod
+    std::vector<int> slot;      // physical TF slot of the frame
+    int fic_buf = 0;            // which h_fic_out holds its FIBs
+    int demod_ev = -1;          // ev_demod_done index covering its CIFs
+  } lag;
+  int fic_buf = 0;
+  std::vector<int> frame_slot;  // per stream: slot of the frame in flight
+  int take_slot(int s) {
+    const int slot = back[s].phys;
+    back[s].phys = (slot + 1) % PHYS_TF_SLOTS;
+    return frame_slot[s] = slot;
+  }
+  int backend_host(cudaStream_t st);
   // MSC decoding may lag by up to msc_batch calls so that one Viterbi launch covers several
   // transmission frames per stream (more, better balanced work per launch)
   int msc_batch = 1, pend_calls = 0;
@@ -175,9 +198,8 @@ struct Engine {
   int process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *mask, bool on_device);
 
  private:
-  int fic_and_backend(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride,
-                      const SyncOut *h_sync_or_null);
-  int after_fic(cudaStream_t st);
+  int fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride);
+  int fic_finish(cudaStream_t st, const SyncOut *h_sync_or_null, int demod_ev);
   int refresh_layout(int s);
   int upload_tables(cudaStream_t st);
 };

@@ -137,7 +137,8 @@ static bool merge_and_diff(ens_info_t *ei, const tf_info_t *info) {
 }
 
 // dab.c:35-99
-void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *crc_ok, FrameWork *out, bool quiet) {
+void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *crc_ok, int slot, FrameWork *out,
+                        bool quiet) {
   out->n_eti = 0;
   int ok_count = 0;
   for (int i = 0; i < 12; i++) ok_count += crc_ok[i] ? 1 : 0;
@@ -164,7 +165,7 @@ void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *cr
   if (merge_and_diff(&st.ens_info, &st.tf_info)) st.ens_version++;
 
   if (st.ncifs < 16) {
-    for (int k = 0; k < 4; k++) st.win[st.ncifs++] = st.phys * 4 + k;
+    for (int k = 0; k < 4; k++) st.win[st.ncifs++] = slot * 4 + k;
   } else {
     if (!st.ens_info_shown) {
       if (!quiet) dump_ens_info(&st.ens_info);
@@ -181,11 +182,10 @@ void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *cr
         if (++st.ens_info.CIFCount_hi == 20) st.ens_info.CIFCount_hi = 0;
       }
       memmove(st.win, st.win + 1, 15 * sizeof(int));
-      st.win[15] = st.phys * 4 + k;
+      st.win[15] = slot * 4 + k;
     }
   }
   st.tfidx = (st.tfidx + 1) % 5;
-  st.phys = (st.phys + 1) % PHYS_TF_SLOTS;
 }
 
 }  // namespace dabgpu

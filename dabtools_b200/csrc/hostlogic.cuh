@@ -26,8 +26,9 @@ struct GlibcRand {
 
 // The reference keeps 5 TF buffers (4 in the window + the incoming one).  The device store is a
 // deeper ring because MSC decoding is batched over up to D = 4 TFs and runs asynchronously to the
-// front-end: a batch references D + 4 slots while up to D newer frames are being written.
-enum { PHYS_TF_SLOTS = 12, MAX_MSC_BATCH = 4 };
+// front-end, whose host logic may additionally trail by one frame: a batch references D + 4 slots
+// while up to D + 1 newer frames are being written.
+enum { PHYS_TF_SLOTS = 14, MAX_MSC_BATCH = 4 };
 
 // per-stream back-end state: dab_state_t without the 1.2 MB of frame buffers, which
 // live on the device (dab.h:70-89)
@@ -36,8 +37,9 @@ struct BackendState {
   ens_info_t ens_info;
   int win[16];      // physical CIF store slots (phys_tf*4+cif) of the 16-CIF window, [0] oldest
   int ncifs, tfidx, locked, okcount, ens_info_shown;
-  int phys;         // physical TF slot the incoming frame is written to; advances with tfidx but
-                    // over a deeper ring (PHYS_TF_SLOTS) so that MSC decoding can lag behind
+  int phys;         // physical TF slot the next incoming frame is written to: a ring deeper than the
+                    // reference's 5 (PHYS_TF_SLOTS) that the engine advances with every frame it
+                    // stores, so that FIG parsing and MSC decoding can trail the front-end
   uint64_t ens_version;  // bumped whenever ens_info's sub-channel table changes
   void reset();
 };
@@ -49,8 +51,8 @@ struct FrameWork {
   uint8_t cif_hi[4], cif_lo[4];
 };
 // dab.c:35-99 with the FIC results (fibs, crc, ok_count) already decoded on the GPU.
-// tf_slot is the slot the frame was written to (== st.tfidx on entry).
-void host_process_frame(BackendState &st, const uint8_t *fibs384, const uint8_t *crc_ok12, FrameWork *out,
+// `slot` is the physical TF slot the frame's CIFs and FIBs were written to.
+void host_process_frame(BackendState &st, const uint8_t *fibs384, const uint8_t *crc_ok12, int slot, FrameWork *out,
                         bool quiet);
 
 }  // namespace dabgpu

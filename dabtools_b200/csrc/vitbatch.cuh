@@ -25,6 +25,8 @@ struct VitBatch {
   uint64_t total_steps = 0;  // sum over codewords of nbits+6 (for ACS/s accounting)
   int n_ctas = 0;
   bool small_ctas = false;  // one single-warp CTA per group instead of the persistent layout
+  double reserve_scale = 1.0;  // allocate this much more than the current job list needs (the
+                               // caller's ratio of a full batch to this one), so stores never grow
 
   void clear() {
     jobs.clear();
@@ -113,13 +115,16 @@ struct VitBatch {
       int rc;
       const size_t jb = sorted.size() * sizeof(VitJob), gb = groups.size() * sizeof(VitGroup),
                    bb = bin_start.size() * sizeof(uint32_t);
-      if ((rc = d_jobs.reserve(jb))) return rc;
-      if ((rc = d_groups.reserve(gb))) return rc;
-      if ((rc = d_bins.reserve(bb))) return rc;
-      if ((rc = d_dec.reserve(dec_words * sizeof(uint2)))) return rc;
+      auto full = [this](size_t bytes) { return (size_t)((double)bytes * reserve_scale) + 4096; };
+      // bins are per SM; groups can be up to 32x more numerous for another job mix of the same size
+      if (d_jobs.cap < jb && (rc = d_jobs.reserve(full(jb)))) return rc;
+      if (d_groups.cap < gb && (rc = d_groups.reserve(full(gb) * 2))) return rc;
+      if (d_bins.cap < bb && (rc = d_bins.reserve(full(bb)))) return rc;
+      if (d_dec.cap < dec_words * sizeof(uint2) && (rc = d_dec.reserve(full(dec_words * sizeof(uint2)))))
+        return rc;
       // the staging buffer may still be in flight from the previous upload on this stream
       CUDA_TRY(cudaStreamSynchronize(st));
-      if ((rc = h_stage.reserve(jb + gb + bb))) return rc;
+      if (h_stage.cap < jb + gb + bb && (rc = h_stage.reserve(full(jb + gb + bb) + full(gb)))) return rc;
       memcpy(h_stage.p, sorted.data(), jb);
       memcpy((char *)h_stage.p + jb, groups.data(), gb);
       memcpy((char *)h_stage.p + jb + gb, bin_start.data(), bb);

@@ -111,7 +111,7 @@ int dabgpu_engine_feed_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int
 /* The same in two halves, so that the host->device copy of the next callback overlaps the
  * processing of the current one: submit_iq() starts the upload of a host chunk (pinned memory
  * makes it asynchronous) and returns; feed_submitted() processes the oldest submitted chunk.  At
- * most two chunks may be in flight.  feed_iq(host pointer) == submit_iq + feed_submitted. */
+ * most three chunks may be in flight.  feed_iq(host pointer) == submit_iq + feed_submitted. */
 int dabgpu_engine_submit_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int chunk_len);
 int dabgpu_engine_feed_submitted(dabgpu_engine *e);
 /* Back-end only: one demapped transmission frame (fic 9216 + msc 221184 bytes of 0/1, i.e. the

@@ -113,6 +113,49 @@ def test_full_path_eti_bit_exact(gpu, port):
         assert np.array_equal(got[s], want["eti"]), s
 
 
+@pytest.mark.parametrize("batch", [2, 3, 4])
+def test_full_path_with_trailing_backend(gpu, port, batch):
+    """Deferred MSC batches through feed_iq: the host state machines trail the front-end by one frame
+    and the ETI comes out late and in batches, but it is the same ETI; the synchroniser feedback
+    (which the next FIFO read depends on) is not delayed."""
+    ens = synth.small_ensemble()
+    S, n_tf = 3, 24
+    g = synth.ModeITransmitter(ens).generate(S, n_tf, seed=19, snr_db=30, tail_samples=262144)
+    iq_full = g["iq"].numpy()
+    cuts = [777, 0, 190000]
+    n = min(iq_full.shape[1] - 2 * c for c in cuts) // 262144 * 262144
+    iq = np.stack([iq_full[s, 2 * c: 2 * c + n] for s, c in enumerate(cuts)])
+    eng = gpu.Engine(S, 200_000_000, 0)
+    eng.set_msc_batch(batch)
+    out = [[] for _ in range(S)]
+    trace = [[] for _ in range(S)]
+    sizes = []
+    for pos in range(0, n, 262144):
+        k = eng.feed_iq(iq[:, pos: pos + 262144])
+        sizes.append(k)
+        eti, ids = eng.fetch_eti()
+        assert len(eti) == k
+        for f, s in zip(eti, ids):
+            out[s].append(f.copy())
+        for s in range(S):
+            st = eng.status(s)
+            trace[s].append((st.last_ok, st.coarse_timeshift, st.fine_timeshift, st.coarse_freq_shift))
+    if eng.flush():
+        eti, ids = eng.fetch_eti()
+        for f, s in zip(eti, ids):
+            out[s].append(f.copy())
+    eng.close()
+    assert max(sizes) > 4 * S or batch == 1      # frames really were batched
+    for s in range(S):
+        want = port.run_iq(iq[s])
+        want_tr = [(int(a["ok"]), int(a["coarse_timeshift"]), int(a["fine_timeshift"]), int(a["coarse_freq_shift"]))
+                   for a in want["trace"]]
+        assert trace[s] == want_tr, s
+        got = np.array(out[s], dtype=np.uint8).reshape(-1, 6144)
+        assert got.shape == want["eti"].shape and got.shape[0] >= 16
+        assert np.array_equal(got, want["eti"]), s
+
+
 def test_full_path_golden(gpu):
     gold = np.load(os.path.join(GOLDEN, "reference_v1.npz"))
     import zlib
