@@ -16,16 +16,22 @@
 //
 // Kernel layout
 // -------------
-// One lane = one codeword, 64 path metrics as 4 x u8 in 16 registers, state s in
-// byte (s & 3) of register (s >> 2).  Butterfly group k (0..7) takes A = R[k]
-// (states 4k..4k+3) and B = R[k+8] (those +32) and produces the even successors
-// 8k,8k+2,.. (E) and the odd ones (O) with byte-SWAR arithmetic:
+// One lane = one codeword, 64 path metrics as 4 x u8 in 16 registers.  A butterfly pairs the
+// predecessors p and p+32 (state bit 5) and produces the successors 2p and 2p+1 (state bit 0), so
+// with byte-SWAR arithmetic on registers A (bit 5 = 0) and B (bit 5 = 1)
 //     t = a + 0x7f7f7f7f - b   -> bit 7 of each byte = (a > b)      (a,b < 128)
 //     m = prmt(t, 0xba98)      -> 0xff where b wins (sign replicate)
-//     new = (b & m) | (a & ~m) ; decision bits accumulate as m & (0x01010101 << k)
-// and two prmt re-interleave E/O into registers 2k, 2k+1.  Branch distances for the
-// four symbol classes {c, ~c} (generators 0 and 3 are equal, so only 8 of the 16
-// symbols occur) come from a 256-entry shared-memory table indexed by the step byte.
+//     new = (b & m) | (a & ~m) ; decision bits accumulate as m & C
+// the results E (successors 2p) and O (2p+1) hold the new states in the same byte positions as
+// their predecessors.  Which two state bits select the byte inside a register therefore moves up
+// by one position per step; a byte bit that reaches position 5 has to be swapped with the new bit 0
+// (one prmt per register).  Alternating two layouts needs that swap only on every other step:
+//     L0 (before even steps): byte = (s0, s2), register = s1 + 2 s3 + 4 s4 + 8 s5
+//     L1 (before odd steps):  byte = (s1, s3), register = s0 + 2 s2 + 4 s4 + 8 s5
+// Branch distances: generators 0 and 3 are equal, so only the 4 symbol classes {c, ~c} occur, and
+// over the 8 register pairs of a step only 8 distinct 4-byte distance patterns do.  A shared-memory
+// table indexed by the step byte delivers all 8 with two 128-bit loads per step and layout.
+// 112 SASS instructions per 64-state step (1.75 per add-compare-select).
 #include "viterbi.cuh"
 
 #include <algorithm>
@@ -55,86 +61,189 @@ __host__ __device__ constexpr int cx_branch_sym(int reg) {
   return cx_parity(reg & 0x6d) | (cx_parity(reg & 0x4f) << 1) | (cx_parity(reg & 0x53) << 2) |
          (cx_parity(reg & 0x6d) << 3);
 }
-// prmt selector that gathers, for butterfly group k, the distance of the "input bit 0
-// from predecessor p" branch of p = 4k..4k+3 out of {D (bytes 0-3), Dc (bytes 4-7)}
-__host__ __device__ constexpr uint32_t cx_group_sel(int k) {
+// predecessor state (bit 5 = 0) held in byte j of register k before a step of phase ph
+__host__ __device__ constexpr int cx_pre_state(int ph, int k, int j) {
+  const int j0 = j & 1, j1 = j >> 1, k0 = k & 1, k1 = (k >> 1) & 1, k2 = k >> 2;
+  return ph == 0 ? (j0 | (k0 << 1) | (j1 << 2) | (k1 << 3) | (k2 << 4))
+                 : (k0 | (j0 << 1) | (k1 << 2) | (j1 << 3) | (k2 << 4));
+}
+// Distance pattern of register pair k as a prmt selector over {D (bytes 0-3), Dc (bytes 4-7)}:
+// nibble j = class | polarity << 2 of the branch "predecessor in byte j, input bit 0".  The other
+// three branches of the butterfly see this pattern (p+32 -> 2p+1) or its complement (^ 0x4444).
+__host__ __device__ constexpr uint32_t cx_pair_sel(int ph, int k) {
   uint32_t s = 0;
   for (int j = 0; j < 4; j++) {
-    int v = cx_branch_sym(2 * (4 * k + j));
-    int pol = v & 1;  // class representative has bit0 == 0
-    int cls = ((pol ? ~v : v) >> 1) & 3;
+    const int v = cx_branch_sym(2 * cx_pre_state(ph, k, j));
+    const int pol = v & 1;  // class representative has bit0 == 0
+    const int cls = ((pol ? ~v : v) >> 1) & 3;
     s |= (uint32_t)(cls | (pol << 2)) << (4 * j);
   }
   return s;
 }
-
-// Two formulations of "compare, select, record the decision" for 4 states at once.  t holds
-// (a > b) in bit 7 of every byte.
-//  - ALU flavour: m = prmt(t, 0xba98) (sign-replicate), dec |= m & (0x01010101 << K)   [2 ALU ops]
-//  - FMA flavour: f = (t & 0x80808080) >> 7 via IMAD.HI, m = f * 255, dec = f * 2^K + dec
-//                                                                   [1 ALU op + 3 FMA-pipe ops]
-// The integer ALU pipe is the kernel's bottleneck (PRMT/LOP3/IADD3 issue at half rate), the FMA
-// pipe is mostly idle, so a share of the groups uses the second form to balance the two pipes.
-template <int K, bool FMA_FLAVOUR>
-__device__ __forceinline__ uint32_t select_and_record(uint32_t t, uint32_t a, uint32_t b, uint32_t &dec) {
-  uint32_t m;
-  if (FMA_FLAVOUR) {
-    const uint32_t f = __umulhi(t & 0x80808080u, 1u << 25);  // 0x01 where b wins
-    m = f * 255u;
-    dec = f * (1u << K) + dec;
-  } else {
-    m = prmt(t, 0u, 0xba98u);
-    dec |= m & (0x01010101u << K);
-  }
-  return (b & m) | (a & ~m);
+// the 16 patterns X_0, Y_0, X_1, Y_1, ... of a phase and their 8 distinct values
+__host__ __device__ constexpr uint32_t cx_code(int ph, int n) {
+  return (n & 1) ? cx_pair_sel(ph, n >> 1) ^ 0x4444u : cx_pair_sel(ph, n >> 1);
 }
-
-template <int K>
-__device__ __forceinline__ void butterfly(uint32_t A, uint32_t B, uint32_t D, uint32_t Dc,
-                                          uint32_t &R0, uint32_t &R1, uint32_t &decE, uint32_t &decO) {
-  constexpr uint32_t sel = cx_group_sel(K);
-  const uint32_t X = prmt(D, Dc, sel);           // distance of branch p -> 2p
-  const uint32_t Y = prmt(D, Dc, sel ^ 0x4444u); // its complement, n - X
-  const uint32_t a0 = A + X, b0 = B + Y;         // into even state: via p / via p+32
-  const uint32_t a1 = A + Y, b1 = B + X;         // into odd state
-  const uint32_t t0 = a0 + 0x7f7f7f7fu - b0;
-  const uint32_t t1 = a1 + 0x7f7f7f7fu - b1;
-  // measured on B200: the FMA flavour raises the step from 132 to 154 instructions and the decoder
-  // gets 10 % slower -- it is issue-bound, not ALU-pipe-bound -- so every group uses the ALU form
-  constexpr bool fma = false;
-  const uint32_t E = select_and_record<K, fma>(t0, a0, b0, decE);
-  const uint32_t O = select_and_record<K, fma>(t1, a1, b1, decO);
-  R0 = prmt(E, O, 0x5140u);
-  R1 = prmt(E, O, 0x7362u);
+__host__ __device__ constexpr int cx_first(int ph, int n) {
+  for (int q = 0; q < n; q++)
+    if (cx_code(ph, q) == cx_code(ph, n)) return q;
+  return n;
+}
+__host__ __device__ constexpr int cx_n_distinct(int ph) {
+  int r = 0;
+  for (int q = 0; q < 16; q++) r += cx_first(ph, q) == q;
+  return r;
+}
+// index (0..7) of pattern n among the distinct ones
+__host__ __device__ constexpr int cx_slot(int ph, int n) {
+  const int f = cx_first(ph, n);
+  int r = 0;
+  for (int q = 0; q < f; q++) r += cx_first(ph, q) == q;
+  return r;
+}
+// selector of distinct pattern i
+__host__ __device__ constexpr uint32_t cx_pattern(int ph, int i) {
+  int r = 0;
+  for (int q = 0; q < 16; q++)
+    if (cx_first(ph, q) == q) {
+      if (r == i) return cx_code(ph, q);
+      r++;
+    }
+  return 0;
+}
+static_assert(cx_n_distinct(0) == 8 && cx_n_distinct(1) == 8, "8 distance patterns per layout");
+// Where the decision of (byte j, pair k) goes inside byte j of the decision word: any bijection
+// of k per byte will do; this one makes the traceback's bit index a single XOR (see tb_step)
+__host__ __device__ constexpr uint32_t cx_dec_mask(int k) {
+  uint32_t c = 0;
+  for (int j = 0; j < 4; j++) c |= 1u << (8 * j + (((k & 3) ^ j) + (k & 4)));
+  return c;
 }
 
 struct Metrics {
   uint32_t r[16];
 };
+struct Patterns {
+  uint32_t p[8];
+};
 
-__device__ __forceinline__ uint2 acs_step(Metrics &m, uint2 d) {
+// add-compare-select of register pair K: E = successors 2p, O = successors 2p+1
+template <int PH, int K>
+__device__ __forceinline__ void pair_acs(const Metrics &m, const Patterns &P, uint32_t &E, uint32_t &O,
+                                         uint32_t &decE, uint32_t &decO) {
+  constexpr int ix = cx_slot(PH, 2 * K), iy = cx_slot(PH, 2 * K + 1);
+  constexpr uint32_t C = cx_dec_mask(K);
+  const uint32_t A = m.r[K], B = m.r[K + 8];
+  const uint32_t X = P.p[ix], Y = P.p[iy];       // distance of p -> 2p, and its complement
+  const uint32_t a0 = A + X, b0 = B + Y;         // into even state: via p / via p+32
+  const uint32_t a1 = A + Y, b1 = B + X;         // into odd state
+  const uint32_t t0 = a0 + 0x7f7f7f7fu - b0;
+  const uint32_t t1 = a1 + 0x7f7f7f7fu - b1;
+  // Measured on B200, both slower or within 2 %: (1) mask/record on the FMA pipe (f = umulhi(t &
+  // 0x80808080, 1 << 25), m = f * 255, dec = f * 2^k + dec): -10 %; (2) the compare on the FMA pipe
+  // (t = b * -1 + (a * 1 + K) with run-time factors so that ptxas cannot fold them back into IADD3).
+  const uint32_t m0 = prmt(t0, 0u, 0xba98u);
+  const uint32_t m1 = prmt(t1, 0u, 0xba98u);
+  decE |= m0 & C;
+  decO |= m1 & C;
+  E = (b0 & m0) | (a0 & ~m0);
+  O = (b1 & m1) | (a1 & ~m1);
+}
+
+template <int K>
+__device__ __forceinline__ void pair_even(const Metrics &m, const Patterns &P, Metrics &n, uint32_t &dE,
+                                          uint32_t &dO) {
+  uint32_t E, O;
+  pair_acs<0, K>(m, P, E, O, dE, dO);
+  n.r[2 * (K & 3) + 8 * (K >> 2)] = E;  // L1: register = s0 + 2 s2 + 4 s4 + 8 s5, bytes unchanged
+  n.r[2 * (K & 3) + 8 * (K >> 2) + 1] = O;
+}
+template <int K>
+__device__ __forceinline__ void pair_odd(const Metrics &m, const Patterns &P, Metrics &n, uint32_t &dE,
+                                         uint32_t &dO) {
+  uint32_t E, O;
+  pair_acs<1, K>(m, P, E, O, dE, dO);
+  // back to L0: the byte bit that reached position 4 (s3 before the step) trades places with bit 0
+  n.r[(K & 3) + 8 * (K >> 2)] = prmt(E, O, 0x5140u);
+  n.r[(K & 3) + 8 * (K >> 2) + 4] = prmt(E, O, 0x7362u);
+}
+
+__device__ __forceinline__ uint2 acs_even(Metrics &m, const Patterns &P) {
   uint32_t e = 0, o = 0;
   Metrics n;
-  butterfly<0>(m.r[0], m.r[8], d.x, d.y, n.r[0], n.r[1], e, o);
-  butterfly<1>(m.r[1], m.r[9], d.x, d.y, n.r[2], n.r[3], e, o);
-  butterfly<2>(m.r[2], m.r[10], d.x, d.y, n.r[4], n.r[5], e, o);
-  butterfly<3>(m.r[3], m.r[11], d.x, d.y, n.r[6], n.r[7], e, o);
-  butterfly<4>(m.r[4], m.r[12], d.x, d.y, n.r[8], n.r[9], e, o);
-  butterfly<5>(m.r[5], m.r[13], d.x, d.y, n.r[10], n.r[11], e, o);
-  butterfly<6>(m.r[6], m.r[14], d.x, d.y, n.r[12], n.r[13], e, o);
-  butterfly<7>(m.r[7], m.r[15], d.x, d.y, n.r[14], n.r[15], e, o);
+  pair_even<0>(m, P, n, e, o);
+  pair_even<1>(m, P, n, e, o);
+  pair_even<2>(m, P, n, e, o);
+  pair_even<3>(m, P, n, e, o);
+  pair_even<4>(m, P, n, e, o);
+  pair_even<5>(m, P, n, e, o);
+  pair_even<6>(m, P, n, e, o);
+  pair_even<7>(m, P, n, e, o);
+  m = n;
+  return make_uint2(e, o);
+}
+__device__ __forceinline__ uint2 acs_odd(Metrics &m, const Patterns &P) {
+  uint32_t e = 0, o = 0;
+  Metrics n;
+  pair_odd<0>(m, P, n, e, o);
+  pair_odd<1>(m, P, n, e, o);
+  pair_odd<2>(m, P, n, e, o);
+  pair_odd<3>(m, P, n, e, o);
+  pair_odd<4>(m, P, n, e, o);
+  pair_odd<5>(m, P, n, e, o);
+  pair_odd<6>(m, P, n, e, o);
+  pair_odd<7>(m, P, n, e, o);
   m = n;
   return make_uint2(e, o);
 }
 
-// decision bit of state s inside the (E,O) pair written by acs_step
-__device__ __forceinline__ uint32_t decision_bit(uint2 d, uint32_t s) {
-  const uint32_t w = (s & 1u) ? d.y : d.x;
-  return (w >> ((((s >> 1) & 3u) << 3) + (s >> 3))) & 1u;
+// shared-memory distance table: lut[phase][half][step byte] = patterns 4*half .. 4*half+3
+struct VitLut {
+  uint4 t[2][2][256];
+};
+template <int PH>
+__device__ __forceinline__ void lut_fill_row(VitLut &L, uint32_t sb, uint32_t D, uint32_t Dc) {
+  L.t[PH][0][sb] = make_uint4(prmt(D, Dc, cx_pattern(PH, 0)), prmt(D, Dc, cx_pattern(PH, 1)),
+                              prmt(D, Dc, cx_pattern(PH, 2)), prmt(D, Dc, cx_pattern(PH, 3)));
+  L.t[PH][1][sb] = make_uint4(prmt(D, Dc, cx_pattern(PH, 4)), prmt(D, Dc, cx_pattern(PH, 5)),
+                              prmt(D, Dc, cx_pattern(PH, 6)), prmt(D, Dc, cx_pattern(PH, 7)));
+}
+__device__ __forceinline__ void lut_fill(VitLut &L) {
+  for (uint32_t sb = threadIdx.x; sb < 256; sb += blockDim.x) {
+    const uint32_t r = sb & 15, e = sb >> 4;
+    uint32_t D = 0;  // distance to the class representatives 2c (c = 0..3) over the transmitted symbols
+    for (int c = 0; c < 4; c++) D |= (uint32_t)__popc(((2u * c) ^ r) & e) << (8 * c);
+    const uint32_t Dc = (uint32_t)__popc(e) * 0x01010101u - D;
+    lut_fill_row<0>(L, sb, D, Dc);
+    lut_fill_row<1>(L, sb, D, Dc);
+  }
+}
+template <int PH>
+__device__ __forceinline__ Patterns lut_get(const VitLut &L, uint32_t sb) {
+  const uint4 a = L.t[PH][0][sb], b = L.t[PH][1][sb];
+  Patterns P;
+  P.p[0] = a.x, P.p[1] = a.y, P.p[2] = a.z, P.p[3] = a.w;
+  P.p[4] = b.x, P.p[5] = b.y, P.p[6] = b.z, P.p[7] = b.w;
+  return P;
+}
+
+// One traceback step.  The survivor state s (bit 0 = newest input bit) is kept as its even and odd
+// bits, P = s0 + 2 s2 + 4 s4 and Q = s1 + 2 s3 + 4 s5.  For the decisions written by trellis step t:
+//   word = s0; byte = (s1, s3) for even t, (s2, s4) for odd t; bit within the byte = (P >> 1) ^ Q
+// (cx_dec_mask).  The predecessor is (s >> 1) | (bit << 5), i.e. P' = Q, Q' = (P >> 1) | bit << 2.
+template <bool ODD>
+__device__ __forceinline__ uint32_t tb_step(uint2 d, uint32_t &P, uint32_t &Q) {
+  const uint32_t P1 = P >> 1;
+  const uint32_t w = (P & 1u) ? d.y : d.x;
+  const uint32_t byte = prmt(w, w, ODD ? P1 : Q);
+  const uint32_t bit = (byte >> (P1 ^ Q)) & 1u;
+  P = Q;
+  Q = P1 | (bit << 2);
+  return bit;
 }
 
 // Decode one group (up to 32 equal-length codewords, one per lane): forward pass + traceback.
-__device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut,
+__device__ __forceinline__ void decode_group(const VitGroup &g, const VitLut &lut,
                                              const uint8_t *__restrict__ steps, uint8_t *__restrict__ out,
                                              uint2 *__restrict__ dec, const VitJob *__restrict__ jobs, int lane) {
   const bool active = lane < (int)g.nlanes;
@@ -143,33 +252,39 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut
   uint2 *decp = dec + g.dec_off + lane;
   const uint32_t nsteps = g.nsteps;
 
-  // ---- forward pass ----
+  // ---- forward pass: whole 16-step chunks (rows and the decision scratch are padded to 16 steps;
+  // what the padding steps do to the metrics no longer matters) ----
   Metrics m;
 #pragma unroll
   for (int i = 0; i < 16; i++) m.r[i] = 0x30303030u;  // "unreachable" = 48
-  m.r[0] = 0x30303000u;                               // start state 0
+  m.r[0] = 0x30303000u;                               // start state 0 (L0: register 0, byte 0)
   const uint32_t nchunks = (nsteps + 15u) >> 4;
   uint4 nxt = row[0];
+  uint2 *dq = decp;
   for (uint32_t c = 0; c < nchunks; c++) {
     uint4 cur = nxt;
     if (c + 1 < nchunks) nxt = row[c + 1];
-    const uint32_t base = c << 4;
 #pragma unroll 1
     for (int q = 0; q < 4; q++) {
-      uint32_t word = cur.x;
+      const uint32_t word = cur.x;
       cur.x = cur.y;
       cur.y = cur.z;
       cur.z = cur.w;
-#pragma unroll
-      for (int s = 0; s < 4; s++) {
-        const uint32_t t = base + 4 * q + s;
-        if (t < nsteps) {
-          const uint2 d = lut[word & 0xffu];
-          word >>= 8;
-          const uint2 dd = acs_step(m, d);
-          if (active) decp[(size_t)t * 32] = dd;
-        }
+      const Patterns p0 = lut_get<0>(lut, word & 0xffu);
+      const Patterns p1 = lut_get<1>(lut, (word >> 8) & 0xffu);
+      const Patterns p2 = lut_get<0>(lut, (word >> 16) & 0xffu);
+      const Patterns p3 = lut_get<1>(lut, word >> 24);
+      const uint2 d0 = acs_even(m, p0);
+      const uint2 d1 = acs_odd(m, p1);
+      const uint2 d2 = acs_even(m, p2);
+      const uint2 d3 = acs_odd(m, p3);
+      if (active) {
+        dq[0] = d0;
+        dq[32] = d1;
+        dq[64] = d2;
+        dq[96] = d3;
       }
+      dq += 128;
     }
     // common subtraction: every metric is within 24 of state 0's once t >= 6
     const uint32_t m0 = m.r[0] & 0xffu;
@@ -183,13 +298,13 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut
   const uint32_t nbits = job.nbits;
   uint8_t *dst = out + job.out_off;
   const bool scr = job.flags & VIT_DESCRAMBLE;
-  uint32_t state = 0, acc = 0;
+  uint32_t P = 0, Q = 0, acc = 0;
   int i = (int)nbits - 1;
-  // peel so that the main loop runs whole 32-bit words
+  // peel so that the main loop runs whole 32-bit words; bit i is decided by trellis step i + 6
   for (; i >= 0 && (i & 31) != 31; --i) {
-    const uint32_t bit = decision_bit(decp[(size_t)(i + 6) * 32], state);
+    const uint2 d = decp[(size_t)(i + 6) * 32];
+    const uint32_t bit = (i & 1) ? tb_step<true>(d, P, Q) : tb_step<false>(d, P, Q);
     acc |= bit << (31 - (i & 31));
-    state = (state >> 1) | (bit << 5);
     if ((i & 31) == 0) {
       uint32_t w = prmt(acc, 0u, 0x0123u);
       if (scr) w ^= c_prbs_le[i >> 5];
@@ -199,36 +314,36 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const uint2 *lut
   }
   // main loop: 16 bits per half-iteration; the decision words are fetched two half-iterations
   // ahead (their addresses do not depend on the survivor state), so ~32 loads per lane are in
-  // flight while 16 are being walked
+  // flight while 16 are being walked.  i is odd here, so bit i - j comes from an odd trellis step
+  // for even j.
   if (i < 31) return;
-  const uint2 *dp = decp + (size_t)6 * 32;  // dp[step * 32] = decisions of trellis step `step`+6
+  // cur[-32 * n] = decisions of the step that decides bit i - n (constant offsets from one pointer)
+  const uint2 *cur = decp + ((size_t)i + 6) * 32;
   uint2 b0[16], b1[16];
 #pragma unroll
-  for (int j = 0; j < 16; j++) b0[j] = dp[(size_t)(i - j) * 32];
+  for (int j = 0; j < 16; j++) b0[j] = cur[-32 * j];
 #pragma unroll
-  for (int j = 0; j < 16; j++) b1[j] = dp[(size_t)(i - 16 - j) * 32];
-  for (; i >= 31; i -= 32) {
+  for (int j = 0; j < 16; j++) b1[j] = cur[-32 * (16 + j)];
+  for (; i >= 31; i -= 32, cur -= 32 * 32) {
     uint2 b2[16];
     if (i >= 63) {
 #pragma unroll
-      for (int j = 0; j < 16; j++) b2[j] = dp[(size_t)(i - 32 - j) * 32];
+      for (int j = 0; j < 16; j++) b2[j] = cur[-32 * (32 + j)];
     }
     acc = 0;
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const uint32_t bit = decision_bit(b0[j], state);
-      acc |= bit << j;  // bit index (i - j) & 31 = 31 - j
-      state = (state >> 1) | (bit << 5);
+    for (int j = 0; j < 16; j += 2) {
+      acc |= tb_step<true>(b0[j], P, Q) << j;  // bit index (i - j) & 31 = 31 - j
+      acc |= tb_step<false>(b0[j + 1], P, Q) << (j + 1);
     }
     if (i >= 63) {
 #pragma unroll
-      for (int j = 0; j < 16; j++) b0[j] = dp[(size_t)(i - 48 - j) * 32];
+      for (int j = 0; j < 16; j++) b0[j] = cur[-32 * (48 + j)];
     }
 #pragma unroll
-    for (int j = 0; j < 16; j++) {
-      const uint32_t bit = decision_bit(b1[j], state);
-      acc |= bit << (16 + j);
-      state = (state >> 1) | (bit << 5);
+    for (int j = 0; j < 16; j += 2) {
+      acc |= tb_step<true>(b1[j], P, Q) << (16 + j);
+      acc |= tb_step<false>(b1[j + 1], P, Q) << (17 + j);
     }
     uint32_t w = prmt(acc, 0u, 0x0123u);
     if (scr) w ^= c_prbs_le[i >> 5];
@@ -254,13 +369,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) viterbi_kernel(const uint8_t *_
                                                                 const VitJob *__restrict__ jobs,
                                                                 const VitGroup *__restrict__ groups,
                                                                 const uint32_t *__restrict__ bin_start) {
-  __shared__ uint2 lut[256];  // step byte -> {D, Dc}: per-class distances and complements
-  for (int sb = threadIdx.x; sb < 256; sb += blockDim.x) {
-    const uint32_t r = sb & 15, e = sb >> 4;
-    uint32_t D = 0;
-    for (int c = 0; c < 4; c++) D |= (uint32_t)__popc(((2u * c) ^ r) & e) << (8 * c);
-    lut[sb] = make_uint2(D, (uint32_t)__popc(e) * 0x01010101u - D);
-  }
+  __shared__ VitLut lut;  // step byte -> the 8 distance patterns of each layout
+  lut_fill(lut);
   __syncthreads();
   const int lane = threadIdx.x & 31;
   const uint32_t bin = blockIdx.x * WARPS + (threadIdx.x >> 5);

@@ -30,8 +30,10 @@ struct VitGroup {
   uint64_t dec_off;  // offset into the decision scratch, in uint2 units
 };
 
-// decision scratch needed by a group: nsteps * 32 uint2
-__host__ __device__ static inline uint64_t vit_group_dec_words(uint32_t nsteps) { return (uint64_t)nsteps * 32u; }
+// decision scratch needed by a group: 32 uint2 per step, steps padded to whole 16-step chunks
+__host__ __device__ static inline uint64_t vit_group_dec_words(uint32_t nsteps) {
+  return (uint64_t)((nsteps + 15u) & ~15u) * 32u;
+}
 __host__ __device__ static inline uint32_t vit_row_bytes(uint32_t nsteps) { return (nsteps + 15u) & ~15u; }
 
 // warps per persistent CTA (one CTA per SM): 4 schedulers x 3 concurrent work lists

@@ -11,7 +11,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdabgpu.so")
+# DABGPU_LIB selects another build of the same library (kernel experiments); there is no other back-end
+LIB_PATH = os.environ.get("DABGPU_LIB") or os.path.join(HERE, "libdabgpu.so")
 
 u8p = C.POINTER(C.c_uint8)
 
