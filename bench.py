@@ -456,7 +456,7 @@ def run_ours(args, rank, world, local_rank):
             "msc_batch_tf": args.msc_batch,
             "timing": f"CUDA events, max over ranks; inputs ({S * step_bytes / 1e6:.0f} MB per step, distinct every "
                       f"step) exceed the 126 MB L2, no explicit flush",
-            "kernel_timing": "per-kernel CUDA events over the K steps following the timed region",
+            "kernel_timing": "per-kernel CUDA events over the K steps following the timed region, engine streams serialised so that each kernel runs alone",
             "dataset_gen_s": round(t_gen, 1),
         },
         "clocks": clocks,

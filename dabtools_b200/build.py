@@ -35,6 +35,28 @@ def _newer(src_list, target):
     return any(os.path.getmtime(s) > t for s in src_list)
 
 
+def build_variant(name: str, extra_flags: list[str]) -> str:
+    """Kernel experiments: a second library built with extra nvcc flags (e.g. -DDABGPU_VIT_WARPS=8),
+    selected at run time with DABGPU_LIB=<path>.  Not used by the product."""
+    obj = os.path.join(HERE, "build", "variant_" + name)
+    os.makedirs(obj, exist_ok=True)
+    lib = os.path.join(HERE, f"libdabgpu_{name}.so")
+    sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
+    objs = [os.path.join(obj, os.path.basename(s)[:-3] + ".o") for s in sources]
+
+    def run(cmd):
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            sys.stderr.write(" ".join(cmd) + "\n" + r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed")
+
+    with ThreadPoolExecutor(max_workers=8) as ex:
+        list(ex.map(run, [[NVCC] + NVCC_FLAGS + extra_flags + ["-c", s, "-o", o] for s, o in zip(sources, objs)]))
+    run([NVCC, "-shared", "-o", lib] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                               "-Xlinker", "-Bsymbolic", "-lpthread"])
+    return lib
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
@@ -69,4 +91,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))
+    if len(sys.argv) > 2 and sys.argv[1] == "--variant":
+        print(build_variant(sys.argv[2], sys.argv[3:]))
+    else:
+        print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

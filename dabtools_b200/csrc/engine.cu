@@ -797,7 +797,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   eti_stream.clear();
   // With deferred MSC batches the back-end host logic trails the front-end by one frame: it runs
   // below, after this call's kernels have been queued, so the GPU is never waiting for it.
-  const bool trailing = msc_batch > 1;
+  const bool trailing = msc_batch > 1 && !timing;  // per-kernel timing runs everything serially
   bool launched = false;
   int demod_ev = -1;
   if (any_read) {
@@ -833,7 +833,8 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       demod_ev = demod_ev_next;
       demod_ev_next ^= 1;
       CUDA_TRY(cudaEventRecord(ev_demod_done[demod_ev], st));
-      CUDA_TRY(cudaStreamWaitEvent(st_fic, ev_fic_ready, 0));
+      // (when kernels are being timed, each one runs alone: the FIC chain starts after the CIFs)
+      CUDA_TRY(cudaStreamWaitEvent(st_fic, timing ? ev_demod_done[demod_ev] : ev_fic_ready, 0));
       CUDA_TRY(cudaMemcpyAsync(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st_fic));
       if ((rc = fic_launch(st_fic, d_ficbits.as<uint8_t>(), 9216))) return rc;
       launched = true;

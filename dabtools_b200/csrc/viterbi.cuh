@@ -37,7 +37,10 @@ __host__ __device__ static inline uint64_t vit_group_dec_words(uint32_t nsteps) 
 __host__ __device__ static inline uint32_t vit_row_bytes(uint32_t nsteps) { return (nsteps + 15u) & ~15u; }
 
 // warps per persistent CTA (one CTA per SM): 4 schedulers x 3 concurrent work lists
-enum { VIT_WARPS = 12 };
+#ifndef DABGPU_VIT_WARPS
+#define DABGPU_VIT_WARPS 12
+#endif
+enum { VIT_WARPS = DABGPU_VIT_WARPS };
 int device_sm_count();
 // persistent launch: n_ctas CTAs of VIT_WARPS warps; warp-bin b owns groups
 // d_bin_start[b] .. d_bin_start[b+1] (n_ctas * VIT_WARPS + 1 entries)

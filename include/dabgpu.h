@@ -140,7 +140,8 @@ int dabgpu_engine_status(dabgpu_engine *e, int stream, dabgpu_stream_status *out
 int dabgpu_engine_set_seed(dabgpu_engine *e, int stream, unsigned seed); /* srand() of dab2eti.c:88-96 */
 uint64_t dabgpu_engine_trellis_steps(dabgpu_engine *e);
 /* Optional device-side timing of the engine's kernels with CUDA events on the launch stream
- * (adds a stream synchronisation to every feed/process call).  Order of the entries:
+ * (adds a stream synchronisation to every feed/process call and runs the engine's streams one
+ * after the other, so that every kernel is timed alone).  Order of the entries:
  * ingest, fifo_read, sync, demod, fic_prep, fic_viterbi, msc_gather, msc_viterbi, eti_pack. */
 #define DABGPU_ENGINE_KERNELS 9
 int dabgpu_engine_enable_timing(dabgpu_engine *e, int on);
