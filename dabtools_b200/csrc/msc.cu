@@ -28,7 +28,25 @@ int msc_init_constants() {
 }
 
 // ---- shared first half: 16 planes -> packed bits in logical order ---------------------------
-// lin must hold CIF_WORDS + 1 words
+// 16 x 16 bit-matrix transpose (rows in the low halves of M[0..15]): afterwards bit m of M[b] is the
+// former bit b of M[m].  Four swap stages of 8 row pairs each.
+__device__ __forceinline__ void transpose16x16(uint32_t (&M)[16]) {
+#pragma unroll
+  for (int s = 0; s < 4; s++) {
+    const int j = 8 >> s;
+    const uint32_t mask = s == 0 ? 0x00ffu : s == 1 ? 0x0f0fu : s == 2 ? 0x3333u : 0x5555u;
+#pragma unroll
+    for (int k = 0; k < 16; k++) {
+      if (k & j) continue;
+      const uint32_t t = ((M[k] >> j) ^ M[k + j]) & mask;
+      M[k + j] ^= t;
+      M[k] ^= t << j;
+    }
+  }
+}
+
+// lin must hold CIF_WORDS + 1 words.  Logical bit i = 16 q + m comes from plane m, bit q, of the
+// window slot that supplies plane m; 16 consecutive q of all 16 planes are one 16 x 16 transpose.
 __device__ __forceinline__ void deinterleave_to_smem(const uint8_t *__restrict__ cifs, const CifJob &job,
                                                      uint32_t (*pl)[CIF_PLANE_WORDS], uint32_t *lin) {
   for (int idx = threadIdx.x; idx < CIF_WORDS; idx += blockDim.x) {
@@ -37,16 +55,16 @@ __device__ __forceinline__ void deinterleave_to_smem(const uint8_t *__restrict__
     pl[m][w] = __ldg(src + idx);
   }
   __syncthreads();
-  for (int W = threadIdx.x; W < CIF_WORDS; W += blockDim.x) {
-    // logical bits 32W..32W+31 = (q = 2W, m = 0..15), (q = 2W+1, m = 0..15)
-    const int pw = W >> 4, sh = 2 * (W & 15);
-    uint32_t out = 0;
+  for (int item = threadIdx.x; item < 2 * CIF_PLANE_WORDS; item += blockDim.x) {
+    const int pw = item >> 1, half = item & 1;
+    uint32_t M[16];
 #pragma unroll
-    for (int m = 0; m < 16; m++) {
-      const uint32_t t = (pl[m][pw] >> sh) & 3u;
-      out |= ((t & 1u) << m) | ((t >> 1) << (16 + m));
-    }
-    lin[W] = out;
+    for (int m = 0; m < 16; m++) M[m] = half ? pl[m][pw] >> 16 : pl[m][pw] & 0xffffu;
+    transpose16x16(M);
+    // M[b] = the 16 planes' bits of q = 32 pw + 16 half + b, i.e. logical bits 16 q .. 16 q + 15
+    uint32_t *dst = lin + 16 * pw + 8 * half;
+#pragma unroll
+    for (int j = 0; j < 8; j++) dst[j] = (M[2 * j] & 0xffffu) | (M[2 * j + 1] << 16);
   }
   if (threadIdx.x == 0) lin[CIF_WORDS] = 0;
   __syncthreads();
@@ -72,27 +90,29 @@ __global__ void __launch_bounds__(256) msc_gather_kernel(const uint8_t *__restri
     const uint32_t nsteps = (uint32_t)sh->nbits + 6u;
     const uint32_t periods = vit_row_bytes(nsteps) >> 3;
     const int nreg = sh->n_regions;
+    // one thread per puncturing period = 8 trellis steps = 8 step bytes (uep/eep_depuncture,
+    // depuncture.c:84-132, without materialising the 4 soft symbols per step)
     for (uint32_t p = threadIdx.x; p < periods; p += blockDim.x) {
       const uint32_t t0 = p << 3;
-      uint64_t packed = 0;
+      uint2 packed = make_uint2(0u, 0u);
       if (t0 < nsteps) {
         int r = 0;
         while (r + 1 < nreg && (int)t0 >= sh->r[r + 1].step0) r++;
-        const uint32_t mask = sh->r[r].mask;
-        const uint32_t in = sj.in_bit0 + (uint32_t)sh->r[r].in0 +
-                            ((t0 - (uint32_t)sh->r[r].step0) >> 3) * (uint32_t)sh->r[r].ones;
+        const auto &rg = sh->r[r];
+        const uint32_t in = sj.in_bit0 + (uint32_t)rg.in0 + ((t0 - (uint32_t)rg.step0) >> 3) * (uint32_t)rg.ones;
         const uint32_t wi = in >> 5;
         // `ones` <= 32 consecutive channel bits starting at bit `in`
-        uint32_t x = wi < CIF_WORDS ? __funnelshift_r(lin[wi], lin[wi + 1], in & 31u) : 0u;
-        const int nst = min(8, (int)(nsteps - t0));
-        for (int k = 0; k < nst; k++) {
-          const uint32_t e = (mask >> (4 * k)) & 15u;  // kept symbols are always the first popc(e)
-          const uint32_t n = __popc(e);
-          packed |= (uint64_t)((x & e) | (e << 4)) << (8 * k);
-          x >>= n;
-        }
+        const uint32_t x = wi < CIF_WORDS ? __funnelshift_r(lin[wi], lin[wi + 1], in & 31u) : 0u;
+        uint32_t rn = 0;  // received bits as one nibble per step
+        const uint32_t nt = rg.n_terms;
+        for (uint32_t t = 0; t < nt; t++) rn |= (x << rg.dep_shift[t]) & rg.dep_mask[t];
+        uint32_t lo = rn & 0xffffu, hi = rn >> 16;
+        lo = (lo | (lo << 8)) & 0x00ff00ffu;
+        hi = (hi | (hi << 8)) & 0x00ff00ffu;
+        packed.x = ((lo | (lo << 4)) & 0x0f0f0f0fu) | rg.e_lo;
+        packed.y = ((hi | (hi << 4)) & 0x0f0f0f0fu) | rg.e_hi;
       }
-      *reinterpret_cast<uint64_t *>(steps + sj.row_off + 8ull * p) = packed;
+      *reinterpret_cast<uint2 *>(steps + sj.row_off + 8ull * p) = packed;
     }
   }
 }

@@ -444,7 +444,32 @@ void shape_to_dev(const dabgpu_cw_shape &s, ShapeDev *o) {
     o->r[i].step0 = s.r[i].step0;
     o->r[i].in0 = s.r[i].in0;
     o->r[i].ones = 8 + s.r[i].pi;
-    o->r[i].mask = dabgpu_puncture_mask(s.r[i].pi);
+    uint32_t mask = dabgpu_puncture_mask(s.r[i].pi);
+    o->r[i].mask = mask;
+    // deposit tables; a region shorter than a period (the 6-step tail) only has that many steps
+    if (s.r[i].steps < 8) mask &= (1u << (4 * s.r[i].steps)) - 1u;
+    uint32_t taken = 0, nt = 0;
+    for (int k = 0; k < 8; k++) {
+      const uint32_t e = (mask >> (4 * k)) & 15u;
+      if (!e) continue;
+      const uint32_t shift = 4u * k - taken;  // punctured positions before step k
+      taken += (uint32_t)__builtin_popcount(e);
+      if (nt && o->r[i].dep_shift[nt - 1] == shift) {
+        o->r[i].dep_mask[nt - 1] |= e << (4 * k);
+      } else {
+        o->r[i].dep_shift[nt] = (uint8_t)shift;
+        o->r[i].dep_mask[nt] = e << (4 * k);
+        nt++;
+      }
+    }
+    o->r[i].n_terms = nt;
+    auto spread = [](uint32_t v) {  // nibbles of the low 16 bits -> high nibbles of 4 bytes
+      v = (v | (v << 8)) & 0x00ff00ffu;
+      v = (v | (v << 4)) & 0x0f0f0f0fu;
+      return v << 4;
+    };
+    o->r[i].e_lo = spread(mask & 0xffffu);
+    o->r[i].e_hi = spread(mask >> 16);
   }
 }
 

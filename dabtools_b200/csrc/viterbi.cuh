@@ -59,8 +59,14 @@ struct ShapeDev {  // device copy of dabgpu_cw_shape with expanded masks
   int32_t nbits, in_bits, n_regions, pad;
   struct {
     int32_t steps, step0, in0, ones;  // ones = kept bits per 32-bit period
-    uint32_t mask;
-    int32_t pad[3];
+    uint32_t mask;                    // puncturing vector of the period (bit p = coded bit p is sent)
+    // Depositing the `ones` received bits x of a period into the mask positions (nibble k = step k):
+    // the kept symbols of a step are its first popc() ones, so every nibble is a left shift of x:
+    //     r_nibbles = OR_t (x << dep_shift[t]) & dep_mask[t]
+    uint32_t n_terms;
+    uint32_t e_lo, e_hi;              // the mask nibbles as the high nibbles of 8 step bytes
+    uint8_t dep_shift[8];
+    uint32_t dep_mask[8];
   } r[5];
 };
 void shape_to_dev(const dabgpu_cw_shape &s, ShapeDev *o);
