@@ -121,9 +121,13 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   for (int i = 0; i < 2; i++)
     if ((rc = h_fic_out[i].reserve((size_t)S * (FIBS_PER_TF + 12)))) return rc;
   frame_slot.assign(S, 0);
-  CUDA_TRY(cudaStreamCreateWithFlags(&st_msc, cudaStreamNonBlocking));
+  // The FIC chain is small and latency-critical (the host waits for it), the MSC batches are big
+  // and nobody waits for them: give the block scheduler that order of preference.
+  int prio_lo = 0, prio_hi = 0;
+  CUDA_TRY(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+  CUDA_TRY(cudaStreamCreateWithPriority(&st_msc, cudaStreamNonBlocking, prio_lo));
   CUDA_TRY(cudaStreamCreateWithFlags(&st_copy, cudaStreamNonBlocking));
-  CUDA_TRY(cudaStreamCreateWithFlags(&st_fic, cudaStreamNonBlocking));
+  CUDA_TRY(cudaStreamCreateWithPriority(&st_fic, cudaStreamNonBlocking, prio_hi));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_fic_ready, cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_demod_done[0], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_demod_done[1], cudaEventDisableTiming));
