@@ -70,6 +70,12 @@ struct PinBuf {
 // one-time device checks + constant-table upload; returns status
 int ensure_device_ready();
 
+// Small control transfers between pinned host memory and the device done by a kernel (zero-copy
+// over UVA) instead of the copy engines: a 100 KB descriptor upload issued while a 268 MB sample
+// upload is in flight would otherwise queue behind it and stall the kernels that need it.
+// Both pointers 4-byte aligned, bytes a multiple of 4.
+int launch_ctl_copy(void *dst, const void *src, size_t bytes, cudaStream_t st);
+
 // ---- small device helpers -------------------------------------------------------------
 #ifdef __CUDACC__
 __device__ __forceinline__ uint32_t prmt(uint32_t a, uint32_t b, uint32_t sel) {

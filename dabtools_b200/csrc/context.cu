@@ -5,6 +5,8 @@
 
 #include "common.cuh"
 
+#include <algorithm>
+
 namespace dabgpu {
 
 int viterbi_init_constants();
@@ -55,6 +57,19 @@ void PinBuf::release() {
   if (p) cudaFreeHost(p);
   p = nullptr;
   cap = 0;
+}
+
+__global__ void ctl_copy_kernel(uint32_t *__restrict__ dst, const uint32_t *__restrict__ src, size_t words) {
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < words; i += stride) dst[i] = src[i];
+}
+int launch_ctl_copy(void *dst, const void *src, size_t bytes, cudaStream_t st) {
+  if (!bytes) return DABGPU_OK;
+  const size_t words = bytes / 4;
+  const unsigned blocks = (unsigned)std::min<size_t>((words + 255) / 256, 592);
+  ctl_copy_kernel<<<blocks, 256, 0, st>>>(static_cast<uint32_t *>(dst), static_cast<const uint32_t *>(src), words);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
 }
 
 static std::atomic<uint64_t> g_launches{0};

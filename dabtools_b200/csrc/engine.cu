@@ -326,7 +326,7 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
       vb_fic.add(((uint64_t)a * 4 + k) * FIC_ROW, (uint64_t)a * FIBS_PER_TF + 96 * k, 768, VIT_DESCRAMBLE);
   }
   if ((rc = d_gather_idx.reserve((size_t)S * 12 + 8))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(d_gather_idx.p, h_jobs.p, idx_bytes + (size_t)na * 8, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_ctl_copy(d_gather_idx.p, h_jobs.p, idx_bytes + (size_t)na * 8, st))) return rc;
   const uint32_t *d_idx = d_gather_idx.as<uint32_t>();
   const uint64_t *d_dst = reinterpret_cast<const uint64_t *>(d_gather_idx.as<uint8_t>() + idx_bytes);
   t0(K_FIC_PREP, st);
@@ -340,8 +340,7 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
   trellis_steps += vb_fic.total_steps;
   if ((rc = launch_fib_crc(d_fib_c, d_crc_c, 12 * na, st))) return rc;
   if ((rc = launch_scatter_rows(d_fib_c, FIBS_PER_TF, d_dst, d_fibs.as<uint8_t>(), na, st))) return rc;
-  CUDA_TRY(cudaMemcpyAsync(h_fic_out[fic_buf].p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), cudaMemcpyDeviceToHost,
-                           st));
+  if ((rc = launch_ctl_copy(h_fic_out[fic_buf].p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), st))) return rc;
   return DABGPU_OK;
 }
 
@@ -531,10 +530,10 @@ int Engine::flush_msc(cudaStream_t user) {
   uint8_t *hp = hm.as<uint8_t>();
   memcpy(hp, cifjobs.data(), b_cif);
   memcpy(hp + b_cif, etijobs.data(), b_eti);
-  CUDA_TRY(cudaMemcpyAsync(d_cifjobs.p, hp, b_cif + b_eti, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_ctl_copy(d_cifjobs.p, hp, b_cif + b_eti, st))) return rc;
   if (!reuse) {
     memcpy(hp + b_cif + b_eti, subjobs.data(), b_sub);
-    CUDA_TRY(cudaMemcpyAsync(d_subjobs.p, hp + b_cif + b_eti, b_sub, cudaMemcpyHostToDevice, st));
+    if ((rc = launch_ctl_copy(d_subjobs.p, hp + b_cif + b_eti, b_sub, st))) return rc;
   }
   CUDA_TRY(cudaEventRecord(ev_up[msc_buf], st));
   msc_buf ^= 1;
@@ -787,7 +786,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     fr.pending = true;
     active.push_back(s);
   }
-  CUDA_TRY(cudaMemcpyAsync(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), cudaMemcpyHostToDevice, st));
+  if ((rc = launch_ctl_copy(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), st))) return rc;
   CUDA_TRY(cudaEventRecord(ev_ctl[ctl_buf], st));
   ctl_buf ^= 1;
   host_us[H_PRE] += now_us() - t_pre;
@@ -839,7 +838,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       CUDA_TRY(cudaEventRecord(ev_demod_done[demod_ev], st));
       // (when kernels are being timed, each one runs alone: the FIC chain starts after the CIFs)
       CUDA_TRY(cudaStreamWaitEvent(st_fic, timing ? ev_demod_done[demod_ev] : ev_fic_ready, 0));
-      CUDA_TRY(cudaMemcpyAsync(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st_fic));
+      if ((rc = launch_ctl_copy(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), st_fic))) return rc;
       if ((rc = fic_launch(st_fic, d_ficbits.as<uint8_t>(), 9216))) return rc;
       launched = true;
     }
