@@ -52,6 +52,33 @@ def peaks():
     return 6650.0, "fallback"
 
 
+def workload_name(S, bits_per_frame, steps_per_frame):
+    return (f"{S} independent Mode I ensemble streams per GPU, 10 UEP/EEP sub-channels "
+            f"({bits_per_frame} decoded bits, {steps_per_frame} trellis steps per ETI frame), "
+            f"fed as 262144-byte callbacks; step = 3 callbacks = 2 TF = 8 ETI frames per stream")
+
+
+def vit_alu_roofline(lane_steps, lane_bits, ms, clocks):
+    if not ms:
+        return None
+    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
+    peak = 148 * 4 * 0.5 * mhz * 1e6                       # ALU-pipe warp instructions per second
+    achieved = (lane_steps / 32 * 74 + lane_bits / 32 * 10) / (ms * 1e-3)
+    return {"bound": "alu-pipe", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-instr/s",
+            "frac": achieved / peak}
+
+
+def ncu_traffic(kernel_prefix):
+    """DRAM bytes per launch (read + write) of a kernel from the committed `ncu --set full` capture
+    (profiles/ncu_traffic.json, written by tools/summarize_ncu.py); None if absent."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+        rows = [r for k, v in d.items() if k.startswith(kernel_prefix) for r in v]
+        return sum(r["dram_bytes_per_launch"] for r in rows) if rows else None
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------
 def bind_to_gpu_numa_node(gpu_index: int):
     """Run this process (and the pinned buffers it allocates from now on) on the CPUs next to its GPU:
@@ -310,7 +337,8 @@ def run_ours(args, rank, world, local_rank):
     setup_steps = SETUP_TFS // TFS_PER_STEP
     k_e2e = min(K, args.e2e_steps)
     k_e2e = max(2, k_e2e - k_e2e % 2)   # whole MSC batches (4 TF = 2 steps) inside the timed window
-    n_steps_total = setup_steps + max(W + 2 * K, 3 + K) + 1
+    k_timing = min(K, 8)
+    n_steps_total = setup_steps + max(W + K + k_timing, 3 + K) + 1
     n_tf = n_steps_total * TFS_PER_STEP
     t_gen = time.time()
     data, ens = generate_dataset(S, n_tf, dev, seed=1 + rank)
@@ -372,7 +400,7 @@ def run_ours(args, rank, world, local_rank):
     eng.enable_timing(True)
     steps0 = eng.trellis_steps()
     base += K
-    for i in range(K):
+    for i in range(k_timing):
         step_device(eng, base + i)
     kt = eng.kernel_times()
     msc_steps = None
@@ -485,16 +513,14 @@ def run_ours(args, rank, world, local_rank):
         "dtype": "u8 in / fp32 FFT / u8 path metrics",
         "data": "synthetic",
         "config": {
-            "workload": f"{S} independent Mode I ensemble streams per GPU, 10 UEP/EEP sub-channels "
-                        f"({ens.bits_per_frame} decoded bits, {ens.steps_per_frame} trellis steps per ETI frame), "
-                        f"fed as 262144-byte callbacks; step = 3 callbacks = 2 TF = 8 ETI frames per stream",
+            "workload": workload_name(S, ens.bits_per_frame, ens.steps_per_frame),
             "streams_per_gpu": S,
             "frames_per_step": S * TFS_PER_STEP * FRAMES_PER_TF * world,
             "snr_db": 30,
             "msc_batch_tf": args.msc_batch,
             "timing": f"CUDA events, max over ranks; inputs ({S * step_bytes / 1e6:.0f} MB per step, distinct every "
                       f"step) exceed the 126 MB L2, no explicit flush",
-            "kernel_timing": "per-kernel CUDA events over the K steps following the timed region, engine streams serialised so that each kernel runs alone",
+            "kernel_timing": f"per-kernel CUDA events over the {k_timing} steps following the timed region, engine streams serialised so that each kernel runs alone",
             "dataset_gen_s": round(t_gen, 1),
             "numa_binding": numa,
         },
@@ -516,8 +542,12 @@ def run_ours(args, rank, world, local_rank):
             "peak": hbm_peak,
             "unit": "GB/s",
             "frac": achieved / hbm_peak,
-            "traffic": None,
+            # demod is launched as two grids per frame (FIC symbols, CIF symbols): both together
+            "traffic": ncu_traffic("demod_kernel"),
+            "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
             "peak_source": peak_src,
+            "note": "the HBM-bound kernel of the path; the longest kernel (viterbi_kernel) is bound by the integer "
+                    "ALU pipe, see `viterbi`",
             "ms_per_launch": demod_ms,
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * frames_per_demod,
         },
@@ -526,6 +556,10 @@ def run_ours(args, rank, world, local_rank):
             "ms_per_launch": vit_ms,
             "acs_per_s": 64.0 * msc_steps_per_launch / (vit_ms * 1e-3) if vit_ms > 0 else 0.0,
             "decoded_mbit_s": msc_bits_per_launch / (vit_ms * 1e-3) / 1e6 if vit_ms > 0 else 0.0,
+            # integer-ALU-pipe roofline: 74 ALU-pipe instructions per 64-state warp step (LOP3 32, PRMT 24,
+            # IADD3 16, SHF 2: SASS count) + 10 per traced-back bit; the pipe issues one warp instruction
+            # per 2 cycles per SM sub-partition
+            "alu_pipe": vit_alu_roofline(msc_steps_per_launch, msc_bits_per_launch, vit_ms, clocks),
         },
         "fic_only": fic_cfg,
         "host_ms_per_step": {k: (host_t[k] - host_t0[k]) / 1e3 / K for k in host_t},
@@ -555,8 +589,10 @@ def run_reference(args, rank, world):
         "vs_baseline": None,
         "dtype": "u8 in / f64 FFT / long path metrics",
         "data": "synthetic",
-        "config": {"workload": "reference receive loop (sdr_demod -> dab_process_frame) on the same synthetic "
-                               "Mode I ensemble, one stream per host core; " + r["sample"]},
+        "config": {"workload": workload_name(args.streams, 24960, 25026),
+                   "reference_arm": "the unmodified reference receive loop (sdr_demod -> dab_process_frame, compiled "
+                                    "from /root/reference/src into oracle/_ref) on a bounded sample of that "
+                                    "workload, one stream per host core: " + r["sample"]},
         "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"],
                          "sample": r["sample"]},
         "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -566,8 +602,8 @@ def run_reference(args, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=8)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--streams", type=int, default=1024, help="ensemble streams per GPU")
     ap.add_argument("--e2e-steps", type=int, default=6, help="steps of the pinned-host pass (pinned memory bound)")
     ap.add_argument("--msc-batch", type=int, default=2,
