@@ -99,3 +99,56 @@ def test_masked_streams_and_ragged_progress(gpu, port):
     for s in range(S):
         want, _, _ = port.run_backend(bits[s, : fed[s]])
         assert np.array_equal(np.array(out[s]).reshape(-1, 6144), want)
+
+
+def _profile_ensembles():
+    """Ensembles that together use every UEP profile (64) and every EEP level with several sizes,
+    i.e. every puncturing index 1..24 in every region position the standard allows."""
+    from dabtools_b200 import tables as T
+    sizes = [T.UEP[i][1] for i in range(64)]
+    bins = []
+    for i in sorted(range(64), key=lambda i: -sizes[i]):
+        for b in bins:
+            if b["cu"] + sizes[i] <= 864 and len(b["idx"]) < 10 and b["bytes"] + T.shape_uep(i)["nbits"] // 8 <= 5400:
+                break
+        else:
+            b = {"idx": [], "cu": 0, "bytes": 0}
+            bins.append(b)
+        b["idx"].append(i)
+        b["cu"] += sizes[i]
+        b["bytes"] += T.shape_uep(i)["nbits"] // 8
+    out = []
+    for b in bins:
+        subs, cu = [], 0
+        for k, i in enumerate(b["idx"]):
+            subs.append(synth.SubChannel(id=3 * k + 1, start_cu=cu, uep_index=i))
+            cu += sizes[i]
+        out.append(synth.Ensemble(subs))
+    # EEP: (level, size in CU); the second ensemble has the odd sizes
+    eep_a = [(0, 12), (1, 8), (2, 6), (3, 4), (4, 27), (5, 21), (6, 18), (7, 15), (0, 96), (2, 48)]
+    eep_b = [(1, 64), (3, 40), (4, 54), (5, 84), (6, 72), (7, 30), (2, 90), (0, 24)]
+    for spec in (eep_a, eep_b):
+        subs, cu = [], 0
+        for k, (lv, sz) in enumerate(spec):
+            subs.append(synth.SubChannel(id=5 * k + 2, start_cu=cu, eep_level=lv, size_cu=sz))
+            cu += sz
+        out.append(synth.Ensemble(subs))
+    return out
+
+
+def test_every_protection_profile(gpu, port):
+    """One stream per ensemble, all in one engine (different multiplex layouts side by side): the
+    gather's per-region deposit tables and the Viterbi's length classes against the oracle for all
+    64 UEP profiles and all 8 EEP levels."""
+    ensembles = _profile_ensembles()
+    n_tf = 16
+    bits = np.stack([synth.ModeITransmitter(e).generate(1, n_tf, seed=40 + k, want_iq=False)["bits"].numpy()[0]
+                     for k, e in enumerate(ensembles)])
+    rng = np.random.default_rng(3)
+    bits[:, :, 9216:] ^= (rng.random(bits[:, :, 9216:].shape) < 0.02).astype(np.uint8)   # MSC only: stay locked
+    for batch in (1, 3):
+        got, st = _run_engine(gpu, bits, msc_batch=batch)
+        for s in range(len(ensembles)):
+            want, _, _ = port.run_backend(bits[s])
+            assert got[s].shape == want.shape and want.shape[0] == 4 * (n_tf - 13), (s, got[s].shape, want.shape)
+            assert np.array_equal(got[s], want), (batch, s)

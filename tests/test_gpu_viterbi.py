@@ -20,7 +20,7 @@ def _soft_batch(port, rng, n, nbits, p_flip, p_erase):
     return soft, data
 
 
-@pytest.mark.parametrize("nbits", [8, 24, 192, 768, 1536, 3072, 9216])
+@pytest.mark.parametrize("nbits", [8, 24, 40, 104, 192, 768, 1000, 1536, 3072, 3080, 9216])
 @pytest.mark.parametrize("p_flip,p_erase", [(0.0, 0.0), (0.03, 0.25), (0.09, 0.5), (0.5, 0.0)])
 def test_viterbi_batch_matches_oracle(gpu, port, nbits, p_flip, p_erase):
     rng = np.random.default_rng(nbits * 7 + int(p_flip * 100))
