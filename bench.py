@@ -359,10 +359,25 @@ def run_ours(args, rank, world, local_rank):
         return n
 
     # ---------------- device-resident throughput (value) ----------------
+    # The samples are resident in HBM before the timed region.  With --ingest capture (default) the
+    # engine consumes them in place (dabgpu_engine_attach_capture / feed_capture); with --ingest copy
+    # every callback is first copied into the engine's own FIFO ring (dabgpu_engine_feed_iq).
     eng = lib.Engine(S)
     eng.set_msc_batch(args.msc_batch)
+    capture = args.ingest == "capture"
+    if capture:
+        eng.attach_capture(data)
+
+    def step_value(i):
+        if not capture:
+            return step_device(eng, i)
+        n = 0
+        for c in range(CALLS_PER_STEP):
+            n += eng.feed_capture(CALL_BYTES)
+        return n
+
     for i in range(setup_steps):
-        step_device(eng, i)
+        step_value(i)
     locked = sum(eng.status(s).locked for s in range(S))
     if locked != S:
         raise RuntimeError(f"only {locked}/{S} streams locked after set-up")
@@ -371,7 +386,7 @@ def run_ours(args, rank, world, local_rank):
         sampler.start()
     n = 0
     for i in range(W):
-        n += step_device(eng, setup_steps + i)
+        n += step_value(setup_steps + i)
     assert n >= S * TFS_PER_STEP * FRAMES_PER_TF * (W - 2), f"steady state not reached: {n} frames in warm-up"
     # start from an empty pipeline so that the frames counted are exactly the frames fed
     eng.flush()
@@ -385,7 +400,7 @@ def run_ours(args, rank, world, local_rank):
     frames = 0
     base = setup_steps + W
     for i in range(K):
-        frames += step_device(eng, base + i)
+        frames += step_value(base + i)
     frames += eng.flush()   # frames still queued for a deferred MSC batch belong to these steps
     eng.join()              # ... and so does the MSC stream's last batch
     e1.record()
@@ -395,6 +410,13 @@ def run_ours(args, rank, world, local_rank):
     ms = e0.elapsed_time(e1)
     launches = lib.launch_count() - launches0
     host_t = eng.host_times()
+    if capture:   # the per-kernel pass below times the copying path (it has the ingest kernel)
+        eng.close()
+        del eng
+        eng = lib.Engine(S)
+        eng.set_msc_batch(args.msc_batch)
+        for i in range(setup_steps + W + K):
+            step_device(eng, i)
 
     # ---------------- per-kernel timing pass (same engine, next K steps) ----------------
     eng.enable_timing(True)
@@ -518,6 +540,9 @@ def run_ours(args, rank, world, local_rank):
             "frames_per_step": S * TFS_PER_STEP * FRAMES_PER_TF * world,
             "snr_db": 30,
             "msc_batch_tf": args.msc_batch,
+            "ingest": ("in place: dabgpu_engine_attach_capture + feed_capture (the samples are consumed where they lie)"
+                       if args.ingest == "capture" else
+                       "copy: dabgpu_engine_feed_iq (every callback is copied into the engine's FIFO ring first)"),
             "timing": f"CUDA events, max over ranks; inputs ({S * step_bytes / 1e6:.0f} MB per step, distinct every "
                       f"step) exceed the 126 MB L2, no explicit flush",
             "kernel_timing": f"per-kernel CUDA events over the {k_timing} steps following the timed region, engine streams serialised so that each kernel runs alone",
@@ -610,6 +635,8 @@ def main():
                     help="transmission frames per MSC Viterbi launch (dabgpu_engine_set_msc_batch)")
     ap.add_argument("--e2e-msc-batch", type=int, default=4,
                     help="same for the end-to-end pass (larger batches amortise the PCIe round trips)")
+    ap.add_argument("--ingest", default="capture", choices=["capture", "copy"],
+                    help="device-resident pass: consume the samples in place, or copy each callback into the FIFO ring")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -177,7 +177,7 @@ DABGPU_EXPORT int dabgpu_sync_frame(const uint8_t *frame, int force_timesync, in
   CUDA_TRY(cudaMemcpyAsync(ws.aux.p, &ctl, sizeof ctl, cudaMemcpyHostToDevice, st));
   CUDA_TRY(cudaMemcpyAsync(ws.aux.as<uint8_t>() + sizeof ctl, &so, sizeof so, cudaMemcpyHostToDevice, st));
   SyncOut *d_so = reinterpret_cast<SyncOut *>(ws.aux.as<uint8_t>() + sizeof ctl);
-  if ((rc = launch_sync(nullptr, nullptr, ws.in.as<uint8_t>(), ws.aux.as<StepCtl>(), d_so, 1, st))) return rc;
+  if ((rc = launch_sync(RingGeom{nullptr, 0, IQ_RING_BYTES}, nullptr, ws.in.as<uint8_t>(), ws.aux.as<StepCtl>(), d_so, 1, st))) return rc;
   CUDA_TRY(cudaMemcpyAsync(&so, d_so, sizeof so, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
   out4[0] = so.coarse_timeshift;

@@ -622,14 +622,17 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
 
 int Engine::ensure_frontend() {
   int rc;
-  if (d_ring.p) return DABGPU_OK;
-  if ((rc = d_ring.reserve((size_t)S * IQ_RING_BYTES))) return rc;
+  if (d_ctl.p) return DABGPU_OK;
+  if (!capture_base) {
+    if ((rc = d_ring.reserve((size_t)S * IQ_RING_BYTES))) return rc;
+    CUDA_TRY(cudaMemset(d_ring.p, 0, (size_t)S * IQ_RING_BYTES));
+    rg = RingGeom{d_ring.as<uint8_t>(), IQ_RING_BYTES, IQ_RING_BYTES};
+  }
   if ((rc = d_frames.reserve((size_t)S * DABGPU_TF_BYTES))) return rc;
   if ((rc = d_tails.reserve((size_t)S * TAIL_BYTES))) return rc;
   if ((rc = d_ctl.reserve((size_t)S * sizeof(StepCtl)))) return rc;
   if ((rc = d_sync.reserve((size_t)S * sizeof(SyncOut)))) return rc;
   if ((rc = h_sync.reserve((size_t)S * sizeof(SyncOut)))) return rc;
-  CUDA_TRY(cudaMemset(d_ring.p, 0, (size_t)S * IQ_RING_BYTES));
   CUDA_TRY(cudaMemset(d_frames.p, 0, (size_t)S * DABGPU_TF_BYTES));
   CUDA_TRY(cudaMemset(d_tails.p, 0, (size_t)S * TAIL_BYTES));
   CUDA_TRY(cudaMemset(d_sync.p, 0, (size_t)S * sizeof(SyncOut)));
@@ -688,8 +691,52 @@ int Engine::feed_submitted() {
   return rc;
 }
 
+int Engine::attach_capture(const uint8_t *iq_device, size_t pitch, size_t len) {
+  if (d_ctl.p || capture_base || stage_count) {
+    set_error(DABGPU_ERR_STATE, "attach_capture: must come before the first samples are fed");
+    return DABGPU_ERR_STATE;
+  }
+  if (virtual_tuner) {
+    set_error(DABGPU_ERR_STATE, "attach_capture: the virtual tuner rewrites the samples and needs the copying path");
+    return DABGPU_ERR_STATE;
+  }
+  if (!iq_device || ((uintptr_t)iq_device & 15) || (pitch & 15) || (len & 15) || pitch < len ||
+      len < 2u * DABGPU_TF_BYTES || len > 0x7fffffffu) {
+    set_error(DABGPU_ERR_ARG,
+              "attach_capture: pointer, pitch and length must be multiples of 16, pitch >= length, "
+              "2 transmission frames <= length < 2 GiB");
+    return DABGPU_ERR_ARG;
+  }
+  capture_base = iq_device;
+  capture_len = len;
+  capture_fed = 0;
+  rg = RingGeom{iq_device, pitch, (uint32_t)len};
+  return DABGPU_OK;
+}
+
+int Engine::feed_capture(int chunk_len) {
+  if (!capture_base) {
+    set_error(DABGPU_ERR_STATE, "feed_capture: no capture attached");
+    return DABGPU_ERR_STATE;
+  }
+  if (chunk_len > 0 && capture_fed + (uint64_t)chunk_len > capture_len) {
+    set_error(DABGPU_ERR_STATE, "feed_capture: the capture holds %llu more bytes per stream, %d requested",
+              (unsigned long long)(capture_len - capture_fed), chunk_len);
+    return DABGPU_ERR_STATE;
+  }
+  capture_call = true;
+  const int rc = feed_iq(capture_base, (size_t)rg.pitch, chunk_len, true);
+  capture_call = false;
+  if (rc == DABGPU_OK) capture_fed += (uint64_t)chunk_len;
+  return rc;
+}
+
 int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_device) {
   int rc;
+  if (capture_base && !capture_call) {
+    set_error(DABGPU_ERR_STATE, "feed_iq: this engine consumes an attached capture; use dabgpu_engine_feed_capture");
+    return DABGPU_ERR_STATE;
+  }
   if (!on_device) {
     if ((rc = submit_iq(iq, pitch, chunk_len))) return rc;
     // chunks submitted earlier are consumed first (FIFO); this call consumes exactly one
@@ -720,7 +767,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       set_error(DABGPU_ERR_STATE, "stream %d: FIFO overflow", s);
       return DABGPU_ERR_STATE;
     }
-    c.wr_pos = (fr.fifo_start + fr.fifo_count) % IQ_RING_BYTES;
+    c.wr_pos = (fr.fifo_start + fr.fifo_count) % rg.mod;
     c.nco_hz = virtual_tuner ? (int32_t)(fr.frequency - f0) : 0;
     c.nco_sample0 = fr.samples_in;
     fr.samples_in += (uint64_t)chunk_len / 2;
@@ -732,18 +779,18 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     if (shift > 0) {
       const uint32_t skip = std::min<uint32_t>((uint32_t)shift, fr.fifo_count);
       const uint32_t skip_pos = fr.fifo_start;
-      fr.fifo_start = (fr.fifo_start + skip) % IQ_RING_BYTES;
+      fr.fifo_start = (fr.fifo_start + skip) % rg.mod;
       fr.fifo_count -= skip;
       const uint32_t n = std::min(bytes, fr.fifo_count);
       c.rd_pos[0] = fr.fifo_start;
       c.rd_dst[0] = 0;
       c.rd_bytes[0] = n;
-      fr.fifo_start = (fr.fifo_start + n) % IQ_RING_BYTES;
+      fr.fifo_start = (fr.fifo_start + n) % rg.mod;
       fr.fifo_count -= n;
       // the skipped bytes were parked in buffer[0..skip) and are only overwritten up to n
       const uint32_t lim = std::min(skip, bytes);
       if (n < lim) {
-        c.rd_pos[1] = (skip_pos + n) % IQ_RING_BYTES;
+        c.rd_pos[1] = (skip_pos + n) % rg.mod;
         c.rd_dst[1] = n;
         c.rd_bytes[1] = lim - n;
       }
@@ -752,7 +799,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       c.rd_pos[0] = fr.fifo_start;
       c.rd_dst[0] = 0;
       c.rd_bytes[0] = n;
-      fr.fifo_start = (fr.fifo_start + n) % IQ_RING_BYTES;
+      fr.fifo_start = (fr.fifo_start + n) % rg.mod;
       fr.fifo_count -= n;
     }
     any_read = true;
@@ -790,11 +837,12 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   CUDA_TRY(cudaEventRecord(ev_ctl[ctl_buf], st));
   ctl_buf ^= 1;
   host_us[H_PRE] += now_us() - t_pre;
-  const uint8_t *d_src = iq;
-  t0(K_INGEST, st);
-  if ((rc = launch_ingest(d_src, pitch, (uint32_t)chunk_len, d_ring.as<uint8_t>(), d_ctl.as<StepCtl>(), S, st)))
-    return rc;
-  t1(K_INGEST, st);
+  if (!capture_base) {  // (an attached capture is consumed in place)
+    t0(K_INGEST, st);
+    if ((rc = launch_ingest(iq, pitch, (uint32_t)chunk_len, d_ring.as<uint8_t>(), d_ctl.as<StepCtl>(), S, st)))
+      return rc;
+    t1(K_INGEST, st);
+  }
   if (consuming_stage >= 0) CUDA_TRY(cudaEventRecord(ev_consumed[consuming_stage], st));
   n_eti = 0;
   eti_stream.clear();
@@ -805,30 +853,30 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   int demod_ev = -1;
   if (any_read) {
     t0(K_FIFO, st);
-    if (any_mat && (rc = launch_fifo_read(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+    if (any_mat && (rc = launch_fifo_read(rg, d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
                                           d_ctl.as<StepCtl>(), S, true, st)))
       return rc;
-    if (any_copy && (rc = launch_fifo_read(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+    if (any_copy && (rc = launch_fifo_read(rg, d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
                                            d_ctl.as<StepCtl>(), S, false, st)))
       return rc;
-    if ((rc = launch_tail_update(d_ring.as<uint8_t>(), d_frames.as<uint8_t>(), d_tails.as<uint8_t>(),
+    if ((rc = launch_tail_update(rg, d_frames.as<uint8_t>(), d_tails.as<uint8_t>(),
                                  d_ctl.as<StepCtl>(), S, st)))
       return rc;
     t1(K_FIFO, st);
     if (!active.empty()) {
       t0(K_SYNC, st);
-      if ((rc = launch_sync(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+      if ((rc = launch_sync(rg, d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
                             d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), S, st)))
         return rc;
       t1(K_SYNC, st);
       // FIC symbols first; their decoding then runs on st_fic next to the CIF symbols on `st`
       t0(K_DEMOD, st);
-      if ((rc = launch_demod(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+      if ((rc = launch_demod(rg, d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
                              d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), d_ficbits.as<uint8_t>(),
                              d_cifs.as<uint8_t>(), S, 0, 1, st)))
         return rc;
       CUDA_TRY(cudaEventRecord(ev_fic_ready, st));
-      if ((rc = launch_demod(d_ring.as<uint8_t>(), d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
+      if ((rc = launch_demod(rg, d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
                              d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), d_ficbits.as<uint8_t>(),
                              d_cifs.as<uint8_t>(), S, 1, 4, st)))
         return rc;
@@ -888,6 +936,10 @@ DABGPU_EXPORT int dabgpu_engine_submit_iq(dabgpu_engine *h, const uint8_t *iq, s
   return h->e.submit_iq(iq, pitch, chunk_len);
 }
 DABGPU_EXPORT int dabgpu_engine_feed_submitted(dabgpu_engine *h) { return h->e.feed_submitted(); }
+DABGPU_EXPORT int dabgpu_engine_attach_capture(dabgpu_engine *h, const uint8_t *iq_device, size_t pitch, size_t len) {
+  return h->e.attach_capture(iq_device, pitch, len);
+}
+DABGPU_EXPORT int dabgpu_engine_feed_capture(dabgpu_engine *h, int chunk_len) { return h->e.feed_capture(chunk_len); }
 DABGPU_EXPORT int dabgpu_engine_process_demapped(dabgpu_engine *h, const uint8_t *tfs, size_t pitch,
                                                  const uint8_t *mask, int on_device) {
   return h->e.process_demapped(tfs, pitch, mask, on_device != 0);

@@ -122,6 +122,13 @@ struct Engine {
   int consuming_stage = -1;
   int submit_iq(const uint8_t *iq, size_t pitch, int chunk_len);
   int feed_submitted();
+  // zero-copy source: one contiguous device-resident capture per stream, consumed in place
+  RingGeom rg = {nullptr, 0, IQ_RING_BYTES};
+  const uint8_t *capture_base = nullptr;
+  uint64_t capture_len = 0, capture_fed = 0;
+  bool capture_call = false;
+  int attach_capture(const uint8_t *iq_device, size_t pitch, size_t len);
+  int feed_capture(int chunk_len);
   HostPool pool;
   std::vector<FrameWork> works;
   // Transmission frames whose FIC has been decoded but whose dab_process_frame is still to run.

@@ -114,23 +114,22 @@ int launch_ingest(const uint8_t *d_src, uint64_t src_pitch, uint32_t chunk_len, 
 // FIFO read into the persistent per-stream frame buffer
 // =================================================================================================
 // 16 bytes of a ring window starting at the even offset `p` (wraps at word granularity)
-__device__ __forceinline__ uint4 ring_load16(const uint8_t *rs, uint32_t p) {
+__device__ __forceinline__ uint4 ring_load16(const uint8_t *rs, uint32_t mod, uint32_t p) {
   const uint32_t sh = (p & 3u) * 8u;
   uint32_t w[5];
 #pragma unroll
-  for (int k = 0; k < 5; k++) w[k] = *reinterpret_cast<const uint32_t *>(rs + (((p & ~3u) + 4u * k) % IQ_RING_BYTES));
+  for (int k = 0; k < 5; k++) w[k] = *reinterpret_cast<const uint32_t *>(rs + ring_wrap((p & ~3u) + 4u * k, mod));
   return make_uint4(__funnelshift_r(w[0], w[1], sh), __funnelshift_r(w[1], w[2], sh),
                     __funnelshift_r(w[2], w[3], sh), __funnelshift_r(w[3], w[4], sh));
 }
 
 template <bool MATERIALISE>
-__global__ void __launch_bounds__(256) fifo_read_kernel(const uint8_t *__restrict__ ring,
-                                                        const uint8_t *__restrict__ tails,
+__global__ void __launch_bounds__(256) fifo_read_kernel(RingGeom ring, const uint8_t *__restrict__ tails,
                                                         uint8_t *__restrict__ frames,
                                                         const StepCtl *__restrict__ ctl) {
   const int s = blockIdx.y;
   const StepCtl *c = &ctl[s];
-  const uint8_t *rs = ring + (uint64_t)s * IQ_RING_BYTES;
+  const uint8_t *rs = ring.base + (uint64_t)s * ring.pitch;
   uint8_t *fs = frames + (uint64_t)s * DABGPU_TF_BYTES;
   const uint32_t vec = blockIdx.x * blockDim.x + threadIdx.x;
   if (MATERIALISE) {
@@ -140,7 +139,7 @@ __global__ void __launch_bounds__(256) fifo_read_kernel(const uint8_t *__restric
     const uint32_t b = 16u * vec;
     uint4 v;
     if (b < TAIL_OFF)
-      v = ring_load16(rs, c->mat_pos + b);
+      v = ring_load16(rs, ring.mod, c->mat_pos + b);
     else
       v = *reinterpret_cast<const uint4 *>(tails + (uint64_t)s * TAIL_BYTES + (b - TAIL_OFF));
     *reinterpret_cast<uint4 *>(fs + b) = v;
@@ -151,7 +150,7 @@ __global__ void __launch_bounds__(256) fifo_read_kernel(const uint8_t *__restric
   // unaligned ring position (all shifts are even byte counts)
   const uint32_t n0 = c->rd_bytes[0];
   if (16u * vec < n0) {
-    const uint4 o4 = ring_load16(rs, c->rd_pos[0] + 16u * vec);
+    const uint4 o4 = ring_load16(rs, ring.mod, c->rd_pos[0] + 16u * vec);
     if (16u * vec + 16u <= n0) {
       *reinterpret_cast<uint4 *>(fs + 16u * vec) = o4;
     } else {
@@ -162,10 +161,10 @@ __global__ void __launch_bounds__(256) fifo_read_kernel(const uint8_t *__restric
   // segment 1 (rare: FIFO ran dry during a large positive shift): plain byte copy
   const uint32_t n1 = c->rd_bytes[1];
   for (uint32_t b = 16u * vec; b < min(n1, 16u * vec + 16u); b++)
-    fs[c->rd_dst[1] + b] = rs[(c->rd_pos[1] + b) % IQ_RING_BYTES];
+    fs[c->rd_dst[1] + b] = rs[ring_wrap(c->rd_pos[1] + b, ring.mod)];
 }
 
-int launch_fifo_read(const uint8_t *d_ring, const uint8_t *d_tails, uint8_t *d_frames, const StepCtl *d_ctl,
+int launch_fifo_read(RingGeom d_ring, const uint8_t *d_tails, uint8_t *d_frames, const StepCtl *d_ctl,
                      int n_streams, bool materialise, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
   dim3 grid(DABGPU_TF_BYTES / 16 / 256, n_streams);
@@ -178,8 +177,7 @@ int launch_fifo_read(const uint8_t *d_ring, const uint8_t *d_tails, uint8_t *d_f
 }
 
 // tail[j] = byte TAIL_OFF + j of the stream's logical frame buffer after this step's read
-__global__ void __launch_bounds__(128) tail_update_kernel(const uint8_t *__restrict__ ring,
-                                                          const uint8_t *__restrict__ frames,
+__global__ void __launch_bounds__(128) tail_update_kernel(RingGeom ring, const uint8_t *__restrict__ frames,
                                                           uint8_t *__restrict__ tails,
                                                           const StepCtl *__restrict__ ctl) {
   const int s = blockIdx.x;
@@ -195,7 +193,7 @@ __global__ void __launch_bounds__(128) tail_update_kernel(const uint8_t *__restr
   const uint32_t n0 = c->rd_bytes[0];  // fresh bytes; the rest of the buffer keeps its old content
   const uint32_t b = TAIL_OFF + j;
   if (b >= n0) return;
-  const uint4 v = ring_load16(ring + (uint64_t)s * IQ_RING_BYTES, c->src_pos + b);
+  const uint4 v = ring_load16(ring.base + (uint64_t)s * ring.pitch, ring.mod, c->src_pos + b);
   if (b + 16u <= n0) {
     *reinterpret_cast<uint4 *>(t + j) = v;
   } else {
@@ -204,7 +202,7 @@ __global__ void __launch_bounds__(128) tail_update_kernel(const uint8_t *__restr
   }
 }
 
-int launch_tail_update(const uint8_t *d_ring, const uint8_t *d_frames, uint8_t *d_tails, const StepCtl *d_ctl,
+int launch_tail_update(RingGeom d_ring, const uint8_t *d_frames, uint8_t *d_tails, const StepCtl *d_ctl,
                        int n_streams, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
   tail_update_kernel<<<n_streams, 128, 0, st>>>(d_ring, d_frames, d_tails, d_ctl);
@@ -413,7 +411,7 @@ __device__ __forceinline__ uint32_t sym_byte_off(int l) { return 2u * (2656u + 2
 // where a stream's frame lives this step (see StepCtl) and how one symbol is fetched from it
 struct FrameSrc {
   const uint8_t *ring, *tail, *frame;
-  uint32_t ring_mode, pos, delta;
+  uint32_t ring_mode, pos, delta, mod;
 };
 
 // thread 0: start the TMA copies of symbol l into stage buffer `st`
@@ -426,17 +424,16 @@ __device__ __forceinline__ void issue_symbol_load(DemodSmem &sm, const FrameSrc 
   }
   const bool last = l == 75;  // its second half may be stale: it comes from the tail store
   const uint32_t need = (last ? SYM_BYTES - TAIL_BYTES : SYM_BYTES) + 16u;
-  const uint32_t a0 = ((src.pos + off) % IQ_RING_BYTES) & ~15u;
+  const uint32_t a0 = ring_wrap(src.pos + off, src.mod) & ~15u;
   mbar_expect_tx(&sm.full[st], need + (last ? TAIL_BYTES : 0u));
-  const uint32_t first = min(need, IQ_RING_BYTES - a0);
+  const uint32_t first = min(need, src.mod - a0);
   tma_load_1d(sm.stage[st], src.ring + a0, first, &sm.full[st]);
   if (first < need) tma_load_1d(sm.stage[st] + first, src.ring, need - first, &sm.full[st]);
   if (last) tma_load_1d(sm.tailbuf, src.tail, TAIL_BYTES, &sm.full[st]);
 }
 
 template <bool DEBUG>
-__global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__restrict__ ring,
-                                                            const uint8_t *__restrict__ tails,
+__global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(RingGeom ring, const uint8_t *__restrict__ tails,
                                                             const uint8_t *__restrict__ frames,
                                                             const StepCtl *__restrict__ ctl,
                                                             const SyncOut *__restrict__ sync,
@@ -457,7 +454,8 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__
   src.ring_mode = DEBUG ? 0u : ctl[s].src_ring;
   src.pos = DEBUG ? 0u : ctl[s].src_pos;
   src.delta = src.ring_mode ? (src.pos & 15u) : 0u;
-  src.ring = DEBUG ? nullptr : ring + (uint64_t)s * IQ_RING_BYTES;
+  src.ring = DEBUG ? nullptr : ring.base + (uint64_t)s * ring.pitch;
+  src.mod = ring.mod;
   src.tail = DEBUG ? nullptr : tails + (uint64_t)s * TAIL_BYTES;
   const int l0 = seg == 0 ? 0 : 3 + 18 * (seg - 1);
   const int nsym = seg == 0 ? 4 : 19;
@@ -571,7 +569,7 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(const uint8_t *__
   }
 }
 
-int launch_demod(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
+int launch_demod(RingGeom d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
                  const SyncOut *d_sync, uint8_t *d_fic_bits, uint8_t *d_cifs, int n_streams, int seg_first,
                  int seg_count, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
@@ -600,7 +598,7 @@ int launch_demod_debug(const uint8_t *d_frame, float2 *d_symbols, float2 *d_symb
   // one "segment" walking all 76 symbols is what the debug variant needs: reuse seg 0 semantics
   // by launching the five segments; each writes its own rows
   dim3 grid(5, 1);
-  demod_kernel<true><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(nullptr, nullptr, d_frame, nullptr, nullptr,
+  demod_kernel<true><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(RingGeom{nullptr, 0, IQ_RING_BYTES}, nullptr, d_frame, nullptr, nullptr,
                                                                   nullptr, nullptr, d_symbols, d_symbols_d, d_bits, 0);
   LAUNCH_CHECK();
   return DABGPU_OK;
@@ -690,9 +688,9 @@ struct SrcU8 {
 // the frame through the ring window + tail store (StepCtl.src_ring == 1)
 struct SrcRing {
   const uint8_t *ring, *tail;
-  uint32_t pos;
+  uint32_t pos, mod;
   __device__ __forceinline__ const uint8_t *byte_ptr(uint32_t b) const {
-    return b < TAIL_OFF ? ring + (pos + b) % IQ_RING_BYTES : tail + (b - TAIL_OFF);
+    return b < TAIL_OFF ? ring + ring_wrap(pos + b, mod) : tail + (b - TAIL_OFF);
   }
   __device__ __forceinline__ float real(int n) const { return u8_to_sample(*byte_ptr(2u * (uint32_t)n)); }
   __device__ __forceinline__ float2 at(int n) const {
@@ -886,8 +884,7 @@ __device__ void sync_frame(SyncSmem &sm, const Src &src, bool force, SyncOut &r)
 }
 
 // ... for every stream with ctl.run
-__global__ void __launch_bounds__(FFT_THREADS) sync_kernel(const uint8_t *__restrict__ ring,
-                                                           const uint8_t *__restrict__ tails,
+__global__ void __launch_bounds__(FFT_THREADS) sync_kernel(RingGeom ring, const uint8_t *__restrict__ tails,
                                                            const uint8_t *__restrict__ frames,
                                                            const StepCtl *__restrict__ ctl,
                                                            SyncOut *__restrict__ out) {
@@ -898,14 +895,15 @@ __global__ void __launch_bounds__(FFT_THREADS) sync_kernel(const uint8_t *__rest
   SyncOut r = out[s];  // fine_timeshift / fine_freq_shift persist across early exits (sdr_state_t)
   const bool force = ctl[s].force_timesync != 0;
   if (ctl[s].src_ring)
-    sync_frame(sm, SrcRing{ring + (uint64_t)s * IQ_RING_BYTES, tails + (uint64_t)s * TAIL_BYTES, ctl[s].src_pos},
+    sync_frame(sm, SrcRing{ring.base + (uint64_t)s * ring.pitch, tails + (uint64_t)s * TAIL_BYTES, ctl[s].src_pos,
+                           ring.mod},
                force, r);
   else
     sync_frame(sm, SrcU8{frames + (uint64_t)s * DABGPU_TF_BYTES}, force, r);
   if (threadIdx.x == 0) out[s] = r;
 }
 
-int launch_sync(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
+int launch_sync(RingGeom d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
                 SyncOut *d_out, int n_streams, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
   static bool attr_set = false;

@@ -12,6 +12,17 @@ enum : uint32_t {
   TAIL_OFF = 393216u - TAIL_BYTES
 };
 
+// Where the streams' sample FIFOs live: the engine's own ring (pitch = mod = IQ_RING_BYTES), or a
+// caller-owned capture that is consumed in place (dabgpu_engine_attach_capture: no ingest copy).
+// Stream s, FIFO offset p -> base + s * pitch + (p mod `mod`); base, pitch and mod are multiples of 16.
+struct RingGeom {
+  const uint8_t *base;
+  uint64_t pitch;
+  uint32_t mod;
+};
+// offsets stay below 2 * mod everywhere (a position plus less than one frame)
+__host__ __device__ static inline uint32_t ring_wrap(uint32_t x, uint32_t mod) { return x >= mod ? x - mod : x; }
+
 // Per-stream, per-step control block, written by the host FSM, read by the kernels.
 struct StepCtl {
   // ---- ingest (rtlsdr_callback + cbWrite loop, dab2eti.c:125, input_sdr.c:36-38)
@@ -52,16 +63,16 @@ int launch_ingest(const uint8_t *d_src, uint64_t src_pitch, uint32_t chunk_len, 
                   const StepCtl *d_ctl, int n_streams, cudaStream_t st);
 // fallback copy into the frame buffer for the streams with src_ring == 0 (materialise = true runs
 // the "previous frame" pass for the streams with mat == 1 instead)
-int launch_fifo_read(const uint8_t *d_ring, const uint8_t *d_tails, uint8_t *d_frames, const StepCtl *d_ctl,
+int launch_fifo_read(RingGeom ring, const uint8_t *d_tails, uint8_t *d_frames, const StepCtl *d_ctl,
                      int n_streams, bool materialise, cudaStream_t st);
 // keep the tail store equal to the last TAIL_BYTES of every stream's logical frame buffer
-int launch_tail_update(const uint8_t *d_ring, const uint8_t *d_frames, uint8_t *d_tails, const StepCtl *d_ctl,
+int launch_tail_update(RingGeom ring, const uint8_t *d_frames, uint8_t *d_tails, const StepCtl *d_ctl,
                        int n_streams, cudaStream_t st);
-int launch_sync(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
+int launch_sync(RingGeom ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
                 SyncOut *d_out, int n_streams, cudaStream_t st);
 // fic_bits: [n_streams][9216] one byte per bit (reference layout); MSC goes to the CIF store as planes
 // segments: 0 = PRS + the 3 FIC symbols, 1..4 = the 4 CIFs; launched as [seg_first, seg_first+seg_count)
-int launch_demod(const uint8_t *d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
+int launch_demod(RingGeom ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
                  const SyncOut *d_sync, uint8_t *d_fic_bits, uint8_t *d_cifs, int n_streams, int seg_first,
                  int seg_count, cudaStream_t st);
 

@@ -289,5 +289,21 @@ def _engine_feed_submitted(self) -> int:
     return self._lib.dabgpu_engine_eti_count(self._h)
 
 
+def _engine_attach_capture(self, iq):
+    """iq: torch CUDA uint8 [n_streams][len], row-contiguous; consumed in place by feed_capture()"""
+    assert iq.is_cuda and iq.dim() == 2 and iq.shape[0] == self.n_streams and iq.stride(1) == 1
+    self._lib.dabgpu_engine_attach_capture.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_size_t]
+    check(self._lib.dabgpu_engine_attach_capture(self._h, C.c_void_p(iq.data_ptr()), iq.stride(0), iq.shape[1]))
+    self._capture = iq   # keep it alive
+
+
+def _engine_feed_capture(self, chunk_len: int) -> int:
+    self._lib.dabgpu_engine_feed_capture.argtypes = [C.c_void_p, C.c_int]
+    check(self._lib.dabgpu_engine_feed_capture(self._h, chunk_len))
+    return self._lib.dabgpu_engine_eti_count(self._h)
+
+
+Engine.attach_capture = _engine_attach_capture
+Engine.feed_capture = _engine_feed_capture
 Engine.submit_iq = _engine_submit_iq
 Engine.feed_submitted = _engine_feed_submitted

@@ -113,6 +113,15 @@ int dabgpu_engine_feed_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int
  * makes it asynchronous) and returns; feed_submitted() processes the oldest submitted chunk.  At
  * most three chunks may be in flight.  feed_iq(host pointer) == submit_iq + feed_submitted. */
 int dabgpu_engine_submit_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int chunk_len);
+/* Zero-copy source for samples that already are in device memory as one contiguous capture per
+ * stream (a recording loaded into HBM, or the output buffer of a device-side producer): stream s
+ * at iq_device + s * pitch, `len` bytes each.  attach_capture() must precede the first samples;
+ * feed_capture(chunk_len) then consumes the next chunk_len bytes of every stream exactly like
+ * feed_iq() would, reading them in place instead of copying them into the engine's FIFO
+ * (rtlsdr_callback's cbWrite loop, dab2eti.c:125, has no counterpart).  The capture must stay
+ * valid and unchanged while the engine lives.  Not available with DABGPU_ENGINE_VIRTUAL_TUNER. */
+int dabgpu_engine_attach_capture(dabgpu_engine *e, const uint8_t *iq_device, size_t pitch, size_t len);
+int dabgpu_engine_feed_capture(dabgpu_engine *e, int chunk_len);
 int dabgpu_engine_feed_submitted(dabgpu_engine *e);
 /* Back-end only: one demapped transmission frame (fic 9216 + msc 221184 bytes of 0/1, i.e. the
  * payload of demapped_transmission_frame_t) for every stream with mask[s] != 0 (mask NULL = all);

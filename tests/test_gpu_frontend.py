@@ -156,6 +156,51 @@ def test_full_path_with_trailing_backend(gpu, port, batch):
         assert np.array_equal(got, want["eti"]), s
 
 
+@pytest.mark.parametrize("batch", [1, 2])
+def test_attached_capture_is_consumed_in_place(gpu, port, batch):
+    """dabgpu_engine_attach_capture / feed_capture: the kernels read a device-resident capture in
+    place (no ingest copy, FIFO positions taken modulo the capture length); same ETI, same traces."""
+    import torch
+    ens = synth.small_ensemble()
+    S, n_tf = 3, 22
+    g = synth.ModeITransmitter(ens).generate(S, n_tf, seed=23, snr_db=30, tail_samples=262144)
+    iq_full = g["iq"].numpy()
+    cuts = [4242, 0, 150000]
+    n = min(iq_full.shape[1] - 2 * c for c in cuts) // 262144 * 262144
+    iq = np.stack([iq_full[s, 2 * c: 2 * c + n] for s, c in enumerate(cuts)])
+    dev = torch.from_numpy(iq).cuda()
+    eng = gpu.Engine(S, 200_000_000, 0)
+    eng.set_msc_batch(batch)
+    eng.attach_capture(dev)
+    with pytest.raises(gpu.DabGpuError):
+        eng.feed_iq(iq[:, :262144])          # an engine with a capture takes no other samples
+    out = [[] for _ in range(S)]
+    trace = [[] for _ in range(S)]
+    for pos in range(0, n, 262144):
+        eng.feed_capture(262144)
+        eti, ids = eng.fetch_eti()
+        for f, s in zip(eti, ids):
+            out[s].append(f.copy())
+        for s in range(S):
+            st = eng.status(s)
+            trace[s].append((st.last_ok, st.coarse_timeshift, st.fine_timeshift, st.coarse_freq_shift))
+    with pytest.raises(gpu.DabGpuError):
+        eng.feed_capture(262144)             # past the end of the capture
+    if eng.flush():
+        eti, ids = eng.fetch_eti()
+        for f, s in zip(eti, ids):
+            out[s].append(f.copy())
+    eng.close()
+    for s in range(S):
+        want = port.run_iq(iq[s])
+        want_tr = [(int(a["ok"]), int(a["coarse_timeshift"]), int(a["fine_timeshift"]), int(a["coarse_freq_shift"]))
+                   for a in want["trace"]]
+        assert trace[s] == want_tr, s
+        got = np.array(out[s], dtype=np.uint8).reshape(-1, 6144)
+        assert got.shape == want["eti"].shape and got.shape[0] >= 16
+        assert np.array_equal(got, want["eti"]), s
+
+
 def test_full_path_golden(gpu):
     gold = np.load(os.path.join(GOLDEN, "reference_v1.npz"))
     import zlib
