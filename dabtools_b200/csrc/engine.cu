@@ -223,7 +223,7 @@ void Engine::destroy() {
       for (int j = 0; j < 2; j++) cudaEventDestroy(ev[k][j]);
   DevBuf *db[] = {&d_ring, &d_frames, &d_tails, &d_chunk, &d_ctl, &d_sync, &d_cifs, &d_fibs, &d_crc, &d_ficbits,
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
-                  &d_subjobs, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
+                  &d_subjobs, &d_periods, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
   for (DevBuf *b : db) b->release();
   PinBuf *pb[] = {&h_ctl, &h_stepctl[0], &h_stepctl[1], &h_sync, &h_fic_out[0], &h_fic_out[1], &h_jobs, &h_msc[0], &h_msc[1], &h_eti, &h_chunk};
   for (PinBuf *b : pb) b->release();
@@ -281,6 +281,35 @@ int Engine::refresh_layout(int s) {
     return DABGPU_ERR_STATE;
   }
   L.rows_bytes = row;
+  {
+    std::vector<uint32_t> sig;
+    for (int u = 0; u < L.nsub; u++) {
+      sig.push_back(L.sub[u].in_bit0);
+      sig.push_back(L.sub[u].shape);
+      sig.push_back(L.sub[u].row_off);
+    }
+    const LayoutKey *hit = nullptr;
+    for (const LayoutKey &k : layout_keys)
+      if (k.sig == sig) hit = &k;
+    if (!hit) {
+      LayoutKey k;
+      k.sig = sig;
+      k.per0 = (uint32_t)periods.size();
+      for (int u = 0; u < L.nsub; u++)
+        if (!append_periods(shapes[L.sub[u].shape], L.sub[u].in_bit0, L.sub[u].row_off, periods)) {
+          periods.resize(k.per0);
+          set_error(DABGPU_ERR_STATE, "stream %d: sub-channel puncturing outside EN 300 401", s);
+          L.version = 0;
+          return DABGPU_ERR_STATE;
+        }
+      k.nper = (uint32_t)periods.size() - k.per0;
+      layout_keys.push_back(k);
+      periods_dirty = true;
+      hit = &layout_keys.back();
+    }
+    L.per0 = hit->per0;
+    L.nper = hit->nper;
+  }
   L.dev.nst = nst;
   L.dev.fl = fl + nst + 1 + 24;
   L.dev.payload = payload;
@@ -291,6 +320,15 @@ int Engine::refresh_layout(int s) {
 }
 
 int Engine::upload_tables(cudaStream_t st) {
+  if (periods_dirty) {
+    int rc;
+    // (growing the store moves it: the previous batch, which reads it, is complete by now)
+    if ((rc = d_periods.reserve(periods.size() * sizeof(PeriodDesc) * 2 + 4096))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(d_periods.p, periods.data(), periods.size() * sizeof(PeriodDesc), cudaMemcpyHostToDevice,
+                             st));
+    CUDA_TRY(cudaStreamSynchronize(st));  // `periods` may grow (reallocate) right after
+    periods_dirty = false;
+  }
   if (!shapes_dirty) return DABGPU_OK;
   std::vector<ShapeDev> sd(shapes.size());
   for (size_t i = 0; i < shapes.size(); i++) shape_to_dev(shapes[i], &sd[i]);
@@ -482,35 +520,29 @@ int Engine::flush_msc(cudaStream_t user) {
   // The per-sub-channel job lists only depend on which streams produced frames and on their
   // multiplex layouts: in the steady state of locked receivers they repeat from flush to flush and
   // the device copies (and the Viterbi plan) are reused as they are.
-  const bool reuse = pend_sig == cached_sig && (size_t)n_new == frame_sub0.size() && !subjobs.empty();
+  const bool reuse = pend_sig == cached_sig && (size_t)n_new == frame_row.size() && n_new > 0;
   if (!reuse) {
-    subjobs.clear();
-    frame_sub0.clear();
+    frame_row.clear();
     vb_msc.clear();
     row_base = 0;
     for (int f = 0; f < n_new; f++) {
       const EnsLayout &L = layout[pend_stream[f]];
-      frame_sub0.push_back((uint32_t)subjobs.size());
-      for (int u = 0; u < L.nsub; u++) {
-        SubJob sj;
-        sj.row_off = row_base + L.sub[u].row_off;
-        sj.in_bit0 = L.sub[u].in_bit0;
-        sj.shape = L.sub[u].shape;
-        subjobs.push_back(sj);
-        vb_msc.add(sj.row_off, (uint64_t)(base + f) * DABGPU_ETI_BYTES + L.sub[u].eti_off, L.sub[u].nbits,
-                   VIT_DESCRAMBLE);
-      }
+      frame_row.push_back(row_base);
+      for (int u = 0; u < L.nsub; u++)
+        vb_msc.add(row_base + L.sub[u].row_off, (uint64_t)(base + f) * DABGPU_ETI_BYTES + L.sub[u].eti_off,
+                   L.sub[u].nbits, VIT_DESCRAMBLE);
       row_base += L.rows_bytes;
     }
     cached_sig = pend_sig;
   }
   for (int f = 0; f < n_new; f++) {
-    cifjobs[f].sub0 = frame_sub0[f];
-    cifjobs[f].nsub = (uint32_t)layout[pend_stream[f]].nsub;
+    const EnsLayout &L = layout[pend_stream[f]];
+    cifjobs[f].row_base = frame_row[f];
+    cifjobs[f].per0 = L.per0;
+    cifjobs[f].nper = L.nper;
   }
   if ((rc = upload_tables(st))) return rc;
-  const size_t b_cif = cifjobs.size() * sizeof(CifJob), b_eti = etijobs.size() * sizeof(EtiJob),
-               b_sub = subjobs.size() * sizeof(SubJob);
+  const size_t b_cif = cifjobs.size() * sizeof(CifJob), b_eti = etijobs.size() * sizeof(EtiJob);
   // two pinned staging areas alternate; each is free again once its upload has completed.
   // Every store is sized for a full batch (S streams x msc_batch frames) the first time it is
   // needed, so that no allocation ever happens in the steady state.
@@ -518,9 +550,8 @@ int Engine::flush_msc(cudaStream_t user) {
   auto full = [scale](size_t bytes) { return (size_t)((double)bytes * scale) + 4096; };
   PinBuf &hm = h_msc[msc_buf];
   CUDA_TRY(cudaEventSynchronize(ev_up[msc_buf]));
-  if (hm.cap < b_cif + b_eti + b_sub && (rc = hm.reserve(full(b_cif + b_eti + b_sub)))) return rc;
+  if (hm.cap < b_cif + b_eti && (rc = hm.reserve(full(b_cif + b_eti)))) return rc;
   if (d_cifjobs.cap < b_cif + b_eti && (rc = d_cifjobs.reserve(full(b_cif + b_eti)))) return rc;
-  if (d_subjobs.cap < b_sub && (rc = d_subjobs.reserve(full(b_sub)))) return rc;
   if (d_steps_msc.cap < row_base + 64 && (rc = d_steps_msc.reserve(full(row_base + 64)))) return rc;
   vb_msc.reserve_scale = scale;
   if ((size_t)n_eti * DABGPU_ETI_BYTES > d_eti.cap) {
@@ -531,19 +562,14 @@ int Engine::flush_msc(cudaStream_t user) {
   memcpy(hp, cifjobs.data(), b_cif);
   memcpy(hp + b_cif, etijobs.data(), b_eti);
   if ((rc = launch_ctl_copy(d_cifjobs.p, hp, b_cif + b_eti, st))) return rc;
-  if (!reuse) {
-    memcpy(hp + b_cif + b_eti, subjobs.data(), b_sub);
-    if ((rc = launch_ctl_copy(d_subjobs.p, hp + b_cif + b_eti, b_sub, st))) return rc;
-  }
   CUDA_TRY(cudaEventRecord(ev_up[msc_buf], st));
   msc_buf ^= 1;
   const CifJob *dj = d_cifjobs.as<CifJob>();
-  const SubJob *ds = d_subjobs.as<SubJob>();
   const EtiJob *de = reinterpret_cast<const EtiJob *>(d_cifjobs.as<uint8_t>() + b_cif);
   host_us[H_JOBS] += now_us() - tw;
   t0(K_MSC_GATHER, st);
-  if ((rc = launch_msc_gather(d_cifs.as<uint8_t>(), dj, ds, d_shapes.as<ShapeDev>(), d_steps_msc.as<uint8_t>(),
-                              n_new, st)))
+  if ((rc = launch_msc_gather_periods(d_cifs.as<uint8_t>(), dj, d_periods.as<PeriodDesc>(),
+                                      d_steps_msc.as<uint8_t>(), n_new, st)))
     return rc;
   t1(K_MSC_GATHER, st);
   t0(K_MSC_VIT, st);

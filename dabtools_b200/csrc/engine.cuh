@@ -45,6 +45,7 @@ struct EnsLayout {
     uint32_t in_bit0, shape, nbits, row_off, eti_off;
   } sub[64];
   uint32_t rows_bytes = 0;  // step-byte rows of all sub-channels of one CIF
+  uint32_t per0 = 0, nper = 0;  // this layout's puncturing periods in the engine's period store
   uint32_t e1 = 0;          // header length
   EnsDev dev;
 };
@@ -79,6 +80,16 @@ struct Engine {
   std::vector<EnsLayout> layout;
   std::vector<StreamStats> stats;
 
+  // puncturing-period lists of the multiplex layouts seen so far (host copy mirrored in d_periods);
+  // streams with the same sub-channel table share one list
+  std::vector<PeriodDesc> periods;
+  struct LayoutKey {
+    std::vector<uint32_t> sig;  // (in_bit0, shape, row_off) per sub-channel
+    uint32_t per0, nper;
+  };
+  std::vector<LayoutKey> layout_keys;
+  bool periods_dirty = false;
+  DevBuf d_periods;
   // shapes seen so far (host list mirrored in d_shapes)
   std::vector<dabgpu_cw_shape> shapes;
   bool shapes_dirty = false;
@@ -156,7 +167,7 @@ struct Engine {
   uint64_t row_base = 0;
   std::vector<int32_t> pend_stream;
   std::vector<int> pend_of_stream;   // queued frames per stream
-  std::vector<uint32_t> frame_sub0;  // first SubJob of every frame of the cached job list
+  std::vector<uint64_t> frame_row;   // step-byte row base of every frame of the cached job list
   uint64_t pend_sig = 0xcbf29ce484222325ull, cached_sig = 0;
   int flush_msc(cudaStream_t st);
   VitBatch vb_fic, vb_msc;
@@ -193,7 +204,6 @@ struct Engine {
   // scratch vectors reused between steps
   std::vector<int> active;
   std::vector<CifJob> cifjobs;
-  std::vector<SubJob> subjobs;
   std::vector<EtiJob> etijobs;
 
   int init(int n_streams, uint32_t tuner_hz, int flags);

@@ -15,6 +15,7 @@ static uint16_t host_mulmod(uint16_t a, uint16_t b) {
   return (uint16_t)r;
 }
 
+int msc_init_dep_tables();
 int msc_init_constants() {
   CUDA_TRY(cudaMemcpyToSymbol(c_tdi_slot, DABGPU_TDI_DELAY, 16));
   uint16_t p[16];
@@ -24,7 +25,7 @@ int msc_init_constants() {
   p[0] = v;
   for (int j = 1; j < 16; j++) p[j] = host_mulmod(p[j - 1], p[j - 1]);
   CUDA_TRY(cudaMemcpyToSymbol(c_x8pow, p, sizeof p));
-  return DABGPU_OK;
+  return msc_init_dep_tables();
 }
 
 // ---- shared first half: 16 planes -> packed bits in logical order ---------------------------
@@ -117,6 +118,123 @@ __global__ void __launch_bounds__(256) msc_gather_kernel(const uint8_t *__restri
   }
 }
 
+// ---- the same with a per-layout period table -----------------------------------------------------
+// deposit tables for every puncturing vector: index pi (1..24) for whole periods, 32 + pi for the
+// 6-step tail region (only pi = 8 occurs)
+struct DepTab {
+  uint32_t n_terms, e_lo, e_hi, pad;
+  uint32_t shift[8];
+  uint32_t mask[8];
+};
+__device__ DepTab g_dep[64];
+
+static void make_dep(int pi, int steps, DepTab *d) {
+  memset(d, 0, sizeof *d);
+  uint32_t mask = dabgpu_puncture_mask(pi);
+  if (steps < 8) mask &= (1u << (4 * steps)) - 1u;
+  uint32_t taken = 0, nt = 0;
+  for (int k = 0; k < 8; k++) {
+    const uint32_t e = (mask >> (4 * k)) & 15u;
+    if (!e) continue;
+    const uint32_t shift = 4u * k - taken;  // punctured positions before step k
+    taken += (uint32_t)__builtin_popcount(e);
+    if (nt && d->shift[nt - 1] == shift) {
+      d->mask[nt - 1] |= e << (4 * k);
+    } else {
+      d->shift[nt] = shift;
+      d->mask[nt] = e << (4 * k);
+      nt++;
+    }
+  }
+  d->n_terms = nt;
+  auto spread = [](uint32_t v) {  // nibbles of the low 16 bits -> high nibbles of 4 bytes
+    v = (v | (v << 8)) & 0x00ff00ffu;
+    v = (v | (v << 4)) & 0x0f0f0f0fu;
+    return v << 4;
+  };
+  d->e_lo = spread(mask & 0xffffu);
+  d->e_hi = spread(mask >> 16);
+}
+
+int msc_init_dep_tables() {
+  DepTab t[64];
+  memset(t, 0, sizeof t);
+  for (int pi = 1; pi <= 24; pi++) {
+    make_dep(pi, 8, &t[pi]);
+    make_dep(pi, 6, &t[32 + pi]);
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(g_dep, t, sizeof t));
+  return DABGPU_OK;
+}
+
+bool append_periods(const dabgpu_cw_shape &sh, uint32_t in_bit0, uint32_t row_off, std::vector<PeriodDesc> &out) {
+  const uint32_t nsteps = (uint32_t)sh.nbits + 6u;
+  const uint32_t periods = vit_row_bytes(nsteps) >> 3;
+  for (uint32_t p = 0; p < periods; p++) {
+    const uint32_t t0 = p << 3;
+    PeriodDesc d;
+    d.row_off8 = (row_off >> 3) + p;
+    if (t0 >= nsteps) {
+      d.in_tab = 0xffu << 16;
+    } else {
+      int r = 0;
+      while (r + 1 < sh.n_regions && (int)t0 >= sh.r[r + 1].step0) r++;
+      const int pi = sh.r[r].pi, st = sh.r[r].steps;
+      if (pi < 1 || pi > 24 || (st < 8 && st != 6) || (st >= 8 && (st & 7))) return false;
+      const uint32_t in = in_bit0 + (uint32_t)sh.r[r].in0 + ((t0 - (uint32_t)sh.r[r].step0) >> 3) * (8u + (uint32_t)pi);
+      if (in >= 0x10000u) return false;
+      d.in_tab = in | (uint32_t)(st < 8 ? 32 + pi : pi) << 16;
+    }
+    out.push_back(d);
+  }
+  return true;
+}
+
+__global__ void __launch_bounds__(256) msc_gather_periods_kernel(const uint8_t *__restrict__ cifs,
+                                                                 const CifJob *__restrict__ jobs,
+                                                                 const PeriodDesc *__restrict__ periods,
+                                                                 uint8_t *__restrict__ steps) {
+  __shared__ uint32_t pl[16][CIF_PLANE_WORDS];
+  __shared__ uint32_t lin[CIF_WORDS + 1];
+  __shared__ CifJob job;
+  __shared__ DepTab dep[64];
+  if (threadIdx.x < sizeof(CifJob) / 4)
+    reinterpret_cast<uint32_t *>(&job)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&jobs[blockIdx.x])[threadIdx.x];
+  for (uint32_t i = threadIdx.x; i < sizeof(dep) / 4; i += blockDim.x)
+    reinterpret_cast<uint32_t *>(dep)[i] = reinterpret_cast<const uint32_t *>(g_dep)[i];
+  __syncthreads();
+  deinterleave_to_smem(cifs, job, pl, lin);
+  const uint2 *pd = reinterpret_cast<const uint2 *>(periods) + job.per0;
+  uint2 *dst = reinterpret_cast<uint2 *>(steps + job.row_base);
+  for (uint32_t p = threadIdx.x; p < job.nper; p += blockDim.x) {
+    const uint2 d = __ldg(pd + p);
+    const uint32_t idx = d.x >> 16, in = d.x & 0xffffu;
+    uint2 packed = make_uint2(0u, 0u);
+    if (idx != 0xffu) {
+      const DepTab &t = dep[idx];
+      const uint32_t wi = in >> 5;
+      // up to 32 consecutive channel bits starting at bit `in`
+      const uint32_t x = wi < CIF_WORDS ? __funnelshift_r(lin[wi], lin[wi + 1], in & 31u) : 0u;
+      uint32_t rn = 0;  // received bits as one nibble per step
+      for (uint32_t k = 0; k < t.n_terms; k++) rn |= (x << t.shift[k]) & t.mask[k];
+      uint32_t lo = rn & 0xffffu, hi = rn >> 16;
+      lo = (lo | (lo << 8)) & 0x00ff00ffu;
+      hi = (hi | (hi << 8)) & 0x00ff00ffu;
+      packed.x = ((lo | (lo << 4)) & 0x0f0f0f0fu) | t.e_lo;
+      packed.y = ((hi | (hi << 4)) & 0x0f0f0f0fu) | t.e_hi;
+    }
+    dst[d.y] = packed;
+  }
+}
+
+int launch_msc_gather_periods(const uint8_t *d_cifs, const CifJob *d_jobs, const PeriodDesc *d_periods,
+                              uint8_t *d_steps, int n_jobs, cudaStream_t st) {
+  if (n_jobs <= 0) return DABGPU_OK;
+  msc_gather_periods_kernel<<<n_jobs, 256, 0, st>>>(d_cifs, d_jobs, d_periods, d_steps);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
 int launch_msc_gather(const uint8_t *d_cifs, const CifJob *d_jobs, const SubJob *d_subs,
                       const ShapeDev *d_shapes, uint8_t *d_steps, int n_jobs, cudaStream_t st) {
   if (n_jobs <= 0) return DABGPU_OK;
@@ -194,8 +312,12 @@ __device__ __forceinline__ uint32_t crc_shift(uint32_t v, uint32_t nbytes) {
     if (nbytes & 1u) v = gf_mulmod(v, c_x8pow[j]);
   return v;
 }
+// byte-at-a-time CRC step with the 256-entry table T[b] = CRC register after byte b from 0
+__device__ __forceinline__ uint32_t crc_byte_tab(const uint16_t *tab, uint32_t crc, uint32_t byte) {
+  return ((crc << 8) & 0xffffu) ^ tab[(crc >> 8) ^ byte];
+}
 // CRC-16-CCITT (init 0xffff, no final xor) of n bytes (n % 4 == 0, p 4-byte aligned) by one warp
-__device__ uint32_t warp_crc16(const uint8_t *p, uint32_t n, int lane) {
+__device__ uint32_t warp_crc16(const uint16_t *tab, const uint8_t *p, uint32_t n, int lane) {
   const uint32_t words = n >> 2;
   const uint32_t per = (words + 31) / 32;
   const uint32_t w0 = min(words, per * lane), w1 = min(words, per * (lane + 1));
@@ -203,10 +325,10 @@ __device__ uint32_t warp_crc16(const uint8_t *p, uint32_t n, int lane) {
   const uint32_t *pw = reinterpret_cast<const uint32_t *>(p);
   for (uint32_t w = w0; w < w1; w++) {
     const uint32_t v = pw[w];
-    crc = crc_byte(crc, v & 0xffu);
-    crc = crc_byte(crc, (v >> 8) & 0xffu);
-    crc = crc_byte(crc, (v >> 16) & 0xffu);
-    crc = crc_byte(crc, v >> 24);
+    crc = crc_byte_tab(tab, crc, v & 0xffu);
+    crc = crc_byte_tab(tab, crc, (v >> 8) & 0xffu);
+    crc = crc_byte_tab(tab, crc, (v >> 16) & 0xffu);
+    crc = crc_byte_tab(tab, crc, v >> 24);
   }
   uint32_t part = crc_shift(crc, 4 * (words - w1));
   if (lane == 0) part ^= crc_shift(0xffffu, n);
@@ -219,6 +341,9 @@ __global__ void __launch_bounds__(128) eti_pack_kernel(const EtiJob *__restrict_
                                                        const EnsDev *__restrict__ ens,
                                                        const uint8_t *__restrict__ fibs,
                                                        uint8_t *__restrict__ eti_all, int n_frames) {
+  __shared__ uint16_t crc_tab[256];
+  for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) crc_tab[b] = (uint16_t)crc_byte(0u, b);
+  __syncthreads();
   const int lane = threadIdx.x & 31;
   const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (f >= n_frames) return;
@@ -249,7 +374,7 @@ __global__ void __launch_bounds__(128) eti_pack_kernel(const EtiJob *__restrict_
     eti[eoh] = 0xff;
     eti[eoh + 1] = 0xff;
     uint32_t crc = 0xffffu;
-    for (uint32_t i = 4; i < eoh + 2; i++) crc = crc_byte(crc, eti[i]);
+    for (uint32_t i = 4; i < eoh + 2; i++) crc = crc_byte_tab(crc_tab, crc, eti[i]);
     crc = ~crc & 0xffffu;
     eti[eoh + 2] = (uint8_t)(crc >> 8);
     eti[eoh + 3] = (uint8_t)(crc & 0xffu);
@@ -261,7 +386,7 @@ __global__ void __launch_bounds__(128) eti_pack_kernel(const EtiJob *__restrict_
   __syncwarp();
   // EOF: CRC over MST = FIC + sub-channel payload (misc.c:280-296)
   const uint32_t mst = 96 + en->payload;
-  uint32_t crc = ~warp_crc16(eti + e1, mst, lane) & 0xffffu;
+  uint32_t crc = ~warp_crc16(crc_tab, eti + e1, mst, lane) & 0xffffu;
   uint32_t e = e1 + mst;
   if (lane == 0) {
     eti[e] = (uint8_t)(crc >> 8);

@@ -8,6 +8,8 @@
 // words = 6912 bytes, and de-interleaving one logical frame is 16 contiguous 432-byte
 // reads, one plane from each of the 16 window slots.
 #pragma once
+#include <vector>
+
 #include "viterbi.cuh"
 
 namespace dabgpu {
@@ -17,8 +19,22 @@ enum { CIF_PLANE_WORDS = 108, CIF_WORDS = 16 * 108, CIF_BYTES = 6912 };
 // one logical (output) CIF to de-interleave and turn into Viterbi step bytes
 struct CifJob {
   uint64_t slot_off[16];  // byte offsets of the 16 window CIFs (slot 0 = oldest) in the CIF store
-  uint32_t sub0, nsub;    // range in the SubJob array
+  uint32_t sub0, nsub;    // range in the SubJob array (launch_msc_gather)
+  uint64_t row_base;      // step-byte rows of this CIF start here (launch_msc_gather_periods)
+  uint32_t per0, nper;    // range in the PeriodDesc array
 };
+// One puncturing period (8 trellis steps -> 8 step bytes) of a multiplex layout.  A layout's
+// periods depend only on its sub-channel table, so the list is built once per layout on the host
+// and shared by every CIF (and every stream) that uses the layout.
+struct PeriodDesc {
+  uint32_t in_tab;    // first channel bit of the period | deposit table index << 16 (0xff: padding, all zero)
+  uint32_t row_off8;  // byte offset of the 8 step bytes relative to CifJob::row_base, divided by 8
+};
+// append the periods of one sub-channel codeword (uep/eep_depuncture, depuncture.c:84-132);
+// returns false for a puncturing layout outside EN 300 401 (no deposit table)
+bool append_periods(const dabgpu_cw_shape &shape, uint32_t in_bit0, uint32_t row_off, std::vector<PeriodDesc> &out);
+int launch_msc_gather_periods(const uint8_t *d_cifs, const CifJob *d_jobs, const PeriodDesc *d_periods,
+                              uint8_t *d_steps, int n_jobs, cudaStream_t st);
 struct SubJob {
   uint64_t row_off;   // step-byte row of this codeword (16-byte aligned)
   uint32_t in_bit0;   // first channel bit of the sub-channel inside the CIF (start_cu * 64)
