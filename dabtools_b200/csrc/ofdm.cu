@@ -315,7 +315,23 @@ __device__ __forceinline__ void load_twiddles(FftTwiddles &tw, int p) {
   }
 }
 
-__device__ __forceinline__ void fft2048_from_regs(float2 *v, const FftTwiddles &tw, float2 *xch, int p) {
+// the same twiddles fetched from the table when they are needed (two FFTs per frame in the
+// synchroniser: registers matter more than 30 cached loads)
+struct FftTwiddlesMem {
+  int t, u16;
+  struct Row {
+    const FftTwiddlesMem &o;
+    bool second;
+    __device__ __forceinline__ float2 operator[](int km1) const {
+      return g_tw2048[((second ? o.u16 : o.t) * (km1 + 1)) & 2047];
+    }
+  };
+  Row s1{*this, false}, s2{*this, true};
+  __device__ __forceinline__ explicit FftTwiddlesMem(int p) : t(p), u16(16 * (p >> 4)) {}
+};
+
+template <typename Tw>
+__device__ __forceinline__ void fft2048_from_regs(float2 *v, const Tw &tw, float2 *xch, int p) {
   // stage 1 (v = x[p + 128 j])
   dft16(v);
 #pragma unroll
@@ -663,10 +679,22 @@ __device__ void warp_ifft128(float2 *d, int lane) {
   }
 }
 
+#ifndef SYNC_CTAS_PER_SM
+#define SYNC_CTAS_PER_SM 7   // 1024 streams in one wave on 148 SMs; needs <= 72 registers and < 31.5 KB
+#endif
+enum { SPEC_GAP0 = 784, SPEC_GAP1 = 1280, SPEC_SLOTS = 2048 - (SPEC_GAP1 - SPEC_GAP0) };
+// slot of FFT bin `bin` in SyncSmem::spec, -1 for the unused bins between the two carrier blocks
+__device__ __forceinline__ int spec_slot(int bin) {
+  return bin < SPEC_GAP0 ? bin : (bin >= SPEC_GAP1 ? bin - (SPEC_GAP1 - SPEC_GAP0) : -1);
+}
 struct SyncSmem {
-  float2 xch[XCH_ELEMS];
-  float2 spec[2048];   // FFT output in natural bin order
-  float2 work[1536];   // correlation buffers
+  union {              // never live at the same time:
+    float2 xch[XCH_ELEMS];  // FFT exchange buffer (inside fft_window)
+    float2 work[1536];      // correlation buffers (between the FFTs)
+  };
+  // FFT output by bin, without the bins nobody reads: the carriers are bins 1..768 and 1280..2047
+  // (fine time sync reads 3..770 and 1280..2047, the coarse frequency search 1280..1435)
+  float2 spec[SPEC_SLOTS];
   float red_v[FFT_THREADS];
   int red_i[FFT_THREADS];
 };
@@ -776,15 +804,18 @@ __device__ int coarse_time_sync(SyncSmem &sm, const Src &src, bool force, float 
 }
 
 // FFT of the 2048 samples starting at `start` into sm.spec (natural bin order)
-template <typename Src>
-__device__ void fft_window(SyncSmem &sm, const Src &src, int start, const FftTwiddles &tw) {
+template <typename Src, typename Tw>
+__device__ void fft_window(SyncSmem &sm, const Src &src, int start, const Tw &tw) {
   const int p = threadIdx.x;
   float2 v[16];
 #pragma unroll
   for (int j = 0; j < 16; j++) v[j] = src.at(start + p + 128 * j);
   fft2048_from_regs(v, tw, sm.xch, p);
 #pragma unroll
-  for (int m = 0; m < 16; m++) sm.spec[p + 128 * m] = v[m];
+  for (int m = 0; m < 16; m++) {
+    const int slot = spec_slot(p + 128 * m);
+    if (slot >= 0) sm.spec[slot] = v[m];
+  }
   __syncthreads();
 }
 
@@ -794,7 +825,7 @@ __device__ int fine_time_from_spec(SyncSmem &sm) {
   const int p = threadIdx.x;
   for (int i = p; i < 1536; i += FFT_THREADS) {
     const int bin = i < 768 ? i + 1280 : i - 765;  // sic: off by two in the upper half
-    sm.work[(i % 3) * 512 + i / 3] = cmulc(sm.spec[bin], prs_value(i));
+    sm.work[(i % 3) * 512 + i / 3] = cmulc(sm.spec[spec_slot(bin)], prs_value(i));
   }
   __syncthreads();
   block_fft_pow2(sm.work, 9, +1, 3);
@@ -831,7 +862,7 @@ __device__ int coarse_freq_from_spec(SyncSmem &sm) {
   int best_k = 99;
   for (int k = -14 + warp; k <= 14; k += 4) {
     for (int s = lane; s < 128; s += 32)
-      buf[s] = cmulc(sm.spec[(14 + k + 256 + s + 1024) & 2047], prs_value(14 + s));
+      buf[s] = cmulc(sm.spec[spec_slot((14 + k + 256 + s + 1024) & 2047)], prs_value(14 + s));
     __syncwarp();
     warp_ifft128(buf, lane);
     float mag = -99999.f;
@@ -869,8 +900,7 @@ __device__ void sync_frame(SyncSmem &sm, const Src &src, bool force, SyncOut &r)
   r.stage = 1;
   r.coarse_timeshift = coarse_time_sync(sm, src, force, &r.null_energy);
   if (r.coarse_timeshift != 0) return;
-  FftTwiddles tw;
-  load_twiddles(tw, threadIdx.x);
+  const FftTwiddlesMem tw(threadIdx.x);
   fft_window(sm, src, 2656 + 504, tw);
   r.fine_timeshift = fine_time_from_spec(sm);
   // input_sdr.c:91: the reference indexes the frame with the *byte* shift here
@@ -884,7 +914,7 @@ __device__ void sync_frame(SyncSmem &sm, const Src &src, bool force, SyncOut &r)
 }
 
 // ... for every stream with ctl.run
-__global__ void __launch_bounds__(FFT_THREADS) sync_kernel(RingGeom ring, const uint8_t *__restrict__ tails,
+__global__ void __launch_bounds__(FFT_THREADS, SYNC_CTAS_PER_SM) sync_kernel(RingGeom ring, const uint8_t *__restrict__ tails,
                                                            const uint8_t *__restrict__ frames,
                                                            const StepCtl *__restrict__ ctl,
                                                            SyncOut *__restrict__ out) {
@@ -939,7 +969,10 @@ __global__ void __launch_bounds__(FFT_THREADS) sync_single_kernel(int mode, cons
     r = fine_time_from_spec(sm);
   } else if (mode == 2) {
     const float2 *sh = (const float2 *)in;
-    for (int i = p; i < 2048; i += FFT_THREADS) sm.spec[(i + 1024) & 2047] = sh[i];
+    for (int i = p; i < 2048; i += FFT_THREADS) {
+      const int slot = spec_slot((i + 1024) & 2047);
+      if (slot >= 0) sm.spec[slot] = sh[i];
+    }
     __syncthreads();
     r = coarse_freq_from_spec(sm);
   } else {
