@@ -152,6 +152,15 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   return DABGPU_OK;
 }
 
+// Small control transfers between pinned host memory and the device.  While bulk sample uploads or
+// ETI downloads are using the copy engines (host-buffer path) they go by a zero-copy kernel, so
+// that they do not queue behind a 268 MB copy; otherwise the copy engines are the cheaper way.
+int Engine::ctl_transfer(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st) {
+  if (bulk_copies) return launch_ctl_copy(dst, src, bytes, st);
+  if (bytes) CUDA_TRY(cudaMemcpyAsync(dst, src, bytes, kind, st));
+  return DABGPU_OK;
+}
+
 int Engine::enable_timing(bool on) {
   if (on && !ev[0][0])
     for (int k = 0; k < K_COUNT; k++)
@@ -364,7 +373,7 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
       vb_fic.add(((uint64_t)a * 4 + k) * FIC_ROW, (uint64_t)a * FIBS_PER_TF + 96 * k, 768, VIT_DESCRAMBLE);
   }
   if ((rc = d_gather_idx.reserve((size_t)S * 12 + 8))) return rc;
-  if ((rc = launch_ctl_copy(d_gather_idx.p, h_jobs.p, idx_bytes + (size_t)na * 8, st))) return rc;
+  if ((rc = ctl_transfer(d_gather_idx.p, h_jobs.p, idx_bytes + (size_t)na * 8, cudaMemcpyHostToDevice, st))) return rc;
   const uint32_t *d_idx = d_gather_idx.as<uint32_t>();
   const uint64_t *d_dst = reinterpret_cast<const uint64_t *>(d_gather_idx.as<uint8_t>() + idx_bytes);
   t0(K_FIC_PREP, st);
@@ -378,7 +387,7 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
   trellis_steps += vb_fic.total_steps;
   if ((rc = launch_fib_crc(d_fib_c, d_crc_c, 12 * na, st))) return rc;
   if ((rc = launch_scatter_rows(d_fib_c, FIBS_PER_TF, d_dst, d_fibs.as<uint8_t>(), na, st))) return rc;
-  if ((rc = launch_ctl_copy(h_fic_out[fic_buf].p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), st))) return rc;
+  if ((rc = ctl_transfer(h_fic_out[fic_buf].p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), cudaMemcpyDeviceToHost, st))) return rc;
   return DABGPU_OK;
 }
 
@@ -561,7 +570,7 @@ int Engine::flush_msc(cudaStream_t user) {
   uint8_t *hp = hm.as<uint8_t>();
   memcpy(hp, cifjobs.data(), b_cif);
   memcpy(hp + b_cif, etijobs.data(), b_eti);
-  if ((rc = launch_ctl_copy(d_cifjobs.p, hp, b_cif + b_eti, st))) return rc;
+  if ((rc = ctl_transfer(d_cifjobs.p, hp, b_cif + b_eti, cudaMemcpyHostToDevice, st))) return rc;
   CUDA_TRY(cudaEventRecord(ev_up[msc_buf], st));
   msc_buf ^= 1;
   const CifJob *dj = d_cifjobs.as<CifJob>();
@@ -688,6 +697,7 @@ int Engine::submit_iq(const uint8_t *iq, size_t pitch, int chunk_len) {
     set_error(DABGPU_ERR_STATE, "submit_iq: %d chunks are already queued; call dabgpu_engine_feed_submitted", N_STAGE);
     return DABGPU_ERR_STATE;
   }
+  bulk_copies = true;
   const int b = (stage_head + stage_count) % N_STAGE;
   if ((rc = d_stage[b].reserve((size_t)S * 262144))) return rc;
   // the buffer is free once the ingest kernel that read it last has run
@@ -859,7 +869,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     fr.pending = true;
     active.push_back(s);
   }
-  if ((rc = launch_ctl_copy(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), st))) return rc;
+  if ((rc = ctl_transfer(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), cudaMemcpyHostToDevice, st))) return rc;
   CUDA_TRY(cudaEventRecord(ev_ctl[ctl_buf], st));
   ctl_buf ^= 1;
   host_us[H_PRE] += now_us() - t_pre;
@@ -912,7 +922,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       CUDA_TRY(cudaEventRecord(ev_demod_done[demod_ev], st));
       // (when kernels are being timed, each one runs alone: the FIC chain starts after the CIFs)
       CUDA_TRY(cudaStreamWaitEvent(st_fic, timing ? ev_demod_done[demod_ev] : ev_fic_ready, 0));
-      if ((rc = launch_ctl_copy(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), st_fic))) return rc;
+      if ((rc = ctl_transfer(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st_fic))) return rc;
       if ((rc = fic_launch(st_fic, d_ficbits.as<uint8_t>(), 9216))) return rc;
       launched = true;
     }
@@ -978,6 +988,7 @@ DABGPU_EXPORT int dabgpu_engine_fetch_eti(dabgpu_engine *h, uint8_t *eti, int32_
   if (n <= 0) return 0;
   cudaStream_t st = e.st_msc;
   if (eti) {
+    if ((size_t)n * DABGPU_ETI_BYTES > (4u << 20)) e.bulk_copies = true;  // see Engine::ctl_transfer
     cudaError_t err = cudaMemcpyAsync(eti, e.d_eti.p, (size_t)n * DABGPU_ETI_BYTES, cudaMemcpyDeviceToHost, st);
     if (err == cudaSuccess) err = cudaStreamSynchronize(st);
     if (err != cudaSuccess) {

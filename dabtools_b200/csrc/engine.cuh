@@ -133,6 +133,8 @@ struct Engine {
   int consuming_stage = -1;
   int submit_iq(const uint8_t *iq, size_t pitch, int chunk_len);
   int feed_submitted();
+  bool bulk_copies = false;  // host-buffer path in use: the copy engines carry bulk transfers
+  int ctl_transfer(void *dst, const void *src, size_t bytes, cudaMemcpyKind kind, cudaStream_t st);
   // zero-copy source: one contiguous device-resident capture per stream, consumed in place
   RingGeom rg = {nullptr, 0, IQ_RING_BYTES};
   const uint8_t *capture_base = nullptr;
