@@ -36,9 +36,10 @@ __host__ __device__ static inline uint64_t vit_group_dec_words(uint32_t nsteps) 
 }
 __host__ __device__ static inline uint32_t vit_row_bytes(uint32_t nsteps) { return (nsteps + 15u) & ~15u; }
 
-// warps per persistent CTA (one CTA per SM): 4 schedulers x 3 concurrent work lists
+// warps per persistent CTA (one CTA per SM): 4 schedulers x 4 concurrent work lists; at 127
+// registers per thread the CTA takes the whole register file (measured: 16 warps 2 % faster than 12)
 #ifndef DABGPU_VIT_WARPS
-#define DABGPU_VIT_WARPS 12
+#define DABGPU_VIT_WARPS 16
 #endif
 enum { VIT_WARPS = DABGPU_VIT_WARPS };
 int device_sm_count();
