@@ -567,6 +567,7 @@ def run_ours(args, rank, world, local_rank):
             "peak": hbm_peak,
             "unit": "GB/s",
             "frac": achieved / hbm_peak,
+            "frac_of_nominal_8tbs": achieved / 8000.0,
             # demod is launched as two grids per frame (FIC symbols, CIF symbols): both together
             "traffic": ncu_traffic("demod_kernel"),
             "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",

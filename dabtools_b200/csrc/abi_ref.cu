@@ -103,6 +103,12 @@ DABGPU_EXPORT int init_viterbi(void) {
   if (ensure_device_ready()) report("init_viterbi");
   return 0;
 }
+DABGPU_EXPORT void *create_viterbi(int len) {  // viterbi_spiral.c:163, for -DENABLE_SPIRAL_VITERBI callers
+  (void)len;
+  static int handle;
+  init_viterbi();
+  return &handle;
+}
 DABGPU_EXPORT int viterbi(void *p, unsigned char *symbols, unsigned char *data, unsigned int framebits) {
   (void)p;
   if (!data) return 0;  // viterbi.c:437-438

@@ -149,6 +149,10 @@ void fic_depuncture(uint8_t *obuf, uint8_t *inbuf);
 void uep_depuncture(uint8_t *obuf, uint8_t *inbuf, struct subchannel_info_t *s, int *len);
 void eep_depuncture(uint8_t *obuf, uint8_t *inbuf, struct subchannel_info_t *s, int *len);
 int init_viterbi(void);
+/* viterbi_spiral.h:22: what dab.c:27-30 calls instead of init_viterbi() when the reference is built
+ * with -DENABLE_SPIRAL_VITERBI.  Returns an opaque non-null handle; the decoder behind viterbi() is
+ * the same (plain viterbi.c tie-breaking, the alphabet of either to_viterbi() variant is accepted) */
+void *create_viterbi(int len);
 /* viterbi.h:8 declares void, viterbi.c:352 defines int(...unsigned); int is ABI-compatible */
 int viterbi(void *p, unsigned char *symbols, unsigned char *data, unsigned int framebits);
 void dab_descramble_bytes(uint8_t *buf, int32_t nbytes);
