@@ -1,5 +1,6 @@
 // api_batch.cu -- stateless batched entry points of include/dabgpu.h.
 #include "../../include/dabgpu.h"
+#include "msc.cuh"
 #include "ofdm.cuh"
 #include "vitbatch.cuh"
 
@@ -42,6 +43,24 @@ DABGPU_EXPORT int dabgpu_tab_shape(int kind, int a, int b, int32_t *out23) {
   static_assert(sizeof(sh) == 23 * sizeof(int32_t), "shape layout");
   memcpy(out23, &sh, sizeof sh);
   return DABGPU_OK;
+}
+// host-only: the step bytes the MSC gather produces for one sub-channel of a de-interleaved CIF
+DABGPU_EXPORT int dabgpu_tab_depuncture_steps(int kind, int a, int b, int start_cu, const uint8_t *cif_bits55296,
+                                              uint8_t *steps, int steps_cap) {
+  dabgpu_cw_shape sh;
+  int32_t raw[23];
+  if (dabgpu_tab_shape(kind, a, b, raw)) return DABGPU_ERR_ARG;
+  memcpy(&sh, raw, sizeof sh);
+  const int need = (int)vit_row_bytes((uint32_t)sh.nbits + 6u);
+  if (steps_cap < need || start_cu < 0 || start_cu * 64 + sh.in_bits > DABGPU_CIF_BITS) {
+    set_error(DABGPU_ERR_ARG, "dabgpu_tab_depuncture_steps: buffer too small or sub-channel outside the CIF");
+    return DABGPU_ERR_ARG;
+  }
+  if (!host_periods_to_steps(sh, (uint32_t)start_cu * 64u, cif_bits55296, steps)) {
+    set_error(DABGPU_ERR_ARG, "dabgpu_tab_depuncture_steps: puncturing outside EN 300 401");
+    return DABGPU_ERR_ARG;
+  }
+  return need;
 }
 DABGPU_EXPORT void dabgpu_tab_uep(int32_t *o) {
   for (int i = 0; i < 64; i++) {

@@ -190,6 +190,36 @@ bool append_periods(const dabgpu_cw_shape &sh, uint32_t in_bit0, uint32_t row_of
   return true;
 }
 
+// Host restatement of what one CIF's worth of msc_gather_periods_kernel threads do with these
+// tables (for the CPU-side tests of append_periods / make_dep; not used by the product path).
+// bits: the de-interleaved CIF, one byte per channel bit; steps: nsteps padded to 16 step bytes.
+bool host_periods_to_steps(const dabgpu_cw_shape &shape, uint32_t in_bit0, const uint8_t *bits, uint8_t *steps) {
+  std::vector<PeriodDesc> per;
+  if (!append_periods(shape, in_bit0, 0, per)) return false;
+  for (const PeriodDesc &d : per) {
+    const uint32_t idx = d.in_tab >> 16, in = d.in_tab & 0xffffu;
+    uint32_t lo = 0, hi = 0;
+    if (idx != 0xffu) {
+      DepTab t;
+      make_dep((int)(idx & 31u), idx >= 32 ? 6 : 8, &t);
+      uint32_t x = 0;
+      for (int b = 0; b < 32; b++)
+        if (in + b < DABGPU_CIF_BITS) x |= (uint32_t)(bits[in + b] & 1u) << b;
+      uint32_t rn = 0;
+      for (uint32_t k = 0; k < t.n_terms; k++) rn |= (x << t.shift[k]) & t.mask[k];
+      lo = rn & 0xffffu;
+      hi = rn >> 16;
+      lo = (lo | (lo << 8)) & 0x00ff00ffu;
+      hi = (hi | (hi << 8)) & 0x00ff00ffu;
+      lo = ((lo | (lo << 4)) & 0x0f0f0f0fu) | t.e_lo;
+      hi = ((hi | (hi << 4)) & 0x0f0f0f0fu) | t.e_hi;
+    }
+    memcpy(steps + 8ull * d.row_off8, &lo, 4);
+    memcpy(steps + 8ull * d.row_off8 + 4, &hi, 4);
+  }
+  return true;
+}
+
 __global__ void __launch_bounds__(256) msc_gather_periods_kernel(const uint8_t *__restrict__ cifs,
                                                                  const CifJob *__restrict__ jobs,
                                                                  const PeriodDesc *__restrict__ periods,

@@ -33,6 +33,8 @@ struct PeriodDesc {
 // append the periods of one sub-channel codeword (uep/eep_depuncture, depuncture.c:84-132);
 // returns false for a puncturing layout outside EN 300 401 (no deposit table)
 bool append_periods(const dabgpu_cw_shape &shape, uint32_t in_bit0, uint32_t row_off, std::vector<PeriodDesc> &out);
+bool host_periods_to_steps(const dabgpu_cw_shape &shape, uint32_t in_bit0, const uint8_t *bits55296,
+                           uint8_t *steps);
 int launch_msc_gather_periods(const uint8_t *d_cifs, const CifJob *d_jobs, const PeriodDesc *d_periods,
                               uint8_t *d_steps, int n_jobs, cudaStream_t st);
 struct SubJob {

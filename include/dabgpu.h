@@ -50,6 +50,12 @@ int dabgpu_synchronize(void);
 int dabgpu_tab_shape(int kind, int a, int b, int32_t *out23);
 /* 64 rows x {bitrate, size_cu, prot_level, L1..L4, PI1..PI4, pad_bits} */
 void dabgpu_tab_uep(int32_t *out64x12);
+/* Host-only (no GPU needed): the Viterbi step bytes (see csrc/viterbi.cuh) that the MSC gather
+ * derives for one sub-channel (kind/a/b as in dabgpu_tab_shape, first capacity unit start_cu) from
+ * a de-interleaved CIF given as 55296 bytes of 0/1 -- uep/eep_depuncture (depuncture.c:84-132) in
+ * the library's input format.  Returns the number of step bytes written, or a negative error. */
+int dabgpu_tab_depuncture_steps(int kind, int a, int b, int start_cu, const uint8_t *cif_bits55296,
+                                uint8_t *steps, int steps_cap);
 uint32_t dabgpu_tab_puncture_mask(int pi);
 void dabgpu_tab_freq_deint(uint16_t *rev1536);   /* rev_freq_deint_tab, dab_tables.c:164-357 */
 void dabgpu_tab_prs(uint8_t *quarter_turns1536); /* prs_static, sdr_prstab.c */

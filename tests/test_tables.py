@@ -60,3 +60,41 @@ def test_glibc_rand_port(port):
         libc.srand(seed)
         want = [libc.rand() for _ in range(50)]
         assert port.rand_sequence(seed, 50) == want
+
+
+def _steps_from_soft(soft):
+    """the reference depuncturer's output (4 soft symbols per trellis step, 127/128/129) in the
+    library's step-byte format: low nibble received bits, high nibble "symbol was transmitted" """
+    v = soft.reshape(-1, 4)
+    r = ((v > 128).astype(np.uint8) << np.arange(4, dtype=np.uint8)).sum(axis=1)
+    e = ((v != 128).astype(np.uint8) << np.arange(4, 8, dtype=np.uint8)).sum(axis=1)
+    return (r | e).astype(np.uint8)
+
+
+def test_gather_period_tables_match_the_reference_depuncturers(port):
+    """Host half of msc_gather_periods_kernel (period lists + deposit tables, run on the CPU through
+    dabgpu_tab_depuncture_steps) against uep_depuncture / eep_depuncture for every profile."""
+    import ctypes as C
+    from dabtools_b200 import lib
+    L = lib.load()
+    L.dabgpu_tab_depuncture_steps.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_int]
+    rng = np.random.default_rng(8)
+    cases = [(1, i, 0, T.UEP[i][1]) for i in range(64)]
+    cases += [(2, lv, sz, sz) for lv, sz in [(0, 12), (0, 96), (1, 8), (1, 64), (2, 6), (2, 90), (3, 4), (3, 40),
+                                             (4, 27), (4, 54), (5, 21), (5, 84), (6, 18), (6, 72), (7, 15), (7, 30)]]
+    for kind, a, b, size_cu in cases:
+        sh = T.shape_uep(a) if kind == 1 else T.shape_eep(a, b)
+        start_cu = int(rng.integers(0, 864 - size_cu + 1))
+        cif = rng.integers(0, 2, 55296, dtype=np.uint8)
+        steps = np.full(((sh["nbits"] + 6 + 15) // 16) * 16, 0xEE, dtype=np.uint8)
+        n = L.dabgpu_tab_depuncture_steps(kind, a, b, start_cu, cif.ctypes.data, steps.ctypes.data, steps.size)
+        assert n == steps.size, (kind, a, b, n)
+        sub = cif[64 * start_cu:]
+        if kind == 1:
+            soft = port.uep_depuncture(sub, a)
+        else:
+            soft = port.eep_depuncture(sub, a, b, sh["nbits"] // 24)
+        want = _steps_from_soft(soft)
+        assert want.size == sh["nbits"] + 6
+        assert np.array_equal(steps[:want.size], want), (kind, a, b)
+        assert not steps[want.size:].any()          # row padding is "nothing transmitted"
