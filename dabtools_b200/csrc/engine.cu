@@ -89,6 +89,7 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
     return DABGPU_ERR_ARG;
   }
   S = n_streams;
+  trace_on = getenv("DABGPU_TRACE") != nullptr;
   f0 = tuner_hz;
   quiet = !(flags & DABGPU_ENGINE_VERBOSE);
   virtual_tuner = flags & DABGPU_ENGINE_VIRTUAL_TUNER;
@@ -161,6 +162,49 @@ int Engine::ctl_transfer(void *dst, const void *src, size_t bytes, cudaMemcpyKin
   return DABGPU_OK;
 }
 
+void Engine::trace_mark(int k, int which, cudaStream_t st) {
+  if (trace.size() > 20000) return;
+  if (!trace_base) {
+    cudaEventCreate(&trace_base);
+    cudaEventRecord(trace_base, st);
+  }
+  if (which == 0) {
+    TraceRec r;
+    r.k = k;
+    r.host_us = now_us();
+    cudaEventCreate(&r.e[0]);
+    cudaEventCreate(&r.e[1]);
+    cudaEventRecord(r.e[0], st);
+    trace.push_back(r);
+  } else {
+    for (size_t i = trace.size(); i-- > 0;)
+      if (trace[i].k == k) {
+        cudaEventRecord(trace[i].e[1], st);
+        break;
+      }
+  }
+}
+void Engine::trace_dump() {
+  const char *path = getenv("DABGPU_TRACE");
+  if (!path || trace.empty()) return;
+  cudaDeviceSynchronize();
+  FILE *f = fopen(path, "w");
+  if (!f) return;
+  static const char *names[K_COUNT] = {"ingest", "fifo", "sync", "demod", "fic_prep", "fic_viterbi",
+                                       "msc_gather", "msc_viterbi", "eti_pack"};
+  const double h0 = trace[0].host_us;
+  for (const TraceRec &r : trace) {
+    float a = 0, b = 0;
+    if (cudaEventElapsedTime(&a, trace_base, r.e[0]) != cudaSuccess ||
+        cudaEventElapsedTime(&b, trace_base, r.e[1]) != cudaSuccess) {
+      cudaGetLastError();
+      continue;
+    }
+    fprintf(f, "%-12s %10.4f %10.4f   launched_at_host_ms %10.4f\n", names[r.k], a, b, (r.host_us - h0) / 1e3);
+  }
+  fclose(f);
+}
+
 int Engine::enable_timing(bool on) {
   if (on && !ev[0][0])
     for (int k = 0; k < K_COUNT; k++)
@@ -198,6 +242,12 @@ int Engine::join_msc(cudaStream_t user) {
 }
 
 void Engine::destroy() {
+  trace_dump();
+  for (TraceRec &r : trace) {
+    cudaEventDestroy(r.e[0]);
+    cudaEventDestroy(r.e[1]);
+  }
+  trace.clear();
   pool.stop();
   if (st_fic) {
     cudaStreamSynchronize(st_fic);
@@ -499,7 +549,13 @@ int Engine::backend_host(cudaStream_t st) {
     if (lag.demod_ev >= 0) msc_wait_ev = lag.demod_ev;  // the newest CIFs these frames reference
   }
   host_us[H_JOBS] += now_us() - tw;
-  if (pend_calls >= msc_batch) return flush_msc(st);
+  if (pend_calls >= msc_batch) {
+    // An MSC batch is best queued right before a stretch in which no front-end kernels will be:
+    // it then fills what would be an idle GPU while the host turns around.  If the next callback is
+    // expected to complete frames again, the batch may wait for one more transmission frame.
+    const bool hold = hold_msc_hint && pend_calls < std::min<int>(msc_batch + 1, MAX_MSC_BATCH);
+    if (!hold) return flush_msc(st);
+  }
   return DABGPU_OK;
 }
 
@@ -623,6 +679,7 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
   const int na = (int)active.size();
   n_eti = 0;
   eti_stream.clear();
+  hold_msc_hint = false;
   if ((rc = backend_host(st))) return rc;  // a frame left over from a feed_iq call comes first
   if (!na) return DABGPU_OK;
   for (int s : active) take_slot(s);
@@ -869,6 +926,12 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
     fr.pending = true;
     active.push_back(s);
   }
+  {
+    // will the next callback (same size) complete frames?  (input_sdr.c:41-43)
+    int next_frames = 0;
+    for (int s = 0; s < S; s++) next_frames += front[s].fifo_count + (uint32_t)chunk_len >= 196608u * 3u;
+    hold_msc_hint = trailing_hint_enabled() && 2 * next_frames >= S;
+  }
   if ((rc = ctl_transfer(d_ctl.p, ctl, (size_t)S * sizeof(StepCtl), cudaMemcpyHostToDevice, st))) return rc;
   CUDA_TRY(cudaEventRecord(ev_ctl[ctl_buf], st));
   ctl_buf ^= 1;
@@ -927,7 +990,9 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       launched = true;
     }
   }
-  if ((rc = backend_host(st))) return rc;  // the previous frame's, overlapping the kernels above
+  // The previous frame's dab_process_frame runs here, while the kernels queued above execute.  A
+  // callback that completed no frame has queued nothing to hide it behind: leave it for the next one.
+  if ((launched || !trailing) && (rc = backend_host(st))) return rc;
   if (launched) {
     if ((rc = fic_finish(st_fic, h_sync.as<SyncOut>(), demod_ev))) return rc;
     if (!trailing && (rc = backend_host(st))) return rc;
@@ -1055,6 +1120,7 @@ DABGPU_EXPORT int dabgpu_engine_set_msc_batch(dabgpu_engine *h, int calls) {
 DABGPU_EXPORT int dabgpu_engine_flush(dabgpu_engine *h) {
   h->e.n_eti = 0;
   h->e.eti_stream.clear();
+  h->e.hold_msc_hint = false;
   int rc = h->e.backend_host(current_stream());  // a frame whose host logic is still outstanding
   if (rc) return rc;
   rc = h->e.flush_msc(current_stream());

@@ -163,6 +163,8 @@ struct Engine {
     return frame_slot[s] = slot;
   }
   int backend_host(cudaStream_t st);
+  bool hold_msc_hint = false;  // feed_iq: the next callback is expected to complete frames again
+  bool trailing_hint_enabled() const { return msc_batch > 1 && msc_batch < MAX_MSC_BATCH && !timing; }
   // MSC decoding may lag by up to msc_batch calls so that one Viterbi launch covers several
   // transmission frames per stream (more, better balanced work per launch)
   int msc_batch = 1, pend_calls = 0;
@@ -185,13 +187,27 @@ struct Engine {
     if (timing) {
       cudaEventRecord(ev[k][0], st);
     }
+    if (trace_on) trace_mark(k, 0, st);
   }
   void t1(int k, cudaStream_t st) {
     if (timing) {
       cudaEventRecord(ev[k][1], st);
       ev_used[k] = true;
     }
+    if (trace_on) trace_mark(k, 1, st);
   }
+  // development aid (DABGPU_TRACE=<file>): GPU timeline of the kernels above without serialising
+  // anything -- one event pair per launch, dumped as "kernel start_ms end_ms" when the engine dies
+  struct TraceRec {
+    int k;
+    cudaEvent_t e[2];
+    double host_us;
+  };
+  bool trace_on = false;
+  std::vector<TraceRec> trace;
+  cudaEvent_t trace_base = nullptr;
+  void trace_mark(int k, int which, cudaStream_t st);
+  void trace_dump();
   // host-side wall-clock breakdown of a step (always on; microseconds, cumulative)
   enum HostPhase { H_PRE, H_WAIT, H_FSM, H_JOBS, H_COUNT };
   double host_us[H_COUNT] = {};
