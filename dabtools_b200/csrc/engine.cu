@@ -137,6 +137,13 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
     CUDA_TRY(cudaEventCreateWithFlags(&ev_copied[i], cudaEventDisableTiming));
     CUDA_TRY(cudaEventCreateWithFlags(&ev_consumed[i], cudaEventDisableTiming));
   }
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_sync_done, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_sync_out, cudaEventDisableTiming));
+  CUDA_TRY(cudaEventCreateWithFlags(&ev_prep_done, cudaEventDisableTiming));
+  for (int i = 0; i < 2; i++) {
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_fic_done[i], cudaEventDisableTiming));
+    CUDA_TRY(cudaEventCreateWithFlags(&ev_jobs[i], cudaEventDisableTiming));
+  }
   CUDA_TRY(cudaEventCreateWithFlags(&ev_ctl[0], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_ctl[1], cudaEventDisableTiming));
   CUDA_TRY(cudaEventCreateWithFlags(&ev_up[0], cudaEventDisableTiming));
@@ -275,6 +282,13 @@ void Engine::destroy() {
     cudaEventDestroy(ev_up[1]);
     cudaEventDestroy(ev_ctl[0]);
     cudaEventDestroy(ev_ctl[1]);
+    cudaEventDestroy(ev_sync_done);
+    cudaEventDestroy(ev_sync_out);
+    cudaEventDestroy(ev_prep_done);
+    for (int i = 0; i < 2; i++) {
+      cudaEventDestroy(ev_fic_done[i]);
+      cudaEventDestroy(ev_jobs[i]);
+    }
     cudaEventDestroy(ev_msc_done);
   }
   if (ev[0][0])
@@ -284,7 +298,7 @@ void Engine::destroy() {
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
                   &d_subjobs, &d_periods, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
   for (DevBuf *b : db) b->release();
-  PinBuf *pb[] = {&h_ctl, &h_stepctl[0], &h_stepctl[1], &h_sync, &h_fic_out[0], &h_fic_out[1], &h_jobs, &h_msc[0], &h_msc[1], &h_eti, &h_chunk};
+  PinBuf *pb[] = {&h_ctl, &h_stepctl[0], &h_stepctl[1], &h_sync, &h_fic_out[0], &h_fic_out[1], &h_jobs[0], &h_jobs[1], &h_msc[0], &h_msc[1], &h_eti, &h_chunk};
   for (PinBuf *b : pb) b->release();
   vb_fic.release();
   vb_msc.release();
@@ -402,7 +416,7 @@ int Engine::upload_tables(cudaStream_t st) {
 // FIC decode of the `active` streams' frames: depuncture, Viterbi, CRC, FIBs into the FIB store,
 // compact copy back to the host.  Nothing here waits for the GPU.
 // d_fic_src + s*fic_stride holds stream s' 9216 demapped FIC bits (one byte each).
-int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride) {
+int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride, bool early) {
   int rc;
   const int na = (int)active.size();
   if (na == 0) return DABGPU_OK;
@@ -410,9 +424,12 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
   uint8_t *d_fib_c = d_gather_out.as<uint8_t>();
   uint8_t *d_crc_c = d_fib_c + (size_t)na * FIBS_PER_TF;
   const size_t idx_bytes = ((size_t)na * 4 + 7) & ~(size_t)7;
-  if ((rc = h_jobs.reserve((size_t)S * 12 + 8))) return rc;
-  uint32_t *h_idx = h_jobs.as<uint32_t>();
-  uint64_t *h_dst = reinterpret_cast<uint64_t *>(h_jobs.as<uint8_t>() + idx_bytes);
+  // two staging buffers alternate: with early return the previous frame's upload may not have run yet
+  PinBuf &hj = h_jobs[jobs_buf];
+  CUDA_TRY(cudaEventSynchronize(ev_jobs[jobs_buf]));
+  if ((rc = hj.reserve((size_t)S * 12 + 8))) return rc;
+  uint32_t *h_idx = hj.as<uint32_t>();
+  uint64_t *h_dst = reinterpret_cast<uint64_t *>(hj.as<uint8_t>() + idx_bytes);
   vb_fic.clear();
   vb_fic.reserve_scale = std::max(1.0, (double)S / na);
   for (int a = 0; a < na; a++) {
@@ -423,7 +440,9 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
       vb_fic.add(((uint64_t)a * 4 + k) * FIC_ROW, (uint64_t)a * FIBS_PER_TF + 96 * k, 768, VIT_DESCRAMBLE);
   }
   if ((rc = d_gather_idx.reserve((size_t)S * 12 + 8))) return rc;
-  if ((rc = ctl_transfer(d_gather_idx.p, h_jobs.p, idx_bytes + (size_t)na * 8, cudaMemcpyHostToDevice, st))) return rc;
+  if ((rc = ctl_transfer(d_gather_idx.p, hj.p, idx_bytes + (size_t)na * 8, cudaMemcpyHostToDevice, st))) return rc;
+  CUDA_TRY(cudaEventRecord(ev_jobs[jobs_buf], st));
+  jobs_buf ^= 1;
   const uint32_t *d_idx = d_gather_idx.as<uint32_t>();
   const uint64_t *d_dst = reinterpret_cast<const uint64_t *>(d_gather_idx.as<uint8_t>() + idx_bytes);
   t0(K_FIC_PREP, st);
@@ -431,6 +450,10 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
                              d_fic_shape.as<ShapeDev>(), 774, st)))
     return rc;
   t1(K_FIC_PREP, st);
+  if (early) {  // the next frame's FIC symbols may overwrite d_ficbits from here on
+    CUDA_TRY(cudaEventRecord(ev_prep_done, st));
+    prep_pending = true;
+  }
   t0(K_FIC_VIT, st);
   if ((rc = vb_fic.run(d_steps_fic.as<uint8_t>(), d_fib_c, st))) return rc;
   t1(K_FIC_VIT, st);
@@ -438,6 +461,7 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
   if ((rc = launch_fib_crc(d_fib_c, d_crc_c, 12 * na, st))) return rc;
   if ((rc = launch_scatter_rows(d_fib_c, FIBS_PER_TF, d_dst, d_fibs.as<uint8_t>(), na, st))) return rc;
   if ((rc = ctl_transfer(h_fic_out[fic_buf].p, d_fib_c, (size_t)na * (FIBS_PER_TF + 12), cudaMemcpyDeviceToHost, st))) return rc;
+  if (early) CUDA_TRY(cudaEventRecord(ev_fic_done[fic_buf], st));
   return DABGPU_OK;
 }
 
@@ -445,15 +469,19 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
 // the part of sdr_demod that feeds back into the next FIFO read, and hand the frames that passed
 // to the back-end host logic (`lag`), which runs either right away or during the next call.
 // sync: SyncOut per stream (front-end path) or null (demapped path: every active frame is "ok").
-int Engine::fic_finish(cudaStream_t st, const SyncOut *sync, int demod_ev) {
+int Engine::fic_finish(cudaStream_t st, const SyncOut *sync, int demod_ev, bool early) {
   const int na = (int)active.size();
   if (na == 0) return DABGPU_OK;
   double tw = now_us();
-  CUDA_TRY(cudaStreamSynchronize(st));
+  if (early)
+    CUDA_TRY(cudaEventSynchronize(ev_sync_out));  // synchroniser outputs only; the FIC chain runs on
+  else
+    CUDA_TRY(cudaStreamSynchronize(st));
   host_us[H_WAIT] += now_us() - tw;
   tw = now_us();
   lag.valid = true;
   lag.fic_buf = fic_buf;
+  lag.fic_wait = early;
   lag.demod_ev = demod_ev;
   lag.active.swap(active);
   lag.proc.assign(na, 1);
@@ -496,6 +524,12 @@ int Engine::backend_host(cudaStream_t st) {
   lag.valid = false;
   const int na = (int)lag.active.size();
   double tw = now_us();
+  if (lag.fic_wait) {
+    CUDA_TRY(cudaEventSynchronize(ev_fic_done[lag.fic_buf]));
+    lag.fic_wait = false;
+    host_us[H_WAIT] += now_us() - tw;
+    tw = now_us();
+  }
   // ---- host: per-stream dab_process_frame (streams are independent) ----
   const uint8_t *h_fibs = h_fic_out[lag.fic_buf].as<uint8_t>();
   const uint8_t *h_crc = h_fibs + (size_t)na * FIBS_PER_TF;
@@ -706,8 +740,8 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
                                    d_planeoff.as<uint64_t>() + 4 * a, d_cifs.as<uint8_t>(), 1, st)))
         return rc;
   }
-  if ((rc = fic_launch(st, d_tf, pitch))) return rc;
-  if ((rc = fic_finish(st, nullptr, -1))) return rc;  // also covers the pack kernels on `st`
+  if ((rc = fic_launch(st, d_tf, pitch, false))) return rc;
+  if ((rc = fic_finish(st, nullptr, -1, false))) return rc;  // also covers the pack kernels on `st`
   if ((rc = backend_host(st))) return rc;
   return collect_timing(st);
 }
@@ -968,6 +1002,20 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
                             d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), S, st)))
         return rc;
       t1(K_SYNC, st);
+      // With trailing back-end logic the call returns as soon as the synchroniser outputs are on
+      // the host (they are all the next FIFO read depends on): copy them out right after the
+      // synchroniser, ahead of the demodulator.
+      if (trailing) {
+        CUDA_TRY(cudaEventRecord(ev_sync_done, st));
+        CUDA_TRY(cudaStreamWaitEvent(st_fic, ev_sync_done, 0));
+        if ((rc = ctl_transfer(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st_fic)))
+          return rc;
+        CUDA_TRY(cudaEventRecord(ev_sync_out, st_fic));
+        if (prep_pending) {  // the previous frame's FIC depuncture still reads d_ficbits
+          CUDA_TRY(cudaStreamWaitEvent(st, ev_prep_done, 0));
+          prep_pending = false;
+        }
+      }
       // FIC symbols first; their decoding then runs on st_fic next to the CIF symbols on `st`
       t0(K_DEMOD, st);
       if ((rc = launch_demod(rg, d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
@@ -985,8 +1033,10 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       CUDA_TRY(cudaEventRecord(ev_demod_done[demod_ev], st));
       // (when kernels are being timed, each one runs alone: the FIC chain starts after the CIFs)
       CUDA_TRY(cudaStreamWaitEvent(st_fic, timing ? ev_demod_done[demod_ev] : ev_fic_ready, 0));
-      if ((rc = ctl_transfer(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st_fic))) return rc;
-      if ((rc = fic_launch(st_fic, d_ficbits.as<uint8_t>(), 9216))) return rc;
+      if (!trailing &&
+          (rc = ctl_transfer(h_sync.p, d_sync.p, (size_t)S * sizeof(SyncOut), cudaMemcpyDeviceToHost, st_fic)))
+        return rc;
+      if ((rc = fic_launch(st_fic, d_ficbits.as<uint8_t>(), 9216, trailing))) return rc;
       launched = true;
     }
   }
@@ -994,7 +1044,7 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
   // callback that completed no frame has queued nothing to hide it behind: leave it for the next one.
   if ((launched || !trailing) && (rc = backend_host(st))) return rc;
   if (launched) {
-    if ((rc = fic_finish(st_fic, h_sync.as<SyncOut>(), demod_ev))) return rc;
+    if ((rc = fic_finish(st_fic, h_sync.as<SyncOut>(), demod_ev, trailing))) return rc;
     if (!trailing && (rc = backend_host(st))) return rc;
   }
   for (int s = 0; s < S; s++) tuner_feedback(front[s]);

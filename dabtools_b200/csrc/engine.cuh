@@ -107,7 +107,7 @@ struct Engine {
   DevBuf d_ens;       // EnsDev[S]
   DevBuf d_shapes, d_fic_shape;
   DevBuf d_cifjobs, d_subjobs, d_etijobs, d_planeoff, d_gather_idx, d_gather_out;
-  PinBuf h_ctl, h_stepctl[2], h_sync, h_fic_out[2], h_jobs, h_msc[2], h_eti, h_chunk;
+  PinBuf h_ctl, h_stepctl[2], h_sync, h_fic_out[2], h_jobs[2], h_msc[2], h_eti, h_chunk;
   // MSC work runs on its own stream so that it overlaps the next frames' front-end kernels
   // ... and the FIC chain (depuncture, Viterbi, CRC, copy back) on another one, so that the host
   // gets the FIBs while the CIF symbols of the same frame are still being demodulated
@@ -153,9 +153,16 @@ struct Engine {
     std::vector<uint8_t> proc;  // frame passed the synchroniser checks of sdr_demod
     std::vector<int> slot;      // physical TF slot of the frame
     int fic_buf = 0;            // which h_fic_out holds its FIBs
+    bool fic_wait = false;      // ... once ev_fic_done[fic_buf] has fired (early-return mode)
     int demod_ev = -1;          // ev_demod_done index covering its CIFs
   } lag;
   int fic_buf = 0;
+  // Early return (with trailing back-end logic): feed_iq only waits for the synchroniser outputs,
+  // which is all the next FIFO read depends on; the FIC results are awaited where they are used.
+  cudaEvent_t ev_sync_done = nullptr, ev_sync_out = nullptr, ev_prep_done = nullptr, ev_fic_done[2] = {},
+              ev_jobs[2] = {};
+  bool prep_pending = false;
+  int jobs_buf = 0;
   std::vector<int> frame_slot;  // per stream: slot of the frame in flight
   int take_slot(int s) {
     const int slot = back[s].phys;
@@ -233,8 +240,8 @@ struct Engine {
   int process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *mask, bool on_device);
 
  private:
-  int fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride);
-  int fic_finish(cudaStream_t st, const SyncOut *h_sync_or_null, int demod_ev);
+  int fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride, bool early);
+  int fic_finish(cudaStream_t st, const SyncOut *h_sync_or_null, int demod_ev, bool early);
   int refresh_layout(int s);
   int upload_tables(cudaStream_t st);
 };
