@@ -25,6 +25,7 @@ struct VitBatch {
   uint64_t total_steps = 0;  // sum over codewords of nbits+6 (for ACS/s accounting)
   int n_ctas = 0;
   bool small_ctas = false;  // one single-warp CTA per group instead of the persistent layout
+  bool one_warp_ctas = false;  // what plan() chose
   double reserve_scale = 1.0;  // allocate this much more than the current job list needs (the
                                // caller's ratio of a full batch to this one), so stores never grow
 
@@ -57,7 +58,10 @@ struct VitBatch {
       g0.push_back(g);
       i = j;
     }
-    if (small_ctas) {
+    // sparse batches (fewer than two groups per warp scheduler) are latency-bound: one single-warp
+    // CTA per group lets the hardware spread them, whatever else is running
+    one_warp_ctas = small_ctas || g0.size() < (size_t)device_sm_count() * 8;
+    if (one_warp_ctas) {
       groups.swap(g0);
       n_ctas = (int)groups.size();
       bin_start.resize(groups.size() + 1);
@@ -66,7 +70,9 @@ struct VitBatch {
     }
     // LPT over the warp schedulers (4 per SM); a scheduler's groups are then dealt round-robin to
     // its VIT_WARPS/4 resident warps so that they overlap each other's latencies
-    const int n_sm = device_sm_count();
+    // (with several CTAs per SM every CTA is planned on its own: which CTAs end up sharing an SM, and
+    // which of their warps a scheduler, is the hardware's choice; equal work lists make it irrelevant)
+    const int n_sm = device_sm_count() * VIT_CTAS_PER_SM;
     const int per_sched = VIT_WARPS / 4;
     const int n_sched = std::min<int>(n_sm * 4, std::max<size_t>(1, g0.size()));
     n_ctas = std::min(n_sm, n_sched);  // small batches spread over SMs before doubling up
@@ -137,7 +143,7 @@ struct VitBatch {
   // launch again with the descriptors of the last run() (identical job list by construction)
   int relaunch(const uint8_t *d_steps, uint8_t *d_out, cudaStream_t st) {
     return launch_viterbi(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
-                          d_bins.as<uint32_t>(), n_ctas, small_ctas ? 1 : VIT_WARPS, st);
+                          d_bins.as<uint32_t>(), n_ctas, one_warp_ctas ? 1 : VIT_WARPS, st);
   }
   void release() {
     d_jobs.release();

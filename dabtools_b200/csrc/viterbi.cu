@@ -363,7 +363,7 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const VitLut &lu
 // w % 4) so that every scheduler gets the same number of trellis steps, then over the scheduler's
 // VIT_WARPS/4 warps so that they all stay busy until the end of the launch.
 template <int WARPS>
-__global__ void __launch_bounds__(32 * WARPS, 1) viterbi_kernel(const uint8_t *__restrict__ steps,
+__global__ void __launch_bounds__(32 * WARPS, WARPS == 1 ? 1 : VIT_CTAS_PER_SM) viterbi_kernel(const uint8_t *__restrict__ steps,
                                                                 uint8_t *__restrict__ out,
                                                                 uint2 *__restrict__ dec,
                                                                 const VitJob *__restrict__ jobs,

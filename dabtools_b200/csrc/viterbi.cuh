@@ -36,12 +36,19 @@ __host__ __device__ static inline uint64_t vit_group_dec_words(uint32_t nsteps) 
 }
 __host__ __device__ static inline uint32_t vit_row_bytes(uint32_t nsteps) { return (nsteps + 15u) & ~15u; }
 
-// warps per persistent CTA (one CTA per SM): 4 schedulers x 4 concurrent work lists; at 127
-// registers per thread the CTA takes the whole register file (measured: 16 warps 2 % faster than 12)
+// Persistent launch shape: VIT_CTAS_PER_SM CTAs of VIT_WARPS warps on every SM, each warp with its
+// own work list.  Measured on B200 (1024 streams, whole receive step / MSC launch alone):
+//   1 x 16 warps (whole register file)  2.58 ms / 1.18 ms      3 x 4 warps  2.50 ms / 1.21 ms
+//   1 x  8 warps                        2.54 ms / 1.26 ms      2 x 4 warps  2.71 ms / 1.40 ms
+// Twelve warps in three small CTAs leave a quarter of the registers to the demodulator's CTAs of
+// the next frames, whose FP32 work then shares the SM with the decoder's integer work.
 #ifndef DABGPU_VIT_WARPS
-#define DABGPU_VIT_WARPS 16
+#define DABGPU_VIT_WARPS 4
 #endif
-enum { VIT_WARPS = DABGPU_VIT_WARPS };
+#ifndef DABGPU_VIT_CTAS_PER_SM
+#define DABGPU_VIT_CTAS_PER_SM 3
+#endif
+enum { VIT_WARPS = DABGPU_VIT_WARPS, VIT_CTAS_PER_SM = DABGPU_VIT_CTAS_PER_SM };
 int device_sm_count();
 // persistent launch: n_ctas CTAs of VIT_WARPS warps; warp-bin b owns groups
 // d_bin_start[b] .. d_bin_start[b+1] (n_ctas * VIT_WARPS + 1 entries)
