@@ -68,10 +68,10 @@ struct VitBatch {
       for (size_t i = 0; i <= groups.size(); i++) bin_start[i] = (uint32_t)i;
       return;
     }
-    // LPT over the warp schedulers (4 per SM); a scheduler's groups are then dealt round-robin to
-    // its VIT_WARPS/4 resident warps so that they overlap each other's latencies
-    // (with several CTAs per SM every CTA is planned on its own: which CTAs end up sharing an SM, and
-    // which of their warps a scheduler, is the hardware's choice; equal work lists make it irrelevant)
+    // LPT over the CTAs' scheduler quarters (warp w of a CTA runs on scheduler w % 4); a quarter's
+    // groups are then dealt LPT to its VIT_WARPS/4 warps so that they overlap each other's latencies.
+    // With several CTAs per SM every CTA is planned on its own: which CTAs end up sharing an SM is the
+    // hardware's choice, and equal work lists make it irrelevant.
     const int n_sm = device_sm_count() * VIT_CTAS_PER_SM;
     const int per_sched = VIT_WARPS / 4;
     const int n_sched = std::min<int>(n_sm * 4, std::max<size_t>(1, g0.size()));

@@ -357,11 +357,11 @@ __device__ __forceinline__ void decode_group(const VitGroup &g, const VitLut &lu
   }
 }
 
-// Persistent decoder: one CTA per SM, VIT_WARPS warps per CTA.  Warp w of CTA b owns work list
-// `bin = b * VIT_WARPS + w` (groups bin_start[bin] .. bin_start[bin+1]).  The host packs the
-// groups longest-processing-time-first, first over the warp schedulers (warp w runs on scheduler
-// w % 4) so that every scheduler gets the same number of trellis steps, then over the scheduler's
-// VIT_WARPS/4 warps so that they all stay busy until the end of the launch.
+// Persistent decoder: VIT_CTAS_PER_SM CTAs of VIT_WARPS warps on every SM (see viterbi.cuh for the
+// measured shapes).  Warp w of CTA b owns work list `bin = b * VIT_WARPS + w` (groups
+// bin_start[bin] .. bin_start[bin+1]).  The host packs the groups longest-processing-time-first over
+// the CTAs' scheduler quarters (warp w runs on scheduler w % 4) and then over each quarter's
+// VIT_WARPS/4 warps, so that all warps stay busy until the end of the launch.
 template <int WARPS>
 __global__ void __launch_bounds__(32 * WARPS, WARPS == 1 ? 1 : VIT_CTAS_PER_SM) viterbi_kernel(const uint8_t *__restrict__ steps,
                                                                 uint8_t *__restrict__ out,

@@ -52,7 +52,7 @@ enum { VIT_WARPS = DABGPU_VIT_WARPS, VIT_CTAS_PER_SM = DABGPU_VIT_CTAS_PER_SM };
 int device_sm_count();
 // persistent launch: n_ctas CTAs of VIT_WARPS warps; warp-bin b owns groups
 // d_bin_start[b] .. d_bin_start[b+1] (n_ctas * VIT_WARPS + 1 entries)
-// warps_per_cta: VIT_WARPS (persistent, one CTA per SM) or 1 (one small CTA per work list: a
+// warps_per_cta: VIT_WARPS (persistent, VIT_CTAS_PER_SM CTAs per SM) or 1 (one small CTA per work list: a
 // footprint that can share SMs with other kernels, used for the latency-critical FIC batches)
 int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
                    const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, int warps_per_cta,
