@@ -93,6 +93,7 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   f0 = tuner_hz;
   quiet = !(flags & DABGPU_ENGINE_VERBOSE);
   virtual_tuner = flags & DABGPU_ENGINE_VIRTUAL_TUNER;
+  subch_mask.assign(S, ~0ull);
   front.assign(S, FrontState());
   back.resize(S);
   layout.assign(S, EnsLayout());
@@ -310,16 +311,18 @@ int Engine::refresh_layout(int s) {
   const ens_info_t &ei = back[s].ens_info;
   if (L.version == back[s].ens_version) return DABGPU_OK;
   L.version = back[s].ens_version;
+  L.epoch = ++layout_epoch;
   L.nsub = 0;
   memset(&L.dev, 0, sizeof L.dev);
   uint32_t row = 0, nst = 0, fl = 0, payload = 0;
+  const uint64_t keep = subch_mask[s];  // dabgpu_engine_set_subchannel_mask: all ones by default
   for (int j = 0; j < 64; j++)
-    if (ei.subchans[j].id >= 0) nst++;
+    if (ei.subchans[j].id >= 0 && ((keep >> j) & 1)) nst++;
   L.e1 = 12 + 4 * nst;
   uint32_t e = L.e1 + 96;
   for (int j = 0; j < 64; j++) {
     const subchannel_info_t &sc = ei.subchans[j];
-    if (sc.id < 0) continue;
+    if (sc.id < 0 || !((keep >> j) & 1)) continue;
     dabgpu_cw_shape sh;
     if (host_subch_shape(&sc, &sh) || sh.nbits <= 0 || sh.nbits > 9216 ||
         sc.start_cu * 64 + sh.in_bits > DABGPU_CIF_BITS) {
@@ -562,7 +565,7 @@ int Engine::backend_host(cudaStream_t st) {
     for (int k = 0; k < work.n_eti; k++) {
       pend_stream.push_back(s);
       pend_of_stream[s]++;
-      pend_sig = (pend_sig ^ (uint64_t)(uint32_t)s ^ (layout[s].version << 32)) * 0x100000001b3ull;
+      pend_sig = (pend_sig ^ (uint64_t)(uint32_t)s ^ (layout[s].epoch << 32)) * 0x100000001b3ull;
       CifJob cj;
       for (int j = 0; j < 16; j++)
         cj.slot_off[j] = ((uint64_t)s * CIF_SLOTS + (uint64_t)work.win[k][j]) * CIF_BYTES;
@@ -1157,6 +1160,20 @@ DABGPU_EXPORT int dabgpu_engine_kernel_times(dabgpu_engine *h, double *ms_total,
 
 DABGPU_EXPORT void dabgpu_engine_host_times(dabgpu_engine *h, double *us4) {
   for (int i = 0; i < Engine::H_COUNT; i++) us4[i] = h->e.host_us[i];
+}
+
+DABGPU_EXPORT int dabgpu_engine_set_subchannel_mask(dabgpu_engine *h, int stream, uint64_t mask) {
+  Engine &e = h->e;
+  if (stream < -1 || stream >= e.S) {
+    set_error(DABGPU_ERR_ARG, "set_subchannel_mask: bad stream index");
+    return DABGPU_ERR_ARG;
+  }
+  for (int s = stream < 0 ? 0 : stream; s < (stream < 0 ? e.S : stream + 1); s++)
+    if (e.subch_mask[s] != mask) {
+      e.subch_mask[s] = mask;
+      e.layout[s].version = 0;  // re-derived (after the frames already queued) with the next frame
+    }
+  return DABGPU_OK;
 }
 
 DABGPU_EXPORT int dabgpu_engine_set_msc_batch(dabgpu_engine *h, int calls) {

@@ -40,6 +40,7 @@ class HostPool {
 // derived from a stream's ens_info whenever its sub-channel table changes
 struct EnsLayout {
   uint64_t version = 0;
+  uint64_t epoch = 0;  // engine-wide counter value of the last re-derivation (job-list cache key)
   int nsub = 0;
   struct Sub {
     uint32_t in_bit0, shape, nbits, row_off, eti_off;
@@ -78,6 +79,8 @@ struct Engine {
   std::vector<FrontState> front;
   std::vector<BackendState> back;
   std::vector<EnsLayout> layout;
+  uint64_t layout_epoch = 0;
+  std::vector<uint64_t> subch_mask;  // per stream: SubChIds that are decoded and carried in the ETI
   std::vector<StreamStats> stats;
 
   // puncturing-period lists of the multiplex layouts seen so far (host copy mirrored in d_periods);

@@ -303,6 +303,12 @@ def _engine_feed_capture(self, chunk_len: int) -> int:
     return self._lib.dabgpu_engine_eti_count(self._h)
 
 
+def _engine_set_subchannel_mask(self, mask: int, stream: int = -1):
+    self._lib.dabgpu_engine_set_subchannel_mask.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
+    check(self._lib.dabgpu_engine_set_subchannel_mask(self._h, stream, mask & 0xFFFFFFFFFFFFFFFF))
+
+
+Engine.set_subchannel_mask = _engine_set_subchannel_mask
 Engine.attach_capture = _engine_attach_capture
 Engine.feed_capture = _engine_feed_capture
 Engine.submit_iq = _engine_submit_iq

@@ -152,6 +152,12 @@ const uint8_t *dabgpu_engine_eti_device(dabgpu_engine *e);
  * returns the number of frames, or a negative error */
 int dabgpu_engine_fetch_eti(dabgpu_engine *e, uint8_t *eti, int32_t *stream_ids, int max_frames);
 int dabgpu_engine_status(dabgpu_engine *e, int stream, dabgpu_stream_status *out);
+/* Sub-channel filter (the reference's open TODO, TODO.md:3): only the sub-channels whose SubChId
+ * bit is set in `mask` are Viterbi-decoded and carried in the ETI frames of `stream` (-1: every
+ * stream) -- NST, the STC list, FL and the MST shrink accordingly, FIC and everything else stay as
+ * misc.c:153-314 builds them.  Takes effect with the next transmission frame; frames already queued
+ * keep the old selection.  Default: all ones (the reference's behaviour). */
+int dabgpu_engine_set_subchannel_mask(dabgpu_engine *e, int stream, uint64_t mask);
 int dabgpu_engine_set_seed(dabgpu_engine *e, int stream, unsigned seed); /* srand() of dab2eti.c:88-96 */
 uint64_t dabgpu_engine_trellis_steps(dabgpu_engine *e);
 /* Optional device-side timing of the engine's kernels with CUDA events on the launch stream

@@ -152,3 +152,82 @@ def test_every_protection_profile(gpu, port):
             want, _, _ = port.run_backend(bits[s])
             assert got[s].shape == want.shape and want.shape[0] == 4 * (n_tf - 13), (s, got[s].shape, want.shape)
             assert np.array_equal(got[s], want), (batch, s)
+
+
+def _crc16(data: bytes, crc: int = 0xFFFF) -> int:
+    for b in data:
+        crc ^= b << 8
+        for _ in range(8):
+            crc = ((crc << 1) ^ 0x1021) & 0xFFFF if crc & 0x8000 else (crc << 1) & 0xFFFF
+    return crc
+
+
+def _parse_eti(frame):
+    """ETI(NI) frame -> (nst, {SubChId: (stl words, payload bytes)}, header/EOF CRC ok)"""
+    f = bytes(frame)
+    nst = f[5] & 0x7F
+    fl = ((f[6] & 7) << 8) | f[7]
+    eoh = 8 + 4 * nst
+    hcrc_ok = (~_crc16(f[4:eoh + 2]) & 0xFFFF) == (f[eoh + 2] << 8 | f[eoh + 3])
+    pos = eoh + 4 + 96
+    subs = {}
+    for j in range(nst):
+        w = f[8 + 4 * j: 12 + 4 * j]
+        scid = w[0] >> 2
+        stl = ((w[2] & 3) << 8) | w[3]
+        subs[scid] = (w, f[pos: pos + 8 * stl])
+        pos += 8 * stl
+    mst = f[eoh + 4: pos]
+    eof_ok = (~_crc16(mst) & 0xFFFF) == (f[pos] << 8 | f[pos + 1])
+    assert fl == nst + 1 + (pos - (eoh + 4)) // 4
+    return nst, subs, f[eoh + 4: eoh + 4 + 96], hcrc_ok and eof_ok, f[pos + 8:]
+
+
+def test_subchannel_filter(gpu, port):
+    """dabgpu_engine_set_subchannel_mask: the selected sub-channels come out exactly as in the
+    unfiltered ETI (STC words, payload), the frame is a consistent ETI(NI) frame (NST, FL, both CRCs,
+    padding), and the full mask is the reference's behaviour."""
+    ens = synth.small_ensemble()            # SubChIds 3, 7, 12
+    S, n_tf = 2, 18
+    bits = synth.ModeITransmitter(ens).generate(S, n_tf, seed=31, want_iq=False)["bits"].numpy()
+    full, _ = _run_engine(gpu, bits, msc_batch=2)
+    want, _, _ = port.run_backend(bits[0])
+    assert np.array_equal(full[0], want)
+
+    def run(mask0, change_at=None, mask1=None):
+        eng = gpu.Engine(S)
+        eng.set_msc_batch(2)
+        eng.set_subchannel_mask(mask0, stream=0)          # stream 1 keeps everything
+        out = [[] for _ in range(S)]
+        for t in range(n_tf + 1):
+            if t == change_at:
+                eng.set_subchannel_mask(mask1, stream=0)
+            n = eng.process_demapped(bits[:, t]) if t < n_tf else eng.flush()
+            eti, ids = eng.fetch_eti()
+            for f, s in zip(eti, ids):
+                out[s].append(f.copy())
+        eng.close()
+        return [np.array(o, dtype=np.uint8).reshape(-1, 6144) for o in out]
+
+    keep = (1 << 3) | (1 << 12)
+    got = run(keep)
+    assert np.array_equal(got[1], full[1])                 # the other stream is untouched
+    assert got[0].shape == full[0].shape
+    for fr, ref_fr in zip(got[0], full[0]):
+        nst, subs, fic, ok, pad = _parse_eti(fr)
+        nst_r, subs_r, fic_r, ok_r, _ = _parse_eti(ref_fr)
+        assert ok and ok_r and nst == 2 and nst_r == 3
+        assert sorted(subs) == [3, 12] and fic == fic_r
+        for scid in subs:
+            assert subs[scid] == subs_r[scid]
+        assert bytes(fr[:5]) == bytes(ref_fr[:5])          # ERR, FSYNC, FCT
+        assert set(pad) == {0x55}
+    # nothing selected: header + FIC only
+    none = run(0)
+    nst, subs, fic, ok, pad = _parse_eti(none[0][0])
+    assert nst == 0 and ok and not subs
+    # a change while frames are queued takes effect with the next transmission frame
+    mixed = run(~0, change_at=16, mask1=keep)
+    nsts = [_parse_eti(fr)[0] for fr in mixed[0]]
+    assert nsts[:8] == [3] * 8 and nsts[-4:] == [2] * 4 and sorted(set(nsts)) == [2, 3]
+    assert all(_parse_eti(fr)[3] for fr in mixed[0])
