@@ -600,7 +600,8 @@ def run_reference(args, rank, world):
         return None
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     K, W = args.steps, args.warmup
-    r = cpu_reference_rate(cores, reps=max(1, min(K + W, 3)))
+    n2 = int(os.environ.get("DABGPU_BENCH_REF_TFS", "40"))   # (tests shorten the sample)
+    r = cpu_reference_rate(cores, reps=max(1, min(K + W, 3)), n2=max(n2, 20))
     return {
         "impl": "reference",
         "metric": "ETI frames/s (Mode I)",
