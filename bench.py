@@ -362,54 +362,77 @@ def run_ours(args, rank, world, local_rank):
     # The samples are resident in HBM before the timed region.  With --ingest capture (default) the
     # engine consumes them in place (dabgpu_engine_attach_capture / feed_capture); with --ingest copy
     # every callback is first copied into the engine's own FIFO ring (dabgpu_engine_feed_iq).
-    eng = lib.Engine(S)
-    eng.set_msc_batch(args.msc_batch)
     capture = args.ingest == "capture"
-    if capture:
-        eng.attach_capture(data)
 
-    def step_value(i):
-        if not capture:
-            return step_device(eng, i)
+    def measure_value():
+        """set-up, warm-up and the timed region on a fresh engine; returns everything the report needs"""
+        eng = lib.Engine(S)
+        eng.set_msc_batch(args.msc_batch)
+        if capture:
+            eng.attach_capture(data)
+
+        def step_value(i):
+            if not capture:
+                return step_device(eng, i)
+            n = 0
+            for c in range(CALLS_PER_STEP):
+                n += eng.feed_capture(CALL_BYTES)
+            return n
+
+        for i in range(setup_steps):
+            step_value(i)
+        locked = sum(eng.status(s).locked for s in range(S))
+        if locked != S:
+            raise RuntimeError(f"only {locked}/{S} streams locked after set-up")
+        sampler = ClockSampler(local_rank)
+        if rank == 0:
+            sampler.start()
         n = 0
-        for c in range(CALLS_PER_STEP):
-            n += eng.feed_capture(CALL_BYTES)
-        return n
+        for i in range(W):
+            n += step_value(setup_steps + i)
+        assert n >= S * TFS_PER_STEP * FRAMES_PER_TF * (W - 2), f"steady state not reached: {n} frames in warm-up"
+        # start from an empty pipeline so that the frames counted are exactly the frames fed
+        eng.flush()
+        eng.join()
+        launches0 = lib.launch_count()
+        host_t0 = eng.host_times()
+        barrier()
+        sampler.begin()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        frames = 0
+        base = setup_steps + W
+        for i in range(K):
+            frames += step_value(base + i)
+        frames += eng.flush()   # frames still queued for a deferred MSC batch belong to these steps
+        eng.join()              # ... and so does the MSC stream's last batch
+        e1.record()
+        barrier()
+        sampler.end()
+        clocks = sampler.stop() if rank == 0 else None
+        ms = e0.elapsed_time(e1)
+        launches = lib.launch_count() - launches0
+        host_t = eng.host_times()
+        return dict(eng=eng, ms=ms, frames=frames, clocks=clocks, launches=launches, host_t=host_t, host_t0=host_t0)
 
-    for i in range(setup_steps):
-        step_value(i)
-    locked = sum(eng.status(s).locked for s in range(S))
-    if locked != S:
-        raise RuntimeError(f"only {locked}/{S} streams locked after set-up")
-    sampler = ClockSampler(local_rank)
-    if rank == 0:
-        sampler.start()
-    n = 0
-    for i in range(W):
-        n += step_value(setup_steps + i)
-    assert n >= S * TFS_PER_STEP * FRAMES_PER_TF * (W - 2), f"steady state not reached: {n} frames in warm-up"
-    # start from an empty pipeline so that the frames counted are exactly the frames fed
-    eng.flush()
-    eng.join()
-    launches0 = lib.launch_count()
-    host_t0 = eng.host_times()
-    barrier()
-    sampler.begin()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    frames = 0
+    res = measure_value()
+    # a run that saw thermal / hardware slowdown is rejected and measured again, once
+    bad_reasons = {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"}
+    redo = torch.zeros(1, dtype=torch.int32, device=dev)
+    if rank == 0 and res["clocks"] and (bad_reasons & set(res["clocks"].get("reasons", []))
+                                        or os.environ.get("DABGPU_BENCH_FORCE_REDO")):   # (test hook)
+        redo += 1
+    if world > 1:
+        dist.broadcast(redo, src=0)
+    if int(redo.item()):
+        rejected = res["clocks"]
+        res["eng"].close()
+        res = measure_value()
+        if rank == 0 and res["clocks"] is not None:
+            res["clocks"]["rejected_first_run"] = rejected
+    eng, ms, frames, clocks, launches = res["eng"], res["ms"], res["frames"], res["clocks"], res["launches"]
+    host_t, host_t0 = res["host_t"], res["host_t0"]
     base = setup_steps + W
-    for i in range(K):
-        frames += step_value(base + i)
-    frames += eng.flush()   # frames still queued for a deferred MSC batch belong to these steps
-    eng.join()              # ... and so does the MSC stream's last batch
-    e1.record()
-    barrier()
-    sampler.end()
-    clocks = sampler.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
-    launches = lib.launch_count() - launches0
-    host_t = eng.host_times()
     if capture:   # the per-kernel pass below times the copying path (it has the ingest kernel)
         eng.close()
         del eng
