@@ -126,3 +126,49 @@ def test_init_eti_matches_the_reference(libs):
         nb = theirs.init_eti(b, C.byref(e2))
         assert na == nb and bytes(a[:na]) == bytes(b[:nb]), trial
         assert bytes(e) == bytes(e2)
+
+
+def test_fifo_drop_ins_match_the_reference(libs):
+    """cbInit/cbWrite/cbRead/cbIsEmpty/cbIsFull/sdr_read_fifo (sdr_fifo.c:26-61): same buffer contents,
+    same FIFO state, including the stale tail of negative shifts and the parked skip bytes of positive
+    ones (the quirks the batched FIFO bookkeeping reproduces on the GPU side)."""
+    ours, theirs = libs
+    rng = np.random.default_rng(99)
+    u8p = C.POINTER(C.c_uint8)
+    for L in (ours, theirs):
+        L.cbInit.argtypes = [C.POINTER(R.CircularBuffer), C.c_uint32]
+        L.cbWrite.argtypes = [C.POINTER(R.CircularBuffer), u8p]
+        L.cbRead.argtypes = [C.POINTER(R.CircularBuffer), u8p]
+        L.cbIsEmpty.argtypes = [C.POINTER(R.CircularBuffer)]
+        L.cbIsFull.argtypes = [C.POINTER(R.CircularBuffer)]
+        L.sdr_read_fifo.argtypes = [C.POINTER(R.CircularBuffer), C.c_uint32, C.c_int32, u8p]
+    size, frame = 4096, 1000
+    fa, fb = R.CircularBuffer(), R.CircularBuffer()
+    ours.cbInit(C.byref(fa), size)
+    theirs.cbInit(C.byref(fb), size)
+    buf_a = (C.c_uint8 * frame)()
+    buf_b = (C.c_uint8 * frame)()
+    for trial in range(60):
+        n = int(rng.integers(200, 1500))
+        n = min(n, size - fa.count)               # (an overflow only makes the reference print)
+        data = rng.integers(0, 256, n, dtype=np.uint8)
+        for v in data:
+            x = C.c_uint8(int(v))
+            ours.cbWrite(C.byref(fa), C.byref(x))
+            theirs.cbWrite(C.byref(fb), C.byref(x))
+        assert (fa.start, fa.count) == (fb.start, fb.count)
+        assert ours.cbIsFull(C.byref(fa)) == theirs.cbIsFull(C.byref(fb))
+        shift = int(rng.choice([0, 0, 2, 16, 300, -2, -20, -400]))
+        need = frame + max(shift, 0)
+        if fa.count >= need:
+            ours.sdr_read_fifo(C.byref(fa), frame, shift, buf_a)
+            theirs.sdr_read_fifo(C.byref(fb), frame, shift, buf_b)
+            assert bytes(buf_a) == bytes(buf_b), (trial, shift)
+            assert (fa.start, fa.count) == (fb.start, fb.count)
+        assert ours.cbIsEmpty(C.byref(fa)) == theirs.cbIsEmpty(C.byref(fb))
+    x, y = C.c_uint8(0), C.c_uint8(0)
+    while fa.count:
+        ours.cbRead(C.byref(fa), C.byref(x))
+        theirs.cbRead(C.byref(fb), C.byref(y))
+        assert x.value == y.value
+    assert fb.count == 0
