@@ -655,7 +655,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--streams", type=int, default=1024, help="ensemble streams per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=6, help="steps of the pinned-host pass (pinned memory bound)")
+    ap.add_argument("--e2e-steps", type=int, default=8, help="steps of the pinned-host pass (pinned memory bound)")
     ap.add_argument("--msc-batch", type=int, default=2,
                     help="transmission frames per MSC Viterbi launch (dabgpu_engine_set_msc_batch)")
     ap.add_argument("--e2e-msc-batch", type=int, default=4,
