@@ -408,16 +408,145 @@ __device__ __forceinline__ void tma_load_1d(void *dst_smem, const void *src_gmem
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
-enum { SYM_BYTES = 4096, STAGE_BYTES = SYM_BYTES + 16, N_STAGES = 3 };
+// ---- packed single precision (sm_100 FADD2 / FMUL2 / FFMA2) -------------------------------------
+// The demodulator transforms TWO consecutive OFDM symbols per thread: every real quantity of the FFT
+// is a 64-bit register pair (low half: symbol A = l, high half: symbol B = l + 1).  The two
+// transforms share every twiddle factor, which the packed instructions take as a broadcast scalar
+// operand, so one issue slot does the work of two and nothing has to be shuffled between halves.
+typedef unsigned long long pk_t;
+__device__ __forceinline__ pk_t pk(float lo, float hi) {
+  pk_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ pk_t pku(uint32_t lo, uint32_t hi) {
+  pk_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "r"(lo), "r"(hi));
+  return r;
+}
+__device__ __forceinline__ float pk_lo(pk_t v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return a;
+}
+__device__ __forceinline__ float pk_hi(pk_t v) {
+  float a, b;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v));
+  return b;
+}
+__device__ __forceinline__ pk_t add2(pk_t a, pk_t b) {
+  pk_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ pk_t sub2(pk_t a, pk_t b) {
+  pk_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ pk_t mul2(pk_t a, pk_t b) {
+  pk_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ pk_t fma2(pk_t a, pk_t b, pk_t c) {
+  pk_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ pk_t bc(float s) { return pk(s, s); }  // becomes a scalar (.F32) operand
+
+struct C2 {  // two complex numbers: (re.lo, im.lo) of symbol A and (re.hi, im.hi) of symbol B
+  pk_t re, im;
+};
+__device__ __forceinline__ C2 cadd2(C2 a, C2 b) { return C2{add2(a.re, b.re), add2(a.im, b.im)}; }
+__device__ __forceinline__ C2 csub2(C2 a, C2 b) { return C2{sub2(a.re, b.re), sub2(a.im, b.im)}; }
+// a * (wr + i wi), the same factor for both halves: 2 FMUL2 + 2 FFMA2
+__device__ __forceinline__ C2 cmul2s(C2 a, float wr, float wi) {
+  const pk_t t = mul2(a.re, bc(wr)), u = mul2(a.re, bc(wi));
+  return C2{fma2(a.im, bc(-wi), t), fma2(a.im, bc(wr), u)};
+}
+// forward 4-point DFT in place; the rotation by -i is a renaming of halves folded into the adds
+__device__ __forceinline__ void dft4p(C2 &a, C2 &b, C2 &c, C2 &d) {
+  const C2 s0 = cadd2(a, c), s1 = csub2(a, c), s2 = cadd2(b, d), t = csub2(b, d);
+  a = cadd2(s0, s2);
+  c = csub2(s0, s2);
+  b = C2{add2(s1.re, t.im), sub2(s1.im, t.re)};
+  d = C2{sub2(s1.re, t.im), add2(s1.im, t.re)};
+}
+// forward 8-point DFT, natural order in and out; the 1/sqrt2 factors ride in the last butterflies
+__device__ __forceinline__ void dft8p(C2 *v) {
+  const float h = 0.70710678118654752f;
+  C2 e0 = v[0], e1 = v[2], e2 = v[4], e3 = v[6];
+  C2 o0 = v[1], o1 = v[3], o2 = v[5], o3 = v[7];
+  dft4p(e0, e1, e2, e3);
+  dft4p(o0, o1, o2, o3);
+  // W8^1 o1 = h (x + y, y - x) ; W8^2 o2 = (y, -x) ; W8^3 o3 = h (y - x, -(x + y))
+  const pk_t s1 = add2(o1.re, o1.im), d1 = sub2(o1.im, o1.re);
+  const pk_t s3 = add2(o3.re, o3.im), d3 = sub2(o3.im, o3.re);
+  v[0] = cadd2(e0, o0);
+  v[4] = csub2(e0, o0);
+  v[1] = C2{fma2(s1, bc(h), e1.re), fma2(d1, bc(h), e1.im)};
+  v[5] = C2{fma2(s1, bc(-h), e1.re), fma2(d1, bc(-h), e1.im)};
+  v[2] = C2{add2(e2.re, o2.im), sub2(e2.im, o2.re)};
+  v[6] = C2{sub2(e2.re, o2.im), add2(e2.im, o2.re)};
+  v[3] = C2{fma2(d3, bc(h), e3.re), fma2(s3, bc(-h), e3.im)};
+  v[7] = C2{fma2(d3, bc(-h), e3.re), fma2(s3, bc(h), e3.im)};
+}
+// forward 16-point DFT, natural order in and out (4 x 4)
+__device__ __forceinline__ void dft16p(C2 *v) {
+  const float h = 0.70710678118654752f, c1 = 0.92387953251128674f, s1 = 0.38268343236508977f;
+  C2 x[4][4];
+#pragma unroll
+  for (int b = 0; b < 4; b++) {
+    x[b][0] = v[b];
+    x[b][1] = v[4 + b];
+    x[b][2] = v[8 + b];
+    x[b][3] = v[12 + b];
+    dft4p(x[b][0], x[b][1], x[b][2], x[b][3]);
+  }
+  // twiddles W16^(b p): W1 = (c1,-s1) W2 = (h,-h) W3 = (s1,-c1) W4 = -i W6 = (-h,-h) W9 = (-c1,s1)
+  x[1][1] = cmul2s(x[1][1], c1, -s1);
+  x[1][3] = cmul2s(x[1][3], s1, -c1);
+  x[3][1] = cmul2s(x[3][1], s1, -c1);
+  x[3][3] = cmul2s(x[3][3], -c1, s1);
+  {  // W2 z = h (x + y, y - x) ; W6 z = h (y - x, -(x + y))
+    C2 z = x[1][2];
+    x[1][2] = C2{mul2(add2(z.re, z.im), bc(h)), mul2(sub2(z.im, z.re), bc(h))};
+    z = x[2][1];
+    x[2][1] = C2{mul2(add2(z.re, z.im), bc(h)), mul2(sub2(z.im, z.re), bc(h))};
+    z = x[2][3];
+    x[2][3] = C2{mul2(sub2(z.im, z.re), bc(h)), mul2(add2(z.re, z.im), bc(-h))};
+    z = x[3][2];
+    x[3][2] = C2{mul2(sub2(z.im, z.re), bc(h)), mul2(add2(z.re, z.im), bc(-h))};
+    z = x[2][2];
+    x[2][2] = C2{z.im, sub2(bc(0.f), z.re)};  // -i z
+  }
+#pragma unroll
+  for (int p = 0; p < 4; p++) {
+    dft4p(x[0][p], x[1][p], x[2][p], x[3][p]);
+    v[p] = x[0][p];
+    v[p + 4] = x[1][p];
+    v[p + 8] = x[2][p];
+    v[p + 12] = x[3][p];
+  }
+}
+
+
+enum { SYM_BYTES = 4096, STAGE_BYTES = SYM_BYTES + 16, N_STAGES = 3, DEMOD_CTAS_PER_SM = 3 };
+enum { N_SLOTS = 12 };  // carriers per thread and symbol
 
 struct DemodSmem {
-  float2 xch[XCH_ELEMS];
+  // exchange buffer, real and imaginary parts apart: a 128-bit store would need (re, im) in four
+  // consecutive registers, which costs three moves per store; two 64-bit stores cost none
+  pk_t xre[XCH_ELEMS], xim[XCH_ELEMS];
   // a symbol is fetched from the 16-byte aligned address below its first byte (TMA needs aligned
-  // sources; ring windows start at any even offset), hence 16 spare bytes per stage
-  __align__(16) uint8_t stage[N_STAGES][STAGE_BYTES];
+  // sources; ring windows start at any even offset), hence 16 spare bytes per buffer
+  __align__(16) uint8_t stage[N_STAGES][2][STAGE_BYTES];
   __align__(16) uint8_t tailbuf[TAIL_BYTES];   // second half of symbol 75 in ring mode
-  uint8_t bits[3072];                          // one symbol's sliced bits, one per byte
+  __align__(16) uint8_t nib[1536];             // sliced bits of a symbol pair: A.b0 | A.b1<<1 | B.b0<<2 | B.b1<<3
   uint32_t planes[16][CIF_PLANE_WORDS];        // the CIF being assembled
+  __align__(16) float2 tw2[8][16];             // W128^(u k): stage-2 twiddles (shared by 16 threads each)
   uint64_t full[N_STAGES];
 };
 
@@ -430,38 +559,112 @@ struct FrameSrc {
   uint32_t ring_mode, pos, delta, mod;
 };
 
-// thread 0: start the TMA copies of symbol l into stage buffer `st`
-__device__ __forceinline__ void issue_symbol_load(DemodSmem &sm, const FrameSrc &src, int l, int st) {
+// thread 0: start the TMA copies of symbol l into `buf`; each symbol arrives once on the barrier
+__device__ __forceinline__ void issue_symbol_load(DemodSmem &sm, const FrameSrc &src, int l, uint8_t *buf,
+                                                  uint64_t *bar) {
   const uint32_t off = sym_byte_off(l);
   if (!src.ring_mode) {
-    mbar_expect_tx(&sm.full[st], SYM_BYTES);
-    tma_load_1d(sm.stage[st], src.frame + off, SYM_BYTES, &sm.full[st]);
+    mbar_expect_tx(bar, SYM_BYTES);
+    tma_load_1d(buf, src.frame + off, SYM_BYTES, bar);
     return;
   }
   const bool last = l == 75;  // its second half may be stale: it comes from the tail store
   const uint32_t need = (last ? SYM_BYTES - TAIL_BYTES : SYM_BYTES) + 16u;
   const uint32_t a0 = ring_wrap(src.pos + off, src.mod) & ~15u;
-  mbar_expect_tx(&sm.full[st], need + (last ? TAIL_BYTES : 0u));
+  mbar_expect_tx(bar, need + (last ? TAIL_BYTES : 0u));
   const uint32_t first = min(need, src.mod - a0);
-  tma_load_1d(sm.stage[st], src.ring + a0, first, &sm.full[st]);
-  if (first < need) tma_load_1d(sm.stage[st] + first, src.ring, need - first, &sm.full[st]);
-  if (last) tma_load_1d(sm.tailbuf, src.tail, TAIL_BYTES, &sm.full[st]);
+  tma_load_1d(buf, src.ring + a0, first, bar);
+  if (first < need) tma_load_1d(buf + first, src.ring, need - first, bar);
+  if (last) tma_load_1d(sm.tailbuf, src.tail, TAIL_BYTES, bar);
 }
 
+// 16 samples x[p + 128 j] of symbols A and B -> packed floats carrying a common offset.
+// The reference's sample is (int8)(b - 127) (input_sdr.c:61-62: 255 wraps to -128) = ((b + 1) & 255)
+// - 128.  The byte increment is done on four bytes at once; each byte then becomes the float
+// 32768 + byte by placing it in mantissa bits 8..15 under the exponent of 2^15 (one PRMT, no
+// integer-to-float conversion).  The common offset 32896 (1 + i) only reaches the DC path of the
+// transform, where every operation is an exact integer sum below 2^24; it is taken out again at
+// (k1, k2) = (0, 0) after stage 2 (see below), so all 2048 bins are bit-identical to a transform
+// of the signed samples.
+__device__ __forceinline__ void load_pair(C2 *v, const uint8_t *aLo, const uint8_t *aHi, const uint8_t *bLo,
+                                          const uint8_t *bHi, int p) {
+#pragma unroll
+  for (int j = 0; j < 16; j++) {
+    const uint32_t o = 2u * (uint32_t)(p + 128 * j);
+    const uint32_t ha = *reinterpret_cast<const uint16_t *>((j < 8 ? aLo : aHi) + o);
+    const uint32_t hb = *reinterpret_cast<const uint16_t *>((j < 8 ? bLo : bHi) + o);
+    const uint32_t w = prmt(ha, hb, 0x5410u);  // IA QA IB QB
+    const uint32_t r = (((w & 0x7f7f7f7fu) + 0x01010101u) ^ (w & 0x80808080u));
+    const uint32_t e = 0x47000000u;
+    v[j].re = pku(prmt(r, e, 0x7404u), prmt(r, e, 0x7424u));
+    v[j].im = pku(prmt(r, e, 0x7414u), prmt(r, e, 0x7434u));
+  }
+}
+#define DEMOD_DC_OFFSET 8421376.0f  // 256 samples x (32768 + 128)
+
+// 2048-point forward FFT of a symbol pair by 128 threads, 16 x 16 x 8 as fft2048_from_regs.
+// In: v[j] = x[p + 128 j].  Out: v[m] = bin p + 128 m.  Three barriers; the caller must place one
+// more between this call's last shared-memory read and the next call.
+__device__ __forceinline__ void fft2048_pair(C2 *v, const float2 *tw1, DemodSmem &sm, int p) {
+  pk_t *xre = sm.xre, *xim = sm.xim;
+  dft16p(v);
+#pragma unroll
+  for (int k = 1; k < 16; k++) v[k] = cmul2s(v[k], tw1[k - 1].x, tw1[k - 1].y);
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    xre[k * XCH_PAD + p] = v[k].re;
+    xim[k * XCH_PAD + p] = v[k].im;
+  }
+  __syncthreads();
+  const int u = p >> 4, k1 = p & 15;
+#pragma unroll
+  for (int j = 0; j < 16; j++) v[j] = C2{xre[k1 * XCH_PAD + u + 8 * j], xim[k1 * XCH_PAD + u + 8 * j]};
+  __syncthreads();
+  dft16p(v);
+  {  // remove the input offset where it has accumulated (exact: see load_pair)
+    const pk_t dc = bc(k1 == 0 ? DEMOD_DC_OFFSET : 0.f);
+    v[0].re = sub2(v[0].re, dc);
+    v[0].im = sub2(v[0].im, dc);
+  }
+#pragma unroll
+  for (int k = 1; k < 16; k += 2) {
+    const float4 t = *reinterpret_cast<const float4 *>(&sm.tw2[u][k - 1]);  // factors k-1 (1 for k = 1) and k
+    if (k > 1) v[k - 1] = cmul2s(v[k - 1], t.x, t.y);
+    v[k] = cmul2s(v[k], t.z, t.w);
+  }
+#pragma unroll
+  for (int k = 0; k < 16; k++) {
+    xre[u * 256 + k * 16 + k1] = v[k].re;
+    xim[u * 256 + k * 16 + k1] = v[k].im;
+  }
+  __syncthreads();
+  C2 a[8], b[8];
+#pragma unroll
+  for (int uu = 0; uu < 8; uu++) {
+    a[uu] = C2{xre[uu * 256 + p], xim[uu * 256 + p]};
+    b[uu] = C2{xre[uu * 256 + p + 128], xim[uu * 256 + p + 128]};
+  }
+  dft8p(a);
+  dft8p(b);
+#pragma unroll
+  for (int k3 = 0; k3 < 8; k3++) {
+    v[2 * k3] = a[k3];
+    v[2 * k3 + 1] = b[k3];
+  }
+}
+
+// Grid (segments, streams): segment 0 = PRS + the three FIC symbols, segment c = 1..4 = CIF c-1
+// (its 18 symbols and the one before them).  A CTA walks its symbols two at a time.
 template <bool DEBUG>
-__global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(RingGeom ring, const uint8_t *__restrict__ tails,
-                                                            const uint8_t *__restrict__ frames,
-                                                            const StepCtl *__restrict__ ctl,
-                                                            const SyncOut *__restrict__ sync,
-                                                            uint8_t *__restrict__ fic_bits,
-                                                            uint8_t *__restrict__ cifs,
-                                                            float2 *__restrict__ dbg_sym,
-                                                            float2 *__restrict__ dbg_symd,
-                                                            uint8_t *__restrict__ dbg_bits, int seg_first) {
+__global__ void __launch_bounds__(FFT_THREADS, DEMOD_CTAS_PER_SM)
+    demod_kernel(RingGeom ring, const uint8_t *__restrict__ tails, const uint8_t *__restrict__ frames,
+                 const StepCtl *__restrict__ ctl, const SyncOut *__restrict__ sync, uint8_t *__restrict__ fic_bits,
+                 uint8_t *__restrict__ cifs, float2 *__restrict__ dbg_sym, float2 *__restrict__ dbg_symd,
+                 uint8_t *__restrict__ dbg_bits, int seg_first) {
   extern __shared__ __align__(128) uint8_t smem_raw[];
   DemodSmem &sm = *reinterpret_cast<DemodSmem *>(smem_raw);
   const int p = threadIdx.x;
-  const int s = blockIdx.y, seg = blockIdx.x + seg_first;  // seg 0: PRS + FIC symbols, seg 1..4: CIF seg-1
+  const int s = blockIdx.y, seg = blockIdx.x + seg_first;
   if (!DEBUG) {
     if (!ctl[s].run || sync[s].ok != 1) return;
   }
@@ -475,113 +678,162 @@ __global__ void __launch_bounds__(FFT_THREADS, 4) demod_kernel(RingGeom ring, co
   src.tail = DEBUG ? nullptr : tails + (uint64_t)s * TAIL_BYTES;
   const int l0 = seg == 0 ? 0 : 3 + 18 * (seg - 1);
   const int nsym = seg == 0 ? 4 : 19;
+  const int npair = (nsym + 1) / 2;
 
   if (p == 0) {
-    for (int i = 0; i < N_STAGES; i++) mbar_init(&sm.full[i], 1);
+    for (int i = 0; i < N_STAGES; i++) mbar_init(&sm.full[i], 2);
     fence_barrier_init();
   }
+  sm.tw2[p >> 4][p & 15] = g_tw2048[(16 * (p >> 4) * (p & 15)) & 2047];  // W128^(u k)
   __syncthreads();
+  // pair i = symbols (l0 + 2 i, l0 + 2 i + 1); the last pair of a CIF segment has no second symbol
+  auto issue_pair = [&](int i, int st) {
+    const int la = l0 + 2 * i;
+    issue_symbol_load(sm, src, la, sm.stage[st][0], &sm.full[st]);
+    if (2 * i + 1 < nsym)
+      issue_symbol_load(sm, src, la + 1, sm.stage[st][1], &sm.full[st]);
+    else
+      mbar_expect_tx(&sm.full[st], 0);
+  };
   if (p == 0) {
-    for (int i = 0; i < N_STAGES && i < nsym; i++) issue_symbol_load(sm, src, l0 + i, i);
+    for (int i = 0; i < N_STAGES && i < npair; i++) issue_pair(i, i);
   }
-  FftTwiddles tw;
-  load_twiddles(tw, p);
-  // Thread p ends every FFT with bins p + 128 m.  Carriers are bins 1..768 and 1280..2047, so
-  // m = 0..5 and 10..15 are always carriers (except bin 0 = DC for p = 0), m = 6 only for p = 0
-  // (bin 768), m = 7..9 never.  Slot k = 0..11 <-> m = k (k < 6) or k + 4; slot 12 = bin 768.
-  // The byte position of each carrier's first bit in sm.bits is constant over symbols.
+  float2 tw1[15];  // W2048^(p k), k = 1..15: the same for every symbol
+#pragma unroll
+  for (int k = 1; k < 16; k++) tw1[k - 1] = g_tw2048[(p * k) & 2047];
+  // Thread p ends every FFT with bins p + 128 m.  Carriers are bins 1..768 and 1280..2047: m = 0..5
+  // and 10..15 always (except bin 0 = DC for p = 0) and m = 6 for p = 0 only (bin 768), which takes
+  // the place of thread 0's DC bin: slot k <-> m = k (k < 6) or k + 4.  A carrier's four bits of a
+  // symbol pair go to one byte of sm.nib whose position is constant over symbols: plane order for
+  // the MSC (msc.cuh), n itself for the FIC symbols.
   const bool plane_order = !(seg == 0 || DEBUG);
-  uint16_t pos[13];
+  uint32_t pos[N_SLOTS];
 #pragma unroll
-  for (int k = 0; k < 13; k++) {
-    const int m = k < 6 ? k : (k < 12 ? k + 4 : 6);
-    const uint32_t n = g_bin_dst[p + 128 * m];  // 0xffff on the two non-carrier cases
-    pos[k] = (uint16_t)(n == 0xffffu ? 0xffffu : (plane_order ? (n & 15u) * 192u + (n >> 4) : n));
+  for (int k = 0; k < N_SLOTS; k++) {
+    const int m = k < 6 ? k : k + 4;
+    const uint32_t n = g_bin_dst[(k == 0 && p == 0) ? 768 : p + 128 * m];
+    pos[k] = plane_order ? (n & 15u) * 96u + (n >> 4) : n;
   }
-  const uint32_t second = plane_order ? 96u : 1536u;  // distance from a carrier's bit 0 to its bit 1
-
-  float2 prev[13];
+  float px[N_SLOTS], py[N_SLOTS];  // the previous symbol's carriers
 #pragma unroll
-  for (int k = 0; k < 13; k++) prev[k] = make_float2(0.f, 0.f);
+  for (int k = 0; k < N_SLOTS; k++) px[k] = py[k] = 0.f;
 
-  for (int i = 0; i < nsym; i++) {
-    const int l = l0 + i, st = i % N_STAGES;
-    float2 v[16];
+  for (int i = 0; i < npair; i++) {
+    const int la = l0 + 2 * i, st = i % N_STAGES;
+    const bool b_valid = 2 * i + 1 < nsym;
+    C2 v[16];
     mbar_wait(&sm.full[st], (uint32_t)(i / N_STAGES) & 1u);
-    if (src.ring_mode && l == 75) {
-      const uint16_t *h0 = reinterpret_cast<const uint16_t *>(sm.stage[st] + src.delta);
-      const uint16_t *h1 = reinterpret_cast<const uint16_t *>(sm.tailbuf);
-#pragma unroll
-      for (int j = 0; j < 8; j++) v[j] = iq_to_sample(h0[p + 128 * j]);
-#pragma unroll
-      for (int j = 8; j < 16; j++) v[j] = iq_to_sample(h1[p + 128 * (j - 8)]);
-    } else {
-      load_symbol(v, sm.stage[st] + src.delta, p);
+    {
+      const uint8_t *a = sm.stage[st][0] + src.delta;
+      const uint8_t *b = b_valid ? sm.stage[st][1] + src.delta : a;
+      const uint8_t *ah = a, *bh = b;
+      if (src.ring_mode) {  // symbol 75: samples 1024.. come from the tail store
+        if (la == 75) ah = sm.tailbuf - 2048;
+        if (la + 1 == 75) bh = sm.tailbuf - 2048;
+      }
+      load_pair(v, a, ah, b, bh, p);
     }
-    __syncthreads();  // everyone has consumed the staging buffer -> refill it
-    if (p == 0 && i + N_STAGES < nsym) {
+    fft2048_pair(v, tw1, sm, p);  // (its first barrier also says: staging buffer consumed)
+    if (p == 0 && i + N_STAGES < npair) {
       fence_proxy_async();
-      issue_symbol_load(sm, src, l + N_STAGES, st);
+      issue_pair(i + N_STAGES, st);
     }
-    fft2048_from_regs(v, tw, sm.xch, p);
     if (DEBUG) {
 #pragma unroll
-      for (int m = 0; m < 16; m++) dbg_sym[(size_t)l * 2048 + ((p + 128 * m + 1024) & 2047)] = v[m];
+      for (int m = 0; m < 16; m++) {
+        const int bin = (p + 128 * m + 1024) & 2047;
+        dbg_sym[(size_t)la * 2048 + bin] = make_float2(pk_lo(v[m].re), pk_lo(v[m].im));
+        if (b_valid) dbg_sym[(size_t)(la + 1) * 2048 + bin] = make_float2(pk_hi(v[m].re), pk_hi(v[m].im));
+      }
     }
-    float2 cur[13];
+    // DQPSK against the previous symbol and hard slicing (input_sdr.c:132-158):
+    //   re = Re(s_l conj(s_l-1)),  im' = -Im(s_l conj(s_l-1))   (the reference divides both by
+    //   |s_l-1|^2 > 0, which cannot change a sign);  bit0 = !(re > 0),  bit1 = (im' > 0).
+    // Both are read off sign bits: r = re - tiny is negative exactly when !(re > 0), q = tiny - im'
+    // exactly when im' > 0 (tiny = 1e-30 is far below the rounding unit of any non-zero product of
+    // two spectrum values, so it only decides the case of an exact zero, as `> 0` does).
+    const float tiny = 1e-30f;
 #pragma unroll
-    for (int k = 0; k < 13; k++) cur[k] = v[k < 6 ? k : (k < 12 ? k + 4 : 6)];
-    if (i > 0) {
-      // DQPSK against the previous symbol and hard slicing (input_sdr.c:132-158):
-      //   re = Re(s_l conj(s_l-1)) / |s_l-1|^2 ,  im' = -Im(s_l conj(s_l-1)) / |s_l-1|^2
-      //   bit0 = !(re > 0) ; bit1 = (im' > 0)      (division by a positive number dropped)
+    for (int k = 0; k < N_SLOTS; k++) {
+      const int m = k < 6 ? k : k + 4;
+      C2 c = v[m];
+      if (k == 0) {
+        if (p == 0) c = v[6];
+      }
+      const float xa = pk_lo(c.re), ya = pk_lo(c.im), xb = pk_hi(c.re), yb = pk_hi(c.im);
+      const float ra = fmaf(xa, px[k], fmaf(ya, py[k], -tiny));
+      const float qa = fmaf(ya, px[k], fmaf(-xa, py[k], tiny));
+      const float rb = fmaf(xb, xa, fmaf(yb, ya, -tiny));
+      const float qb = fmaf(yb, xa, fmaf(-xb, ya, tiny));
       if (DEBUG) {
-        // the reference computes the quotient on all 2048 bins; only the carriers are compared
-#pragma unroll
-        for (int k = 0; k < 13; k++) {
-          const int m = k < 6 ? k : (k < 12 ? k + 4 : 6);
-          const float re = cur[k].x * prev[k].x + cur[k].y * prev[k].y;
-          const float imn = cur[k].x * prev[k].y - cur[k].y * prev[k].x;
-          const float den = prev[k].x * prev[k].x + prev[k].y * prev[k].y;
-          dbg_symd[(size_t)l * 2048 + ((p + 128 * m + 1024) & 2047)] = make_float2(re / den, imn / den);
+        const int bin = (((k == 0 && p == 0) ? 768 : p + 128 * m) + 1024) & 2047;
+        {
+          const float da = px[k] * px[k] + py[k] * py[k], db = xa * xa + ya * ya;
+          if (i > 0)
+            dbg_symd[(size_t)la * 2048 + bin] =
+                make_float2((xa * px[k] + ya * py[k]) / da, (xa * py[k] - ya * px[k]) / da);
+          if (b_valid)
+            dbg_symd[(size_t)(la + 1) * 2048 + bin] = make_float2((xb * xa + yb * ya) / db, (xb * ya - yb * xa) / db);
         }
       }
-#pragma unroll
-      for (int k = 0; k < 13; k++) {
-        if (k == 12 && p != 0) continue;  // bin 768 belongs to thread 0 only
-        const float re = cur[k].x * prev[k].x + cur[k].y * prev[k].y;
-        const float imn = cur[k].x * prev[k].y - cur[k].y * prev[k].x;
-        const uint32_t a = pos[k];
-        if (k == 0 && a == 0xffffu) continue;  // bin 0 (DC) of thread 0
-        sm.bits[a] = re > 0.f ? 0 : 1;
-        sm.bits[a + second] = imn > 0.f ? 1 : 0;
-      }
-      __syncthreads();
-      if (DEBUG) {
-        for (int k = p; k < 3072 / 4; k += FFT_THREADS)
-          reinterpret_cast<uint32_t *>(dbg_bits + (size_t)(l - 1) * 3072)[k] = reinterpret_cast<uint32_t *>(sm.bits)[k];
-      } else if (seg == 0) {
-        uint32_t *o = reinterpret_cast<uint32_t *>(fic_bits + (uint64_t)s * 9216 + (size_t)(l - 1) * 3072);
-        for (int k = p; k < 3072 / 4; k += FFT_THREADS) o[k] = reinterpret_cast<uint32_t *>(sm.bits)[k];
-      } else if (p < 96) {
-        // 32 byte-bits -> one plane word; plane m = p / 6, word w = p % 6 of this symbol's 192 bits
-        const uint32_t *b = reinterpret_cast<const uint32_t *>(sm.bits + 32 * p);
-        uint32_t word = 0;
-#pragma unroll
-        for (int k = 0; k < 8; k++) word |= ((b[k] * 0x01020408u) >> 24) << (4 * k);
-        sm.planes[p / 6][(i - 1) * 6 + p % 6] = word;
-      }
-      // the next symbol's slicing must not overwrite sm.bits before it has been read: the
-      // barriers inside fft2048_from_regs of the next iteration order that
+      uint32_t nb = __funnelshift_l(__float_as_uint(qb), 0u, 1);
+      nb = __funnelshift_l(__float_as_uint(rb), nb, 1);
+      nb = __funnelshift_l(__float_as_uint(qa), nb, 1);
+      nb = __funnelshift_l(__float_as_uint(ra), nb, 1);
+      sm.nib[pos[k]] = (uint8_t)nb;
+      px[k] = xb;
+      py[k] = yb;
     }
+    __syncthreads();
+    // rows: symbol A is data symbol la - 1 of the frame, B is la
+    if (!plane_order) {
+      uint8_t *out = DEBUG ? dbg_bits : fic_bits + (uint64_t)s * 9216;
+      const bool a_valid = i > 0;  // the first symbol of a segment is only the phase reference
+      for (int c = p; c < 384; c += FFT_THREADS) {
+        const uint32_t w = reinterpret_cast<const uint32_t *>(sm.nib)[c];
+        if (a_valid) {
+          uint32_t *o = reinterpret_cast<uint32_t *>(out + (size_t)(la - 1) * 3072);
+          o[c] = w & 0x01010101u;
+          o[384 + c] = (w >> 1) & 0x01010101u;
+        }
+        if (b_valid) {
+          uint32_t *o = reinterpret_cast<uint32_t *>(out + (size_t)la * 3072);
+          o[c] = (w >> 2) & 0x01010101u;
+          o[384 + c] = (w >> 3) & 0x01010101u;
+        }
+      }
+    } else if (p < 96) {
+      // 32 carriers' nibbles -> the bit-0 and the bit-1 word of one symbol: plane m, word wq of
+      // the symbol's 96 positions.  (x & 0x01010101 << k) * (0x10204080 >> k) gathers bit k of
+      // four bytes into bits 28..31.
+      const int m = p / 6, r = p % 6, wq = r % 3, ab = r / 3;
+      const uint4 *q = reinterpret_cast<const uint4 *>(sm.nib + m * 96 + 32 * wq);
+      const uint4 q0 = q[0], q1 = q[1];
+      const uint32_t w[8] = {q0.x, q0.y, q0.z, q0.w, q1.x, q1.y, q1.z, q1.w};
+      const uint32_t k0 = 2u * (uint32_t)ab;
+      const uint32_t mask0 = 0x01010101u << k0, mul0 = 0x10204080u >> k0;
+      const uint32_t mask1 = mask0 << 1, mul1 = mul0 >> 1;
+      uint32_t acc0 = 0, acc1 = 0;
 #pragma unroll
-    for (int k = 0; k < 13; k++) prev[k] = cur[k];
+      for (int j = 7; j >= 0; j--) {
+        acc0 = __funnelshift_l((w[j] & mask0) * mul0, acc0, 4);
+        acc1 = __funnelshift_l((w[j] & mask1) * mul1, acc1, 4);
+      }
+      const int d = 2 * i - 1 + ab;  // data symbol of the CIF: A = 2 i - 1, B = 2 i
+      if (d >= 0 && d < 18) {
+        sm.planes[m][d * 6 + wq] = acc0;
+        sm.planes[m][d * 6 + 3 + wq] = acc1;
+      }
+    }
+    // the next pair's slicing must not overwrite sm.nib before it has been read, and its first
+    // exchange must not overwrite sm.xch before this pair's last read: the barrier above and the
+    // barriers inside the next fft2048_pair order both
   }
-  if (!DEBUG && seg > 0) {
+  if (plane_order) {
     __syncthreads();
     uint32_t *o = reinterpret_cast<uint32_t *>(cifs + ctl[s].cif_off[seg - 1]);
-    const uint32_t *src = &sm.planes[0][0];
-    for (int k = p; k < CIF_WORDS; k += FFT_THREADS) o[k] = src[k];
+    const uint32_t *pl = &sm.planes[0][0];
+    for (int k = p; k < CIF_WORDS; k += FFT_THREADS) o[k] = pl[k];
   }
 }
 
