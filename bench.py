@@ -5,15 +5,19 @@
 
 Workload (BASELINE.json configs[2], and configs[4] when N > 1): S = 1024 independent synthetic
 Mode I ensemble streams per GPU (10 UEP/EEP sub-channels, dabtools_b200.synth.reference_ensemble),
-each fed exactly like dab2eti feeds the reference: 262144-byte rtlsdr callbacks.  One *step* is
-three callbacks per stream = 2 transmission frames = 8 ETI frames per stream, run through the whole
-path: FIFO read -> synchronisers -> 76 FFTs + DQPSK + demap -> FIC Viterbi + CRC -> lock state
+each fed exactly like dab2eti feeds the reference: 262144-byte rtlsdr callbacks, run through the
+whole path: FIFO read -> synchronisers -> 76 FFTs + DQPSK + demap -> FIC Viterbi + CRC -> lock state
 machine -> time de-interleave + depuncture -> MSC Viterbi + descramble -> ETI assembly.
+One *step* is one pass over a batch of --tf-per-step (default 128) transmission frames per stream
+(192 callbacks, 512 ETI frames per stream; 51.5 GB of samples at S = 1024), so that the driver's
+20 steps are a timed region of seconds, not milliseconds.  The samples of a step come from a
+24-TF capture per stream that is resident in HBM (9.7 GB) and consumed cyclically.
 
-  value     frames/s with the IQ batch already resident in HBM and the ETI left in HBM
+  value     frames/s with the IQ already resident in HBM and the ETI left in HBM
   e2e       same call path with the IQ in pinned host memory and every ETI frame copied back
   roofline  the FFT/demod kernel (HBM-bound by design; 155 904 algorithmic bytes per ETI frame)
   viterbi   ACS/s and decoded Mbit/s of the MSC Viterbi kernel (issue-bound, not HBM-bound)
+  parity    after the timed passes: randomly chosen streams of the same dataset through the oracle
   cpu_baseline / --impl reference: the unmodified reference (oracle/_ref) on the host cores
 
 Under torchrun (N > 1) every rank decodes its own S streams (weak scaling, no collective on the
@@ -37,9 +41,9 @@ sys.path.insert(0, ROOT)
 
 TF_BYTES = 393216
 CALL_BYTES = 262144
-CALLS_PER_STEP = 3          # 3 x 262144 = 2 TFs
-TFS_PER_STEP = 2
+CALLS_PER_2TF = 3           # 3 x 262144 bytes = 2 transmission frames
 FRAMES_PER_TF = 4
+CAPTURE_TFS = 24            # per-stream capture resident in HBM (36 callbacks), consumed cyclically
 ALGO_BYTES_PER_FRAME = 155904   # 98304 B IQ in + 57600 B demapped bits out
 SETUP_TFS = 18                  # 1 start-up + 10 to lock + 4 to fill the window, plus slack
 
@@ -52,20 +56,42 @@ def peaks():
     return 6650.0, "fallback"
 
 
-def workload_name(S, bits_per_frame, steps_per_frame):
-    return (f"{S} independent Mode I ensemble streams per GPU, 10 UEP/EEP sub-channels "
-            f"({bits_per_frame} decoded bits, {steps_per_frame} trellis steps per ETI frame), "
-            f"fed as 262144-byte callbacks; step = 3 callbacks = 2 TF = 8 ETI frames per stream")
+def bench_config(S, tf_per_step):
+    """`config` of the JSON line -- the same dict in both arms (ours and --impl reference): it names
+    the workload, not how an arm samples it."""
+    return {
+        "workload": (f"BASELINE configs[2]: {S} independent Mode I ensemble streams per GPU, 10 UEP/EEP "
+                     f"sub-channels (24960 decoded bits, 25026 trellis steps, 11 codewords per ETI frame), "
+                     f"30 dB SNR, fed as 262144-byte rtlsdr callbacks"),
+        "streams_per_gpu": S,
+        "tf_per_step_per_stream": tf_per_step,
+        "frames_per_step_per_gpu": S * tf_per_step * FRAMES_PER_TF,
+        "snr_db": 30,
+        "capture": f"{CAPTURE_TFS} TF per stream ({S * CAPTURE_TFS * TF_BYTES / 1e9:.1f} GB per GPU), consumed cyclically",
+        "l2": "every step reads tens of GB of distinct samples, far beyond the 126 MB L2; no explicit flush",
+    }
 
 
-def vit_alu_roofline(lane_steps, lane_bits, ms, clocks):
-    if not ms:
+def cpu_model():
+    try:
+        for line in open("/proc/cpuinfo"):
+            if line.startswith("model name"):
+                return line.split(":", 1)[1].strip()
+    except OSError:
+        pass
+    return "unknown"
+
+
+def ncu_counters(kernel_prefix, grid=None):
+    """Counters of a kernel from the committed `ncu --set full` capture (profiles/ncu_traffic.json,
+    written by tools/summarize_ncu.py): pipe utilisations are hardware counters, not models."""
+    try:
+        d = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["kernels"]
+        rows = [r for k, v in d.items() if k.startswith(kernel_prefix) for r in v
+                if grid is None or r.get("grid") == grid]
+        return rows or None
+    except Exception:
         return None
-    mhz = (clocks or {}).get("sm_max_mhz") or 1965.0
-    peak = 148 * 4 * 0.5 * mhz * 1e6                       # ALU-pipe warp instructions per second
-    achieved = (lane_steps / 32 * 74 + lane_bits / 32 * 10) / (ms * 1e-3)
-    return {"bound": "alu-pipe", "achieved": achieved / 1e9, "peak": peak / 1e9, "unit": "G warp-instr/s",
-            "frac": achieved / peak}
 
 
 def ncu_traffic(kernel_prefix):
@@ -233,54 +259,119 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------
-def cpu_worker(args):
-    """one host core: the reference receive loop over a capture; returns seconds for n1 and n2 TFs"""
-    path, n1, n2, kind = args
+# The reference on the host cores: one receiver (one stream) per worker process, state kept across
+# steps (oracle ref_stream_* / orc_stream_*), so that every step is a bounded sample of the workload
+# in the steady state (locked, interleaver window full) -- exactly where the GPU arm is timed.
+def _ref_worker(conn, path, kind, setup_tfs, seed):
     sys.path.insert(0, ROOT)
     from oracle import oracle
-    dec = oracle.ref() if kind == "reference" else oracle.port()
-    iq = np.load(path, mmap_mode="r")
+    dec = {"reference": oracle.ref, "spiral": oracle.ref_spiral, "port": oracle.port}[kind]()
     devnull = os.open(os.devnull, os.O_WRONLY)
-    os.dup2(devnull, 2)  # the reference prints "Locked" etc.
-    out = []
-    for n in (n1, n2):
-        buf = np.ascontiguousarray(iq[: n * TF_BYTES + CALL_BYTES])
+    os.dup2(devnull, 2)   # the reference prints "Locked", ensemble dumps, ...
+    iq = np.load(path, mmap_mode="r")
+    n_calls = iq.size // CALL_BYTES
+    h = dec.stream_open(200_000_000, seed)
+    pos = 0
+
+    def feed(n_tf):
+        nonlocal pos
+        frames = 0
+        for _ in range(n_tf * CALLS_PER_2TF // 2):
+            c = pos % n_calls
+            k, _e = dec.stream_feed(h, iq[c * CALL_BYTES:(c + 1) * CALL_BYTES], want_eti=False)
+            frames += k
+            pos += 1
+        return frames
+
+    feed(setup_tfs)
+    conn.send(("ready", int(dec.stream_locked(h))))
+    while True:
+        msg = conn.recv()
+        if msg is None:
+            break
         t = time.perf_counter()
-        r = dec.run_iq(buf)
-        out.append((time.perf_counter() - t, int(r["eti"].shape[0])))
-    return out
+        frames = feed(msg)
+        conn.send((time.perf_counter() - t, frames))
+    dec.stream_close(h)
+    conn.close()
 
 
-def cpu_reference_rate(n_procs: int, reps: int = 1, n1: int = 18, n2: int = 40):
-    """steady-state ETI frames/s of the reference on `n_procs` host cores (one stream per core)"""
-    import multiprocessing as mp
-    import torch
-    from dabtools_b200 import synth
+class ReferencePool:
+    """`cores` worker processes, each running the reference receive loop over its own copy of a
+    cyclic capture of the benchmark's ensemble.  step(n_tf) = every worker decodes n_tf more
+    transmission frames; returns (wall seconds, ETI frames of all workers)."""
+
+    def __init__(self, cores, kind, setup_tfs=SETUP_TFS):
+        import multiprocessing as mp
+        from dabtools_b200 import synth
+        ens = synth.reference_ensemble()
+        g = synth.ModeITransmitter(ens, "cpu").generate(1, CAPTURE_TFS, seed=4242, snr_db=30.0)
+        iq = g["iq"][0].numpy()
+        tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False,
+                                          dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
+        np.save(tmp, iq)
+        tmp.close()
+        self.path, self.kind, self.cores = tmp.name, kind, cores
+        ctx = mp.get_context("spawn")
+        self.conns, self.procs = [], []
+        for w in range(cores):
+            a, b = ctx.Pipe()
+            pr = ctx.Process(target=_ref_worker, args=(b, tmp.name, kind, setup_tfs, 1 + w), daemon=True)
+            pr.start()
+            self.conns.append(a)
+            self.procs.append(pr)
+        self.locked = sum(c.recv()[1] for c in self.conns)
+
+    def step(self, n_tf):
+        t = time.perf_counter()
+        for c in self.conns:
+            c.send(n_tf)
+        res = [c.recv() for c in self.conns]
+        return time.perf_counter() - t, sum(r[1] for r in res)
+
+    def close(self):
+        for c in self.conns:
+            try:
+                c.send(None)
+            except Exception:
+                pass
+        for pr in self.procs:
+            pr.join(timeout=10)
+        try:
+            os.unlink(self.path)
+        except OSError:
+            pass
+
+
+def reference_kind():
     from oracle import oracle
-    kind = "reference" if oracle.ref() is not None else "port"
-    ens = synth.reference_ensemble()
-    g = synth.ModeITransmitter(ens, "cpu").generate(1, n2 + 1, seed=4242, snr_db=30.0, tail_samples=CALL_BYTES)
-    iq = g["iq"][0].numpy()
-    tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False, dir="/dev/shm" if os.path.isdir("/dev/shm") else None)
-    np.save(tmp, iq)
-    tmp.close()
-    ctx = mp.get_context("spawn")
-    step_times, rates = [], []
+    return "reference" if oracle.ref() is not None else "port"
+
+
+def cpu_reference_rate(cores, kind, n_steps, tf_per_step, warmup=1):
+    """steady-state ETI frames/s of the reference on `cores` host cores (one stream per core):
+    `n_steps` timed steps of `tf_per_step` transmission frames per core after `warmup` untimed ones"""
+    pool = ReferencePool(cores, kind)
     try:
-        with ctx.Pool(n_procs) as pool:
-            for _ in range(reps):
-                t = time.perf_counter()
-                res = pool.map(cpu_worker, [(tmp.name, n1, n2, kind)] * n_procs)
-                step_times.append(time.perf_counter() - t)
-                # per core: frames gained between the two capture lengths / extra time
-                r = [(b[1] - a[1]) / max(b[0] - a[0], 1e-9) for a, b in res]
-                rates.append(sum(r))
+        for _ in range(warmup):
+            pool.step(tf_per_step)
+        times, frames = [], 0
+        for _ in range(n_steps):
+            dt, f = pool.step(tf_per_step)
+            times.append(dt)
+            frames += f
     finally:
-        os.unlink(tmp.name)
-    return dict(value=float(np.median(rates)), kind=kind, cores=n_procs,
-                sample=f"1 stream x {n2} TFs per core (steady-state rate from the {n1}->{n2} TF difference), "
-                       f"{n_procs} cores, reference ensemble, plain viterbi.c",
-                step_s=float(np.median(step_times)))
+        pool.close()
+    total = sum(times)
+    label = {"reference": "the unmodified reference (oracle/_ref, plain viterbi.c)",
+             "spiral": "the unmodified reference built with its Spiral SSE2 Viterbi (oracle/_ref)",
+             "port": "the oracle port (oracle/dab_oracle.c)"}[kind]
+    return dict(value=frames / total, unit="frames/s", cores=cores, kind="port" if kind == "port" else "reference",
+                per_core=frames / total / cores, cpu_model=cpu_model(), locked_streams=pool.locked,
+                steps=n_steps, step_s=float(np.median(times)), total_s=total, frames=frames,
+                sample=f"{label}: 1 stream per core, {cores} cores, {n_steps} steps x {tf_per_step} TF per core "
+                       f"in the steady state (locked, interleaver window full) of a cyclic {CAPTURE_TFS}-TF "
+                       f"capture of the same ensemble")
 
 
 # ------------------------------------------------------------------------------------------------
@@ -307,7 +398,7 @@ def reduce_over_ranks(times_ms, frames, device, world):
 
 
 def generate_dataset(S, n_tf, device, seed):
-    """[S][n_tf*393216 + pad] uint8 I/Q on `device`, distinct payload and noise per stream"""
+    """[S][n_tf*393216] uint8 I/Q on `device`, distinct payload and noise per stream"""
     import torch
     from dabtools_b200 import synth
     ens = synth.reference_ensemble()
@@ -323,10 +414,66 @@ def generate_dataset(S, n_tf, device, seed):
     return out, ens
 
 
+def parity_check(lib, data, S, n_streams, seed):
+    """BASELINE config 3 parity, outside every timed region: `n_streams` randomly chosen streams of
+    the benchmark's own dataset, decoded (a) by an engine that consumes the capture in place with
+    MSC batches of 2 -- the `value` configuration -- and (b) by an engine fed from host memory with
+    MSC batches of 4 -- the `e2e` configuration --, compared byte for byte with the oracle's receive
+    loop (oracle.port().run_iq) over the same samples."""
+    from oracle import oracle
+    port = oracle.port()
+    n_calls = data.shape[1] // CALL_BYTES
+    rng = np.random.default_rng(seed)
+    chosen = sorted(rng.choice(S, min(n_streams, S), replace=False).tolist())
+
+    def collect(eng, feed):
+        out = {s: [] for s in chosen}
+        for c in range(n_calls):
+            if feed(c):
+                eti, ids = eng.fetch_eti()
+                for s in chosen:
+                    out[s].extend(f.copy() for f in eti[ids == s])
+        if eng.flush():
+            eti, ids = eng.fetch_eti()
+            for s in chosen:
+                out[s].extend(f.copy() for f in eti[ids == s])
+        eng.close()
+        return out
+
+    eng = lib.Engine(S)
+    eng.set_msc_batch(2)
+    eng.attach_capture(data)
+    a = collect(eng, lambda c: eng.feed_capture(CALL_BYTES))
+    host = {s: data[s].cpu().numpy() for s in chosen}
+    import torch
+    pin = torch.empty((S, CALL_BYTES), dtype=torch.uint8, pin_memory=True)
+    eng = lib.Engine(S)
+    eng.set_msc_batch(4)
+
+    def feed_host(c):
+        pin.copy_(data[:, c * CALL_BYTES:(c + 1) * CALL_BYTES])
+        torch.cuda.synchronize()
+        return eng.feed_iq(pin.numpy())
+
+    b = collect(eng, feed_host)
+    frames = 0
+    for s in chosen:
+        want = port.run_iq(host[s][: n_calls * CALL_BYTES])["eti"]
+        for name, got in (("capture/batch2", a[s]), ("host/batch4", b[s])):
+            got = np.array(got, dtype=np.uint8).reshape(-1, 6144)
+            if got.shape != want.shape or not np.array_equal(got, want):
+                raise RuntimeError(f"parity: stream {s} ({name}): ETI differs from the oracle "
+                                   f"({got.shape[0]} vs {want.shape[0]} frames)")
+        frames += want.shape[0]
+    return {"parity_checked_streams": len(chosen), "streams": chosen, "eti_frames_compared": frames,
+            "engines": ["attach_capture + msc_batch 2 (value path)", "host feed_iq + msc_batch 4 (e2e path)"],
+            "against": "oracle.port().run_iq on the same samples", "result": "byte-identical"}
+
+
 def run_ours(args, rank, world, local_rank):
     import torch
     import torch.distributed as dist
-    from dabtools_b200 import lib
+    from dabtools_b200 import lib, synth
 
     numa = bind_to_gpu_numa_node(local_rank)
     torch.cuda.set_device(local_rank)
@@ -334,53 +481,47 @@ def run_ours(args, rank, world, local_rank):
     lib.check(lib.load().dabgpu_set_device(local_rank))
     lib.use_torch_stream()
     S, K, W = args.streams, args.steps, args.warmup
-    setup_steps = SETUP_TFS // TFS_PER_STEP
-    k_e2e = min(K, args.e2e_steps)
-    k_e2e = max(2, k_e2e - k_e2e % 2)   # whole MSC batches (4 TF = 2 steps) inside the timed window
-    k_timing = min(K, 8)
-    n_steps_total = setup_steps + max(W + K + k_timing, 3 + K) + 1
-    n_tf = n_steps_total * TFS_PER_STEP
+    TFS = args.tf_per_step
+    TFS += TFS % 2
+    calls_per_step = TFS // 2 * CALLS_PER_2TF
+    setup_calls = SETUP_TFS // 2 * CALLS_PER_2TF
+    cap_calls = CAPTURE_TFS // 2 * CALLS_PER_2TF
     t_gen = time.time()
-    data, ens = generate_dataset(S, n_tf, dev, seed=1 + rank)
+    data, ens = generate_dataset(S, CAPTURE_TFS, dev, seed=1 + rank)
     torch.cuda.synchronize()
     t_gen = time.time() - t_gen
-    step_bytes = CALLS_PER_STEP * CALL_BYTES
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step_device(eng, i):
-        n = 0
-        for c in range(CALLS_PER_STEP):
-            off = i * step_bytes + c * CALL_BYTES
-            n += eng.feed_iq_device(data[:, off: off + CALL_BYTES])
-        return n
+    def chunk(c):
+        off = (c % cap_calls) * CALL_BYTES
+        return data[:, off: off + CALL_BYTES]
 
     # ---------------- device-resident throughput (value) ----------------
     # The samples are resident in HBM before the timed region.  With --ingest capture (default) the
-    # engine consumes them in place (dabgpu_engine_attach_capture / feed_capture); with --ingest copy
-    # every callback is first copied into the engine's own FIFO ring (dabgpu_engine_feed_iq).
+    # engine consumes them in place (dabgpu_engine_attach_capture / feed_capture, cyclic); with
+    # --ingest copy every callback is first copied into the engine's own FIFO ring (feed_iq).
     capture = args.ingest == "capture"
 
     def measure_value():
-        """set-up, warm-up and the timed region on a fresh engine; returns everything the report needs"""
         eng = lib.Engine(S)
         eng.set_msc_batch(args.msc_batch)
         if capture:
             eng.attach_capture(data)
+            eng.set_capture_cyclic(True)
+        fed = [0]
 
-        def step_value(i):
-            if not capture:
-                return step_device(eng, i)
-            n = 0
-            for c in range(CALLS_PER_STEP):
-                n += eng.feed_capture(CALL_BYTES)
-            return n
+        def feed_calls(n):
+            frames = 0
+            for _ in range(n):
+                frames += eng.feed_capture(CALL_BYTES) if capture else eng.feed_iq_device(chunk(fed[0]))
+                fed[0] += 1
+            return frames
 
-        for i in range(setup_steps):
-            step_value(i)
+        feed_calls(setup_calls)
         locked = sum(eng.status(s).locked for s in range(S))
         if locked != S:
             raise RuntimeError(f"only {locked}/{S} streams locked after set-up")
@@ -389,10 +530,9 @@ def run_ours(args, rank, world, local_rank):
             sampler.start()
         n = 0
         for i in range(W):
-            n += step_value(setup_steps + i)
-        assert n >= S * TFS_PER_STEP * FRAMES_PER_TF * (W - 2), f"steady state not reached: {n} frames in warm-up"
-        # start from an empty pipeline so that the frames counted are exactly the frames fed
-        eng.flush()
+            n += feed_calls(calls_per_step)
+        assert n >= S * FRAMES_PER_TF * (W * TFS - 4), f"steady state not reached: {n} frames in warm-up"
+        eng.flush()   # start from an empty pipeline so that the frames counted are exactly the frames fed
         eng.join()
         launches0 = lib.launch_count()
         host_t0 = eng.host_times()
@@ -401,9 +541,8 @@ def run_ours(args, rank, world, local_rank):
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
         frames = 0
-        base = setup_steps + W
         for i in range(K):
-            frames += step_value(base + i)
+            frames += feed_calls(calls_per_step)
         frames += eng.flush()   # frames still queued for a deferred MSC batch belong to these steps
         eng.join()              # ... and so does the MSC stream's last batch
         e1.record()
@@ -413,7 +552,8 @@ def run_ours(args, rank, world, local_rank):
         ms = e0.elapsed_time(e1)
         launches = lib.launch_count() - launches0
         host_t = eng.host_times()
-        return dict(eng=eng, ms=ms, frames=frames, clocks=clocks, launches=launches, host_t=host_t, host_t0=host_t0)
+        eng.close()
+        return dict(ms=ms, frames=frames, clocks=clocks, launches=launches, host_t=host_t, host_t0=host_t0)
 
     res = measure_value()
     # a run that saw thermal / hardware slowdown is rejected and measured again, once
@@ -426,29 +566,22 @@ def run_ours(args, rank, world, local_rank):
         dist.broadcast(redo, src=0)
     if int(redo.item()):
         rejected = res["clocks"]
-        res["eng"].close()
         res = measure_value()
         if rank == 0 and res["clocks"] is not None:
             res["clocks"]["rejected_first_run"] = rejected
-    eng, ms, frames, clocks, launches = res["eng"], res["ms"], res["frames"], res["clocks"], res["launches"]
+    ms, frames, clocks, launches = res["ms"], res["frames"], res["clocks"], res["launches"]
     host_t, host_t0 = res["host_t"], res["host_t0"]
-    base = setup_steps + W
-    if capture:   # the per-kernel pass below times the copying path (it has the ingest kernel)
-        eng.close()
-        del eng
-        eng = lib.Engine(S)
-        eng.set_msc_batch(args.msc_batch)
-        for i in range(setup_steps + W + K):
-            step_device(eng, i)
 
-    # ---------------- per-kernel timing pass (same engine, next K steps) ----------------
+    # ---------------- per-kernel timing pass (copying path: it has the ingest kernel) ----------------
+    k_timing = 8
+    eng = lib.Engine(S)
+    eng.set_msc_batch(args.msc_batch)
+    for c in range(setup_calls + 6):
+        eng.feed_iq_device(chunk(c))
     eng.enable_timing(True)
-    steps0 = eng.trellis_steps()
-    base += K
-    for i in range(k_timing):
-        step_device(eng, base + i)
+    for c in range(setup_calls + 6, setup_calls + 6 + k_timing * CALLS_PER_2TF):
+        eng.feed_iq_device(chunk(c))
     kt = eng.kernel_times()
-    msc_steps = None
     eng.enable_timing(False)
     eng.close()
     del eng
@@ -456,38 +589,41 @@ def run_ours(args, rank, world, local_rank):
     # ---------------- end to end: pinned host IQ in, ETI out to host ----------------
     eng = lib.Engine(S)
     eng.set_msc_batch(args.e2e_msc_batch)
-    for i in range(setup_steps):
-        step_device(eng, i)
-    w_e2e, c_e2e = 2, 1   # warm-up and cool-down steps around the timed ones, all through the host path
-    n_e2e = w_e2e + k_e2e + c_e2e
-    host_in = torch.empty((n_e2e, CALLS_PER_STEP, S, CALL_BYTES), dtype=torch.uint8, pin_memory=True)
-    for i in range(n_e2e):
-        for c in range(CALLS_PER_STEP):
-            off = (setup_steps + i) * step_bytes + c * CALL_BYTES
-            host_in[i, c].copy_(data[:, off: off + CALL_BYTES])
+    for c in range(setup_calls):
+        eng.feed_iq_device(chunk(c))
+    host_cap = torch.empty((cap_calls, S, CALL_BYTES), dtype=torch.uint8, pin_memory=True)
+    for c in range(cap_calls):
+        host_cap[c].copy_(chunk(c))
+    torch.cuda.synchronize()
     host_out_t = torch.empty((S * FRAMES_PER_TF * (args.e2e_msc_batch + 1), 6144), dtype=torch.uint8,
                              pin_memory=True)
     host_out = host_out_t.numpy()
-    calls = [host_in[i, c].numpy() for i in range(n_e2e) for c in range(CALLS_PER_STEP)]
+    host_calls = [host_cap[c].numpy() for c in range(cap_calls)]
+    e2e_tfs = args.e2e_tfs - args.e2e_tfs % (2 * args.e2e_msc_batch)   # whole MSC batches in the window
+    w_calls, c_calls = 2 * CALLS_PER_2TF * args.e2e_msc_batch // 2, CALLS_PER_2TF
+    t_calls = e2e_tfs // 2 * CALLS_PER_2TF
+    n_calls_e2e = w_calls + t_calls + c_calls
     AHEAD = 2   # uploads in flight ahead of the callback being processed
 
     # Public API, software-pipelined.  The timed callbacks sit between warm-up and cool-down
     # callbacks that are fed the same way, so the timed window starts and ends in the same pipeline
     # state (uploads in flight at both ends) and holds exactly its own share of the work: 4 ETI
-    # frames per transmission frame and stream, k_e2e steps' worth.
-    first_timed = w_e2e * CALLS_PER_STEP
-    last_timed = first_timed + k_e2e * CALLS_PER_STEP
+    # frames per transmission frame and stream.
+    def call(k):
+        return host_calls[(setup_calls + k) % cap_calls]
+
+    first_timed, last_timed = w_calls, w_calls + t_calls
     f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     d2h = 0
-    for k in range(min(AHEAD, len(calls))):
-        eng.submit_iq(calls[k])
-    for k in range(len(calls)):
+    for k in range(min(AHEAD, n_calls_e2e)):
+        eng.submit_iq(call(k))
+    for k in range(n_calls_e2e):
         if k == first_timed:
             if world > 1:
                 dist.barrier()
             f0.record()
-        if k + AHEAD < len(calls):
-            eng.submit_iq(calls[k + AHEAD])
+        if k + AHEAD < n_calls_e2e:
+            eng.submit_iq(call(k + AHEAD))
         n = eng.feed_submitted()
         if n:
             eng.fetch_eti(host_out)
@@ -499,18 +635,18 @@ def run_ours(args, rank, world, local_rank):
         eng.fetch_eti(host_out)
     barrier()
     e2e_ms = f0.elapsed_time(f1)
-    e2e_frames = k_e2e * TFS_PER_STEP * FRAMES_PER_TF * S
+    e2e_frames = e2e_tfs * FRAMES_PER_TF * S
     # spot check: the frames really are ETI (sync word, padding) -- guards against timing nothing
     assert host_out[0, 0] == 0xFF and host_out[0, 1] in (0x07, 0xF8) and host_out[0, -1] == 0x55
     eng.close()
+    del host_cap, host_calls
 
     # ---------------- BASELINE config 2: FIC-only decode, 16384 groups, device resident ----------------
     fic_cfg = None
     if rank == 0:
         n_grp = 16384
-        g = torch.Generator(device=dev)
-        g.manual_seed(2)
-        fic_bits = torch.randint(0, 2, (n_grp, 2304), generator=g, device=dev, dtype=torch.uint8)
+        fic_np, sent = synth.fic_groups(n_grp, seed=2)     # 1/4 clean, 3/4 at 1 / 4 / 8 % bit flips
+        fic_bits = torch.from_numpy(fic_np).to(dev)
         fibs = torch.zeros((n_grp, 96), dtype=torch.uint8, device=dev)
         okf = torch.zeros((n_grp, 3), dtype=torch.uint8, device=dev)
         for _ in range(3):
@@ -518,15 +654,35 @@ def run_ours(args, rank, world, local_rank):
         torch.cuda.synchronize()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         c0.record()
-        for _ in range(10):
+        for _ in range(20):
             lib.fic_decode_batch_device(fic_bits, fibs, okf)
         c1.record()
         torch.cuda.synchronize()
-        fic_ms = c0.elapsed_time(c1) / 10
+        fic_ms = c0.elapsed_time(c1) / 20
         fic_cfg = {"groups": n_grp, "ms_per_batch": fic_ms, "decoded_mbit_s": n_grp * 768 / fic_ms / 1e3,
                    "acs_per_s": n_grp * 774 * 64 / (fic_ms * 1e-3),
+                   "input": "dabtools_b200.synth.fic_groups(16384, seed=2): 1/4 clean, 3/4 with 1 / 4 / 8 % bit flips",
                    "note": "depuncture + Viterbi + descramble + FIB CRC of 16384 FIC groups (BASELINE configs[1])"}
+        if not args.no_parity:
+            # outside the timed loop: every FIB and CRC flag against the oracle (fic.c:185-206)
+            from oracle import oracle
+            port = oracle.port()
+            got_f, got_ok = fibs.cpu().numpy(), okf.cpu().numpy()
+            for g in range(0, n_grp, 4):
+                f, c, _ = port.fic_decode(fic_np[g:g + 4].reshape(-1))
+                if not (np.array_equal(f.reshape(4, 96), got_f[g:g + 4]) and
+                        np.array_equal(c.reshape(4, 3), got_ok[g:g + 4])):
+                    raise RuntimeError(f"fic_only: group {g} differs from the oracle")
+            assert np.array_equal(got_f[: n_grp // 4], sent[: n_grp // 4])
+            fic_cfg["parity"] = f"all {n_grp} groups (FIBs and CRC flags) byte-identical with oracle.port().fic_decode"
+            fic_cfg["crc_ok_rate_per_quarter"] = [float(got_ok[q * n_grp // 4:(q + 1) * n_grp // 4].mean())
+                                                  for q in range(4)]
         del fic_bits, fibs, okf
+
+    # ---------------- BASELINE config 3 parity on this very dataset ----------------
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = parity_check(lib, data, S, args.parity_streams, seed=7)
 
     # ---------------- reduce over ranks ----------------
     (ms_max, e2e_ms_max), (frames_all, e2e_frames_all) = reduce_over_ranks(
@@ -544,6 +700,9 @@ def run_ours(args, rank, world, local_rank):
     vit_ms = vit["ms"] / max(vit["launches"], 1)
     msc_steps_per_launch = (ens.steps_per_frame - 774) * frames_per_msc
     msc_bits_per_launch = (ens.bits_per_frame - 768) * frames_per_msc
+    demod_ncu = ncu_counters("demod_kernel")
+    vit_ncu = ncu_counters("viterbi_kernel")
+    step_frames = S * TFS * FRAMES_PER_TF
     out = {
         "metric": "ETI frames/s (Mode I)",
         "value": frames_all / (ms_max * 1e-3),
@@ -557,18 +716,18 @@ def run_ours(args, rank, world, local_rank):
         "vs_baseline": None,
         "dtype": "u8 in / fp32 FFT / u8 path metrics",
         "data": "synthetic",
-        "config": {
-            "workload": workload_name(S, ens.bits_per_frame, ens.steps_per_frame),
-            "streams_per_gpu": S,
-            "frames_per_step": S * TFS_PER_STEP * FRAMES_PER_TF * world,
-            "snr_db": 30,
+        "config": bench_config(S, TFS),
+        "run": {
+            "timed_region_s": ms_max / 1e3,
+            "frames_per_step": step_frames * world,
             "msc_batch_tf": args.msc_batch,
-            "ingest": ("in place: dabgpu_engine_attach_capture + feed_capture (the samples are consumed where they lie)"
-                       if args.ingest == "capture" else
+            "ingest": ("in place: dabgpu_engine_attach_capture + feed_capture, cyclic (the samples are consumed "
+                       "where they lie)" if capture else
                        "copy: dabgpu_engine_feed_iq (every callback is copied into the engine's FIFO ring first)"),
-            "timing": f"CUDA events, max over ranks; inputs ({S * step_bytes / 1e6:.0f} MB per step, distinct every "
-                      f"step) exceed the 126 MB L2, no explicit flush",
-            "kernel_timing": f"per-kernel CUDA events over the {k_timing} steps following the timed region, engine streams serialised so that each kernel runs alone",
+            "timing": "CUDA events around the K steps (pipeline empty at both ends: flush + join), barrier + "
+                      "synchronize on both sides, max over ranks",
+            "kernel_timing": f"per-kernel CUDA events over {k_timing} x 2 TF following a set-up on a second engine, "
+                             "engine streams serialised so that each kernel runs alone",
             "dataset_gen_s": round(t_gen, 1),
             "numa_binding": numa,
         },
@@ -577,11 +736,15 @@ def run_ours(args, rank, world, local_rank):
         "e2e": {
             "value": e2e_frames_all / (e2e_ms_max * 1e-3),
             "unit": "frames/s",
-            "h2d_bytes_per_step": S * step_bytes,
-            "d2h_bytes_per_step": int(d2h / max(k_e2e, 1)),
-            "steps": k_e2e,
+            "h2d_bytes_per_step": S * calls_per_step * CALL_BYTES,
+            "d2h_bytes_per_step": int(d2h * TFS / max(e2e_tfs, 1)),
+            "timed_tf_per_stream": e2e_tfs,
+            "timed_region_s": e2e_ms_max / 1e3,
+            "steps": e2e_tfs / TFS,
             "msc_batch_tf": args.e2e_msc_batch,
-            "api": "dabgpu_engine_submit_iq / feed_submitted / fetch_eti (uploads run two callbacks ahead)",
+            "api": "dabgpu_engine_submit_iq / feed_submitted / fetch_eti from pinned host memory (uploads run two "
+                   "callbacks ahead); h2d/d2h bytes are per step of `config`, the timed window is "
+                   "timed_tf_per_stream transmission frames per stream",
         },
         "roofline": {
             "kernel": "demod_kernel (FFT2048 x76 + DQPSK + freq de-interleave + slicing)",
@@ -592,39 +755,51 @@ def run_ours(args, rank, world, local_rank):
             "frac": achieved / hbm_peak,
             "frac_of_nominal_8tbs": achieved / 8000.0,
             # demod is launched as two grids per frame (FIC symbols, CIF symbols): both together
-            "traffic": ncu_traffic("demod_kernel"),
+            "traffic": sum(r["dram_bytes_per_launch"] for r in demod_ncu) if demod_ncu else None,
             "traffic_source": "profiles/ncu_traffic.json (ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum)",
             "peak_source": peak_src,
-            "note": "the HBM-bound kernel of the path; the longest kernel (viterbi_kernel) is bound by the integer "
-                    "ALU pipe, see `viterbi`",
+            "note": "designed HBM-bound (155 904 algorithmic bytes per ETI frame); in practice bound by the "
+                    "shared-memory data pipe of the FFT exchanges (see ncu)",
             "ms_per_launch": demod_ms,
             "algorithmic_bytes_per_launch": ALGO_BYTES_PER_FRAME * frames_per_demod,
+            "ncu": demod_ncu,
         },
         "viterbi": {
             "kernel": "viterbi_kernel (MSC)",
             "ms_per_launch": vit_ms,
             "acs_per_s": 64.0 * msc_steps_per_launch / (vit_ms * 1e-3) if vit_ms > 0 else 0.0,
             "decoded_mbit_s": msc_bits_per_launch / (vit_ms * 1e-3) / 1e6 if vit_ms > 0 else 0.0,
-            # integer-ALU-pipe roofline: 74 ALU-pipe instructions per 64-state warp step (LOP3 32, PRMT 24,
-            # IADD3 16, SHF 2: SASS count) + 10 per traced-back bit; the pipe issues one warp instruction
-            # per 2 cycles per SM sub-partition
-            "alu_pipe": vit_alu_roofline(msc_steps_per_launch, msc_bits_per_launch, vit_ms, clocks),
+            "ncu": vit_ncu,   # ALU-pipe / issue-slot utilisation: hardware counters of the committed capture
         },
         "fic_only": fic_cfg,
-        "host_ms_per_step": {k: (host_t[k] - host_t0[k]) / 1e3 / K for k in host_t},
+        "parity": parity,
+        "host_ms_per_2tf": {k: (host_t[k] - host_t0[k]) / 1e3 / (K * TFS / 2) for k in host_t},
         "kernel_ms_per_launch": {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in kt.items()},
     }
     return out
 
 
 def run_reference(args, rank, world):
-    """--impl reference: the unmodified reference (oracle/_ref) on all host cores, same metric."""
+    """--impl reference: the unmodified reference (oracle/_ref) on all host cores, same metric and
+    config; every step is a bounded sample of the workload (REF_TF_PER_STEP transmission frames per
+    core in the steady state).  Nothing of the product is imported or mapped here."""
     if rank != 0:
         return None
+    os.environ["DABGPU_FORBID_LOAD"] = "1"   # inherited by the workers: libdabgpu.so stays unmapped
     cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     K, W = args.steps, args.warmup
-    n2 = int(os.environ.get("DABGPU_BENCH_REF_TFS", "40"))   # (tests shorten the sample)
-    r = cpu_reference_rate(cores, reps=max(1, min(K + W, 3)), n2=max(n2, 20))
+    tf = int(os.environ.get("DABGPU_BENCH_REF_TFS", str(args.ref_tf_per_step)))
+    tf += tf % 2
+    kind = reference_kind()
+    t_wall = time.perf_counter()
+    r = cpu_reference_rate(cores, kind, n_steps=K, tf_per_step=tf, warmup=W)
+    extra = {}
+    if not args.no_spiral and kind == "reference":
+        try:
+            sp = cpu_reference_rate(cores, "spiral", n_steps=max(2, min(K, 5)), tf_per_step=tf, warmup=min(W, 1))
+            extra["spiral_sse2"] = {k: sp[k] for k in ("value", "unit", "cores", "per_core", "steps", "sample")}
+        except Exception as ex:
+            extra["spiral_sse2"] = {"value": None, "error": str(ex)}
     return {
         "impl": "reference",
         "metric": "ETI frames/s (Mode I)",
@@ -633,19 +808,21 @@ def run_reference(args, rank, world):
         "n_gpus": world,
         "steps": K,
         "warmup": W,
-        "ms_per_step": r["step_s"] * 1e3,
+        "ms_per_step": r["total_s"] * 1e3 / max(K, 1),
         "higher_is_better": True,
         "scaling": "weak",
         "vs_baseline": None,
         "dtype": "u8 in / f64 FFT / long path metrics",
         "data": "synthetic",
-        "config": {"workload": workload_name(args.streams, 24960, 25026),
-                   "reference_arm": "the unmodified reference receive loop (sdr_demod -> dab_process_frame, compiled "
-                                    "from /root/reference/src into oracle/_ref) on a bounded sample of that "
-                                    "workload, one stream per host core: " + r["sample"]},
-        "cpu_baseline": {"value": r["value"], "unit": "frames/s", "cores": r["cores"], "kind": r["kind"],
-                         "sample": r["sample"]},
+        "config": bench_config(args.streams, args.tf_per_step + args.tf_per_step % 2),
+        "run": {"timed_region_s": r["total_s"], "wall_s": time.perf_counter() - t_wall,
+                "frames_per_step": r["frames"] / max(K, 1), "tf_per_step_per_core": tf,
+                "reference_arm": "the unmodified reference receive loop (sdr_demod -> dab_process_frame, compiled "
+                                 "from /root/reference/src into oracle/_ref) on the host cores; every step is a "
+                                 "bounded sample of the workload of `config`: " + r["sample"]},
+        "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "per_core", "cpu_model", "sample")},
         "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        **extra,
     }
 
 
@@ -655,7 +832,10 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--streams", type=int, default=1024, help="ensemble streams per GPU")
-    ap.add_argument("--e2e-steps", type=int, default=8, help="steps of the pinned-host pass (pinned memory bound)")
+    ap.add_argument("--tf-per-step", type=int, default=128,
+                    help="transmission frames per stream and step (one step = one pass over that batch)")
+    ap.add_argument("--e2e-tfs", type=int, default=288,
+                    help="transmission frames per stream in the timed window of the pinned-host pass")
     ap.add_argument("--msc-batch", type=int, default=2,
                     help="transmission frames per MSC Viterbi launch (dabgpu_engine_set_msc_batch)")
     ap.add_argument("--e2e-msc-batch", type=int, default=4,
@@ -663,6 +843,11 @@ def main():
     ap.add_argument("--ingest", default="capture", choices=["capture", "copy"],
                     help="device-resident pass: consume the samples in place, or copy each callback into the FIFO ring")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--ref-tf-per-step", type=int, default=8,
+                    help="reference arm / cpu_baseline: transmission frames per core and step")
+    ap.add_argument("--parity-streams", type=int, default=8)
+    ap.add_argument("--no-parity", action="store_true")
+    ap.add_argument("--no-spiral", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
@@ -693,9 +878,13 @@ def main():
         if not args.no_cpu_baseline:
             cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
             try:
-                r = cpu_reference_rate(cores)
-                out["cpu_baseline"] = {"value": r["value"], "unit": "frames/s", "cores": r["cores"],
-                                       "kind": r["kind"], "sample": r["sample"]}
+                kind = reference_kind()
+                r = cpu_reference_rate(cores, kind, n_steps=3, tf_per_step=args.ref_tf_per_step)
+                out["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "per_core", "cpu_model",
+                                                         "sample")}
+                if kind == "reference" and not args.no_spiral:
+                    sp = cpu_reference_rate(cores, "spiral", n_steps=3, tf_per_step=args.ref_tf_per_step)
+                    out["cpu_baseline"]["spiral_sse2"] = {k: sp[k] for k in ("value", "per_core", "sample")}
             except Exception as ex:  # the baseline is reported context, never the product path
                 out["cpu_baseline"] = {"value": None, "unit": "frames/s", "cores": cores, "kind": "unavailable",
                                        "sample": f"failed: {ex}"}

@@ -18,6 +18,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "libdabgpu.so")
+TABLES_LIB = os.path.join(HERE, "libdabtables.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 
 NVCC_FLAGS = [
@@ -57,8 +58,19 @@ def build_variant(name: str, extra_flags: list[str]) -> str:
     return lib
 
 
+def build_tables(force: bool = False) -> str:
+    """libdabtables.so: the dabgpu_tab_* accessors alone, host-only (gcc, no CUDA); see csrc/tables_host.c"""
+    src = os.path.join(CSRC, "tables_host.c")
+    hdr = os.path.join(HERE, "..", "include", "dabgpu_tables.h")
+    if force or _newer([src, hdr], TABLES_LIB):
+        subprocess.check_call([os.environ.get("CC", "gcc"), "-O2", "-fPIC", "-shared", "-fvisibility=hidden",
+                               "-std=gnu11", "-o", TABLES_LIB, src])
+    return TABLES_LIB
+
+
 def build(force: bool = False, verbose: bool = False) -> str:
     os.makedirs(OBJ, exist_ok=True)
+    build_tables(force)
     sources = sorted(glob.glob(os.path.join(CSRC, "*.cu")))
     headers = sorted(glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(CSRC, "*.h")) +
                      glob.glob(os.path.join(HERE, "..", "include", "*.h")))

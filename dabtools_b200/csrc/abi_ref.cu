@@ -438,7 +438,7 @@ DABGPU_EXPORT int32_t sdr_read_fifo(CircularBuffer *fifo, uint32_t bytes, int32_
 
 // ---- sdr_sync.h:28-31 ------------------------------------------------------------------------------------------
 namespace {
-int sync_single(int mode, const void *host_in, size_t in_bytes, int force, int *ires, float *fres) {
+int sync_single(int mode, const void *host_in, size_t in_bytes, int force, int *ires, double *fres) {
   int rc;
   if ((rc = ensure_device_ready())) return rc;
   std::lock_guard<std::mutex> lk(g_ref.mu);
@@ -446,13 +446,13 @@ int sync_single(int mode, const void *host_in, size_t in_bytes, int force, int *
   if ((rc = g_ref.in.reserve(in_bytes))) return rc;
   if ((rc = g_ref.aux.reserve(64))) return rc;
   CUDA_TRY(cudaMemcpyAsync(g_ref.in.p, host_in, in_bytes, cudaMemcpyHostToDevice, st));
-  if ((rc = launch_sync_single(mode, g_ref.in.p, force, g_ref.aux.as<int>(), g_ref.aux.as<float>() + 1, st)))
+  if ((rc = launch_sync_single(mode, g_ref.in.p, force, g_ref.aux.as<int>(), g_ref.aux.as<double>() + 1, st)))
     return rc;
-  int32_t res[2];
-  CUDA_TRY(cudaMemcpyAsync(res, g_ref.aux.p, 8, cudaMemcpyDeviceToHost, st));
+  int64_t res[2];
+  CUDA_TRY(cudaMemcpyAsync(res, g_ref.aux.p, 16, cudaMemcpyDeviceToHost, st));
   CUDA_TRY(cudaStreamSynchronize(st));
-  *ires = res[0];
-  memcpy(fres, &res[1], 4);
+  *ires = (int)(int32_t)res[0];
+  memcpy(fres, &res[1], 8);
   return DABGPU_OK;
 }
 std::vector<float> to_float2(const fftw_complex *x, size_t n) {
@@ -468,7 +468,7 @@ std::vector<float> to_float2(const fftw_complex *x, size_t n) {
 DABGPU_EXPORT uint32_t dab_coarse_time_sync(int8_t *real, float *filt, uint8_t force_timesync) {
   (void)filt;  // scratch in the reference; the sliding sums live in registers here
   int r = 0;
-  float f;
+  double f;
   if (sync_single(0, real, 196608, force_timesync, &r, &f)) report("dab_coarse_time_sync");
   return (uint32_t)r;
 }
@@ -476,14 +476,14 @@ DABGPU_EXPORT int32_t dab_fine_time_sync(fftw_complex *frame) {
   // needs frame[3160 .. 3160+2048)
   std::vector<float> f = to_float2(frame, 2656 + 504 + 2048);
   int r = 0;
-  float x;
+  double x;
   if (sync_single(1, f.data(), f.size() * 4, 0, &r, &x)) report("dab_fine_time_sync");
   return r;
 }
 DABGPU_EXPORT int32_t dab_coarse_freq_sync_2(fftw_complex *symbols) {
   std::vector<float> f = to_float2(symbols, 2048);
   int r = 0;
-  float x;
+  double x;
   if (sync_single(2, f.data(), f.size() * 4, 0, &r, &x)) report("dab_coarse_freq_sync_2");
   return r;
 }
@@ -491,9 +491,9 @@ DABGPU_EXPORT double dab_fine_freq_corr(fftw_complex *dab_frame, int32_t fine_ti
   (void)fine_timeshift;  // overwritten with 0 by the reference (sdr_sync.c:270)
   std::vector<float> f = to_float2(dab_frame, 2656 + 2048 + 504);
   int r = 0;
-  float x = 0;
+  double x = 0;
   if (sync_single(3, f.data(), f.size() * 4, 0, &r, &x)) report("dab_fine_freq_corr");
-  return (double)x;
+  return x;
 }
 
 // ---- input_sdr.h:43-44 -------------------------------------------------------------------------------------------
@@ -501,8 +501,9 @@ DABGPU_EXPORT void sdr_init(struct sdr_state_t *sdr) {
   cbInit(&sdr->fifo, 196608 * 2 * 4);
   sdr->coarse_timeshift = 0;
   sdr->fine_timeshift = 0;
-  // the reference fftw_malloc()s these and dab2eti never frees them; they are kept so that code
-  // poking at sdr_state_t finds valid pointers, but the GPU path does not fill them
+  // the reference fftw_malloc()s these and dab2eti never frees them; sdr_demod fills dab_frame and
+  // symbols_d like the reference, the PRS scratch arrays stay zero (they are locals of the
+  // synchroniser kernels here)
   sdr->dab_frame = (fftw_complex *)calloc(196608, sizeof(fftw_complex));
   sdr->prs_ifft = (fftw_complex *)calloc(2048 + 32, sizeof(fftw_complex));
   sdr->prs_conj_ifft = (fftw_complex *)calloc(2048 + 32, sizeof(fftw_complex));
@@ -529,7 +530,7 @@ DABGPU_EXPORT int sdr_demod(struct demapped_transmission_frame_t *tf, struct sdr
     return 0;
   }
   int32_t s4[4] = {0, 0, 0, 0};
-  float ffs = 0.f;
+  double ffs = 0.0;
   // the synchronisers keep fine_timeshift / fine_freq_shift on an early exit: seed them
   sdr->coarse_timeshift = 0;
   const uint8_t force = sdr->force_timesync;
@@ -546,11 +547,34 @@ DABGPU_EXPORT int sdr_demod(struct demapped_transmission_frame_t *tf, struct sdr
     sdr->force_timesync = 1;
     return 0;
   }
-  sdr->fine_freq_shift = (double)ffs;
+  sdr->fine_freq_shift = ffs;
+  // This batch-of-one drop-in also leaves behind what a caller poking at sdr_state_t would find
+  // after the reference's sdr_demod: real/imag (input_sdr.c:60-63), dab_frame (:79-82), the
+  // fftshifted spectra `symbols` (:115-130) and the DQPSK quotients `symbols_d` (:132-144, on
+  // the 1536 carriers; the reference also divides noise by noise on the unused bins).  Hence
+  // the demodulator instantiation that writes its spectra out (same arithmetic as the batched
+  // one, which never materialises them); values are the kernel's float32 widened to double.
   static thread_local std::vector<uint8_t> bits(230400);
-  if (dabgpu_demod_frame_debug(sdr->buffer, nullptr, nullptr, bits.data())) {
+  static thread_local std::vector<float> spec(2 * 76 * 2048), specd(2 * 76 * 2048);
+  if (dabgpu_demod_frame_debug(sdr->buffer, spec.data(), specd.data(), bits.data())) {
     report("sdr_demod");
     return 0;
+  }
+  for (int j = 0; j < 196608; j++) {
+    sdr->real[j] = (int8_t)(sdr->buffer[2 * j] - 127);
+    sdr->imag[j] = (int8_t)(sdr->buffer[2 * j + 1] - 127);
+    if (sdr->dab_frame) {
+      sdr->dab_frame[j][0] = sdr->real[j];
+      sdr->dab_frame[j][1] = sdr->imag[j];
+    }
+  }
+  for (int j = 0; j < 76 * 2048; j++) {
+    sdr->symbols[j / 2048][j % 2048][0] = spec[2 * j];
+    sdr->symbols[j / 2048][j % 2048][1] = spec[2 * j + 1];
+    if (sdr->symbols_d && j >= 2048) {
+      sdr->symbols_d[j][0] = specd[2 * j];
+      sdr->symbols_d[j][1] = specd[2 * j + 1];
+    }
   }
   memcpy(tf->fic_symbols_demapped, bits.data(), 9216);
   memcpy(tf->msc_symbols_demapped, bits.data() + 9216, 221184);

@@ -179,7 +179,7 @@ DABGPU_EXPORT int dabgpu_fic_decode_batch(const uint8_t *fic_bits, int n_groups,
 }
 
 // ---- single-frame front-end ---------------------------------------------------------------------------
-DABGPU_EXPORT int dabgpu_sync_frame(const uint8_t *frame, int force_timesync, int32_t *out4, float *fine_freq_hz) {
+DABGPU_EXPORT int dabgpu_sync_frame(const uint8_t *frame, int force_timesync, int32_t *out4, double *fine_freq_hz) {
   int rc;
   if ((rc = ensure_device_ready())) return rc;
   cudaStream_t st = current_stream();

@@ -316,21 +316,31 @@ int Engine::refresh_layout(int s) {
   memset(&L.dev, 0, sizeof L.dev);
   uint32_t row = 0, nst = 0, fl = 0, payload = 0;
   const uint64_t keep = subch_mask[s];  // dabgpu_engine_set_subchannel_mask: all ones by default
-  for (int j = 0; j < 64; j++)
-    if (ei.subchans[j].id >= 0 && ((keep >> j) & 1)) nst++;
+  // A sub-channel whose description cannot be decoded (reserved EEP option, size outside the CIF:
+  // the reference would index past its tables or read out of bounds here) is left out of this
+  // stream's frames and reported through dabgpu_last_error; the other streams of the batched call,
+  // and this stream's other sub-channels, carry on.
+  dabgpu_cw_shape shp[64];
+  bool usable[64];
+  for (int j = 0; j < 64; j++) {
+    const subchannel_info_t &sc = ei.subchans[j];
+    usable[j] = false;
+    if (sc.id < 0 || !((keep >> j) & 1)) continue;
+    if (host_subch_shape(&sc, &shp[j]) || shp[j].nbits <= 0 || shp[j].nbits > 9216 ||
+        sc.start_cu * 64 + shp[j].in_bits > DABGPU_CIF_BITS) {
+      set_error(DABGPU_ERR_STATE, "stream %d: sub-channel %d has an undecodable description (skipped)", s, sc.id);
+      stats[s].undecodable_subch++;
+      continue;
+    }
+    usable[j] = true;
+    nst++;
+  }
   L.e1 = 12 + 4 * nst;
   uint32_t e = L.e1 + 96;
   for (int j = 0; j < 64; j++) {
     const subchannel_info_t &sc = ei.subchans[j];
-    if (sc.id < 0 || !((keep >> j) & 1)) continue;
-    dabgpu_cw_shape sh;
-    if (host_subch_shape(&sc, &sh) || sh.nbits <= 0 || sh.nbits > 9216 ||
-        sc.start_cu * 64 + sh.in_bits > DABGPU_CIF_BITS) {
-      // the reference would read out of bounds / index past its tables here; refuse loudly
-      set_error(DABGPU_ERR_STATE, "stream %d: sub-channel %d has an undecodable description", s, sc.id);
-      L.version = 0;
-      return DABGPU_ERR_STATE;
-    }
+    if (!usable[j]) continue;
+    const dabgpu_cw_shape &sh = shp[j];
     EnsLayout::Sub &u = L.sub[L.nsub];
     u.in_bit0 = (uint32_t)sc.start_cu * 64u;
     u.shape = (uint32_t)shape_index(sh);
@@ -501,14 +511,22 @@ int Engine::fic_finish(cudaStream_t st, const SyncOut *sync, int demod_ev, bool 
       fr.coarse_timeshift = so.coarse_timeshift;
       fr.force_timesync = 0;
       fr.last_ok = 0;
-      if (so.coarse_timeshift) continue;
+      // A frame that fails here never reaches dab_process_frame: the reference leaves tfidx, the
+      // CIF window and its buffers alone (dab2eti.c:68-71, dab.c:97), so the slot taken for it is
+      // handed back -- otherwise a run of sync misses would walk the slot ring into CIFs the
+      // window (or a queued MSC batch) still refers to.  The demodulator wrote nothing (sync.ok).
+      if (so.coarse_timeshift) {
+        back[s].phys = frame_slot[s];
+        continue;
+      }
       fr.fine_timeshift = so.fine_timeshift;
       fr.coarse_freq_shift = so.coarse_freq_shift;
       if (std::abs(so.coarse_freq_shift) > 1) {
         fr.force_timesync = 1;
+        back[s].phys = frame_slot[s];
         continue;
       }
-      fr.fine_freq_shift = (double)so.fine_freq_shift;
+      fr.fine_freq_shift = so.fine_freq_shift;
       fr.last_ok = 1;
       lag.proc[a] = 1;
     }
@@ -558,7 +576,12 @@ int Engine::backend_host(cudaStream_t st) {
     if (layout[s].version != back[s].ens_version) {
       // the multiplex description changed: frames of this stream that are still queued were
       // produced under the old layout and must be decoded first
-      if (pend_of_stream[s] && (rc = flush_msc(st))) return rc;
+      if (pend_of_stream[s]) {
+        // jobs of earlier streams from this same frame may already be queued: the flush has to
+        // wait for the demodulator that is still writing their newest CIFs
+        if (any && lag.demod_ev >= 0) msc_wait_ev = lag.demod_ev;
+        if ((rc = flush_msc(st))) return rc;
+      }
       if ((rc = refresh_layout(s))) return rc;
     }
     any = true;
@@ -849,7 +872,7 @@ int Engine::feed_capture(int chunk_len) {
     set_error(DABGPU_ERR_STATE, "feed_capture: no capture attached");
     return DABGPU_ERR_STATE;
   }
-  if (chunk_len > 0 && capture_fed + (uint64_t)chunk_len > capture_len) {
+  if (chunk_len > 0 && !capture_cyclic && capture_fed + (uint64_t)chunk_len > capture_len) {
     set_error(DABGPU_ERR_STATE, "feed_capture: the capture holds %llu more bytes per stream, %d requested",
               (unsigned long long)(capture_len - capture_fed), chunk_len);
     return DABGPU_ERR_STATE;
@@ -1094,6 +1117,10 @@ DABGPU_EXPORT int dabgpu_engine_attach_capture(dabgpu_engine *h, const uint8_t *
   return h->e.attach_capture(iq_device, pitch, len);
 }
 DABGPU_EXPORT int dabgpu_engine_feed_capture(dabgpu_engine *h, int chunk_len) { return h->e.feed_capture(chunk_len); }
+DABGPU_EXPORT int dabgpu_engine_set_capture_cyclic(dabgpu_engine *h, int on) {
+  h->e.capture_cyclic = on != 0;
+  return DABGPU_OK;
+}
 DABGPU_EXPORT int dabgpu_engine_process_demapped(dabgpu_engine *h, const uint8_t *tfs, size_t pitch,
                                                  const uint8_t *mask, int on_device) {
   return h->e.process_demapped(tfs, pitch, mask, on_device != 0);

@@ -68,7 +68,7 @@ struct FrontState {
 };
 
 struct StreamStats {
-  uint64_t frames_demodulated = 0, eti_frames = 0, fib_crc_errors = 0;
+  uint64_t frames_demodulated = 0, eti_frames = 0, fib_crc_errors = 0, undecodable_subch = 0;
 };
 
 struct Engine {
@@ -142,6 +142,7 @@ struct Engine {
   RingGeom rg = {nullptr, 0, IQ_RING_BYTES};
   const uint8_t *capture_base = nullptr;
   uint64_t capture_len = 0, capture_fed = 0;
+  bool capture_cyclic = false;  // feed_capture wraps around: the capture is one period of an endless signal
   bool capture_call = false;
   int attach_capture(const uint8_t *iq_device, size_t pitch, size_t len);
   int feed_capture(int chunk_len);

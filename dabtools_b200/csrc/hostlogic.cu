@@ -4,7 +4,7 @@
 namespace dabgpu {
 
 // FIG 0/0, 0/1 and 0/2 extraction, behaviour of fic.c:47-130 fib_parse()
-static void parse_fib(tf_info_t *info, const uint8_t *fib) {
+static void parse_fib(tf_info_t *info, const uint8_t *fib, bool quiet) {
   int pos = 0;
   while (fib[pos] != 0xff && pos < 30) {
     const int fig_type = fib[pos] >> 5;
@@ -46,8 +46,13 @@ static void parse_fib(tf_info_t *info, const uint8_t *fib) {
         for (int j = pos + 1; j < pos + fig_len;) {
           j += pd ? 4 : 2;
           const int ncomp = fib[j++] & 0x0f;
-          for (int k = 0; k < ncomp; k++, j += 2)
-            if ((fib[j] >> 6) == 0) info->subchans[fib[j + 1] >> 2].ASCTy = fib[j] & 0x3f;
+          for (int k = 0; k < ncomp; k++, j += 2) {
+            const int tmid = fib[j] >> 6;
+            if (tmid == 0)
+              info->subchans[fib[j + 1] >> 2].ASCTy = fib[j] & 0x3f;
+            else if (tmid != 3 && !quiet)  // fic.c:113-119
+              fprintf(stderr, "Unhandled TMid %d for subchannel %d\n", tmid, fib[j + 1] >> 2);
+          }
         }
       }
     }
@@ -56,11 +61,11 @@ static void parse_fib(tf_info_t *info, const uint8_t *fib) {
 }
 
 // fic.c:132-147
-void host_fib_decode(tf_info_t *info, const uint8_t *fibs, const uint8_t *crc_ok, int nfibs) {
+void host_fib_decode(tf_info_t *info, const uint8_t *fibs, const uint8_t *crc_ok, int nfibs, bool quiet) {
   memset(info, 0, sizeof *info);
   for (int i = 0; i < 64; i++) info->subchans[i].id = info->subchans[i].ASCTy = -1;
   for (int i = 0; i < nfibs; i++)
-    if (crc_ok[i]) parse_fib(info, fibs + 32 * i);
+    if (crc_ok[i]) parse_fib(info, fibs + 32 * i, quiet);
 }
 
 // misc.c:14-27
@@ -142,7 +147,7 @@ void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *cr
   out->n_eti = 0;
   int ok_count = 0;
   for (int i = 0; i < 12; i++) ok_count += crc_ok[i] ? 1 : 0;
-  if (ok_count > 0) host_fib_decode(&st.tf_info, fibs, crc_ok, 12);
+  if (ok_count > 0) host_fib_decode(&st.tf_info, fibs, crc_ok, 12, quiet);
 
   if (ok_count == 12) {
     st.okcount++;
@@ -194,7 +199,7 @@ using namespace dabgpu;
 
 // ---- reference-signature entry points that are pure host logic ----------------------------------
 DABGPU_EXPORT void fib_decode(struct tf_info_t *info, struct tf_fibs_t *fibs, int nfibs) {
-  host_fib_decode(info, &fibs->FIB[0][0], fibs->FIB_CRC_OK, nfibs);
+  host_fib_decode(info, &fibs->FIB[0][0], fibs->FIB_CRC_OK, nfibs, false);
 }
 DABGPU_EXPORT void merge_info(struct ens_info_t *ei, struct tf_info_t *info) { host_merge_info(ei, info); }
 

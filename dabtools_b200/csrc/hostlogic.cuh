@@ -8,7 +8,7 @@
 
 namespace dabgpu {
 
-void host_fib_decode(tf_info_t *info, const uint8_t *fibs384, const uint8_t *crc_ok12, int nfibs);
+void host_fib_decode(tf_info_t *info, const uint8_t *fibs384, const uint8_t *crc_ok12, int nfibs, bool quiet);
 void host_merge_info(ens_info_t *ei, const tf_info_t *info);
 void host_init_ens(ens_info_t *ei);
 // puncturing layout of a sub-channel as the reference's create_eti would decode it

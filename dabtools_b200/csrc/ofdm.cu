@@ -1133,15 +1133,29 @@ __device__ int coarse_freq_from_spec(SyncSmem &sm) {
   return bi - 14;
 }
 
-// sdr_sync.c:259-302: mean phase of x[n+2048] conj(x[n]) over the PRS guard interval, in Hz
+// sdr_sync.c:259-302: mean phase of x[n+2048] conj(x[n]) over the PRS guard interval, in Hz.
+// In double like the reference: the products of 8-bit samples are exact, atan2 is taken in double
+// and the 504 angles are added in the reference's order (i ascending, one thread), because the tuner
+// feedback truncates `frequency + ffs / 3` to an integer (dab2eti.c:98-101) and a float-level
+// difference there would move a borderline stream by 1 Hz for the rest of its life.
 template <typename Src>
-__device__ float fine_freq(SyncSmem &sm, const Src &src) {
-  float acc = 0.f;
+__device__ double fine_freq(SyncSmem &sm, const Src &src) {
+  double *ang = reinterpret_cast<double *>(sm.work);  // 504 doubles; the correlation buffers are free here
   for (int i = threadIdx.x; i < 504; i += FFT_THREADS) {
-    const float2 lr = cmulc(src.at(2656 + 2048 + i), src.at(2656 + i));
-    acc += atan2f(lr.y, lr.x);
+    const float2 l = src.at(2656 + 2048 + i), r = src.at(2656 + i);
+    const double lx = l.x, ly = l.y, rx = r.x, ry = r.y;
+    ang[i] = atan2(ly * rx - lx * ry, lx * rx + ly * ry);
   }
-  return block_sum(sm, acc) / 504.f / (2.f * 3.14159265358979323846f) * 1000.f;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double mean = 0.0;
+    for (int i = 0; i < 504; i++) mean = mean + ang[i];
+    ang[504] = mean / 504 / (2 * 3.14159265358979323846) * 1000;
+  }
+  __syncthreads();
+  const double r = ang[504];
+  __syncthreads();
+  return r;
 }
 
 // the synchroniser half of sdr_demod (input_sdr.c:65-112) on one frame
@@ -1204,12 +1218,12 @@ int launch_sync(RingGeom d_ring, const uint8_t *d_tails, const uint8_t *d_frames
 //   mode 2: dab_coarse_freq_sync_2(shifted spectrum float2[2048]) -> res[0] (carriers)
 //   mode 3: dab_fine_freq_corr(frame as float2[>= 5208]) -> fres[0] (Hz)
 __global__ void __launch_bounds__(FFT_THREADS) sync_single_kernel(int mode, const void *in, int force, int *res,
-                                                                  float *fres) {
+                                                                  double *fres) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SyncSmem &sm = *reinterpret_cast<SyncSmem *>(smem_raw);
   const int p = threadIdx.x;
   int r = 0;
-  float fr = 0.f;
+  double fr = 0.0;
   if (mode == 0) {
     float e;
     r = coarse_time_sync(sm, SrcI8{(const int8_t *)in}, force != 0, &e);
@@ -1236,7 +1250,7 @@ __global__ void __launch_bounds__(FFT_THREADS) sync_single_kernel(int mode, cons
   }
 }
 
-int launch_sync_single(int mode, const void *d_in, int force, int *d_res, float *d_fres, cudaStream_t st) {
+int launch_sync_single(int mode, const void *d_in, int force, int *d_res, double *d_fres, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
     CUDA_TRY(cudaFuncSetAttribute(sync_single_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,

@@ -53,10 +53,9 @@ struct SyncOut {
   int32_t coarse_timeshift;  // bytes
   int32_t fine_timeshift;    // bytes
   int32_t coarse_freq_shift; // carriers
-  float fine_freq_shift;     // Hz
+  double fine_freq_shift;    // Hz (double like sdr_state_t: the tuner feedback truncates it)
   int32_t stage;             // how far the frame got: 1 coarse-time miss, 2 coarse-freq miss, 3 demodulated
   float null_energy;
-  int32_t pad;
 };
 
 int launch_ingest(const uint8_t *d_src, uint64_t src_pitch, uint32_t chunk_len, uint8_t *d_ring,
@@ -82,6 +81,6 @@ int launch_demod_debug(const uint8_t *d_frame, float2 *d_symbols, float2 *d_symb
                        cudaStream_t st);
 
 // the four synchronisers on their own (reference-signature entry points of sdr_sync.h)
-int launch_sync_single(int mode, const void *d_in, int force, int *d_res, float *d_fres, cudaStream_t st);
+int launch_sync_single(int mode, const void *d_in, int force, int *d_res, double *d_fres, cudaStream_t st);
 
 }  // namespace dabgpu

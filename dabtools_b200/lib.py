@@ -28,6 +28,9 @@ def load(build_if_missing: bool = True) -> C.CDLL:
     global _lib
     if _lib is not None:
         return _lib
+    if os.environ.get("DABGPU_FORBID_LOAD"):
+        # bench.py's reference arm sets this: nothing of the product may be mapped into that process
+        raise DabGpuError("libdabgpu.so must not be loaded in this process (DABGPU_FORBID_LOAD is set)")
     if not os.path.exists(LIB_PATH):
         if not build_if_missing:
             raise DabGpuError(f"{LIB_PATH} is missing; run `python -m dabtools_b200.build`")
@@ -100,7 +103,7 @@ def sync_frame(frame: np.ndarray, force_timesync: int = 0) -> dict:
     frame = np.ascontiguousarray(frame, dtype=np.uint8).ravel()
     assert frame.size == 393216
     out = (C.c_int32 * 4)()
-    ffs = C.c_float(0)
+    ffs = C.c_double(0)
     check(load().dabgpu_sync_frame(_np_ptr(frame), force_timesync, out, C.byref(ffs)))
     return dict(coarse_timeshift=out[0], fine_timeshift=out[1], coarse_freq_shift=out[2], ok=out[3],
                 fine_freq_shift=float(ffs.value))
@@ -303,6 +306,11 @@ def _engine_feed_capture(self, chunk_len: int) -> int:
     return self._lib.dabgpu_engine_eti_count(self._h)
 
 
+def _engine_set_capture_cyclic(self, on: bool = True):
+    self._lib.dabgpu_engine_set_capture_cyclic.argtypes = [C.c_void_p, C.c_int]
+    check(self._lib.dabgpu_engine_set_capture_cyclic(self._h, int(on)))
+
+
 def _engine_set_subchannel_mask(self, mask: int, stream: int = -1):
     self._lib.dabgpu_engine_set_subchannel_mask.argtypes = [C.c_void_p, C.c_int, C.c_uint64]
     check(self._lib.dabgpu_engine_set_subchannel_mask(self._h, stream, mask & 0xFFFFFFFFFFFFFFFF))
@@ -310,6 +318,7 @@ def _engine_set_subchannel_mask(self, mask: int, stream: int = -1):
 
 Engine.set_subchannel_mask = _engine_set_subchannel_mask
 Engine.attach_capture = _engine_attach_capture
+Engine.set_capture_cyclic = _engine_set_capture_cyclic
 Engine.feed_capture = _engine_feed_capture
 Engine.submit_iq = _engine_submit_iq
 Engine.feed_submitted = _engine_feed_submitted

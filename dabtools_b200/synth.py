@@ -267,6 +267,43 @@ class ModeITransmitter:
         return out
 
 
+def _crc16_rows(rows: np.ndarray) -> np.ndarray:
+    """CRC-16-CCITT (init 0xffff, no inversion) of every row of a uint8 [n][k] array"""
+    tab = np.zeros(256, dtype=np.uint16)
+    for b in range(256):
+        c = b << 8
+        for _ in range(8):
+            c = ((c << 1) ^ 0x1021) & 0xFFFF if c & 0x8000 else (c << 1) & 0xFFFF
+        tab[b] = c
+    crc = np.full(rows.shape[0], 0xFFFF, dtype=np.uint16)
+    for j in range(rows.shape[1]):
+        crc = ((crc << 8) & 0xFFFF) ^ tab[(crc >> 8) ^ rows[:, j]]
+    return crc
+
+
+def fic_groups(n_groups: int, seed: int = 0, flips=(0.0, 0.01, 0.04, 0.08)):
+    """BASELINE config 2 input: `n_groups` FIC groups (one CIF's 3 FIBs = one 768-bit codeword each).
+    Every FIB carries 30 random bytes and a valid CRC, is scrambled, encoded and punctured like the
+    FIC (fic.c:160-208 in reverse); quarter q of the groups then gets i.i.d. bit flips with
+    probability flips[q].  Returns (bits uint8 [n][2304] hard bits, fibs uint8 [n][96] as sent)."""
+    rng = np.random.default_rng(0xF1C0000 + seed)
+    fibs = rng.integers(0, 256, (n_groups * 3, 32), dtype=np.uint8)
+    crc = ~_crc16_rows(fibs[:, :30]) & 0xFFFF
+    fibs[:, 30] = crc >> 8
+    fibs[:, 31] = crc & 0xFF
+    fibs = fibs.reshape(n_groups, 96)
+    tx = ModeITransmitter(Ensemble([]), "cpu")
+    bits = np.empty((n_groups, 2304), dtype=np.uint8)
+    for i in range(0, n_groups, 2048):
+        bits[i:i + 2048] = tx._code_block(torch.from_numpy(fibs[i:i + 2048]), "fic").numpy()
+    n = n_groups
+    for q, p in enumerate(flips):
+        sl = slice(q * n // len(flips), (q + 1) * n // len(flips))
+        if p > 0:
+            bits[sl] ^= (rng.random(bits[sl].shape) < p).astype(np.uint8)
+    return bits, fibs
+
+
 def expected_eti_payload(ens: Ensemble, payload: dict, stream: int, logical_cif: int) -> bytes:
     """MST sub-channel bytes of the ETI frame that carries logical CIF `logical_cif`."""
     return b"".join(bytes(payload[s.id][stream, logical_cif].cpu().numpy()) for s in ens.subchannels)

@@ -1,13 +1,40 @@
-"""DAB Mode I tables as seen through libdabgpu's C ABI (include/dabgpu_tables.h is the source of
-truth; tests/test_tables.py pins it against the compiled reference)."""
+"""DAB Mode I tables (include/dabgpu_tables.h is the source of truth; tests/test_tables.py pins it
+against the compiled reference).  They are read through libdabtables.so, a host-only build of the
+same dabgpu_tab_* accessors libdabgpu.so exports (csrc/tables_host.c): manufacturing test or
+benchmark input never maps the CUDA library."""
 from __future__ import annotations
 
 import ctypes as C
 import functools
+import os
 
 import numpy as np
 
-from . import lib as _lib
+
+class _TablesLib:
+    _lib = None
+
+    @classmethod
+    def load(cls):
+        if cls._lib is None:
+            from . import build as _b
+            so = _b.TABLES_LIB
+            if not os.path.exists(so):
+                _b.build_tables()
+            lib = C.CDLL(so)
+            lib.dabgpu_tab_shape.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int32)]
+            lib.dabgpu_tab_uep.argtypes = [C.POINTER(C.c_int32)]
+            lib.dabgpu_tab_puncture_mask.restype = C.c_uint32
+            lib.dabgpu_tab_freq_deint.argtypes = [C.POINTER(C.c_uint16)]
+            lib.dabgpu_tab_prs.argtypes = [C.POINTER(C.c_uint8)]
+            lib.dabgpu_tab_prbs.argtypes = [C.POINTER(C.c_uint8), C.c_int]
+            lib.dabgpu_tab_crc16.argtypes = [C.POINTER(C.c_uint8), C.c_int, C.c_uint16]
+            lib.dabgpu_tab_crc16.restype = C.c_uint16
+            cls._lib = lib
+        return cls._lib
+
+
+_lib = _TablesLib
 
 POLYS = (0x6D, 0x4F, 0x53, 0x6D)
 TDI_DELAY = (0, 8, 4, 12, 2, 10, 6, 14, 1, 9, 5, 13, 3, 11, 7, 15)
@@ -106,3 +133,9 @@ def prbs(nbytes: int) -> np.ndarray:
     out = np.zeros(nbytes, dtype=np.uint8)
     _lib.load().dabgpu_tab_prbs(out.ctypes.data_as(C.POINTER(C.c_uint8)), nbytes)
     return out
+
+
+def crc16(data: np.ndarray, init: int = 0xFFFF) -> int:
+    """CRC-16-CCITT as misc.c:96-150 computes it (no final inversion)"""
+    data = np.ascontiguousarray(data, dtype=np.uint8)
+    return int(_lib.load().dabgpu_tab_crc16(data.ctypes.data_as(C.POINTER(C.c_uint8)), data.size, init))

@@ -85,7 +85,7 @@ uint64_t dabgpu_launch_count(void);
 /* frame: 393216 bytes of uint8 I/Q exactly as sdr_demod has them in sdr->buffer after
  * sdr_read_fifo.  Runs the synchronisers of input_sdr.c:65-112; out[0..3] = coarse_timeshift,
  * fine_timeshift (bytes), coarse_freq_shift (carriers), ok; *fine_freq_hz as sdr_state_t. */
-int dabgpu_sync_frame(const uint8_t *frame, int force_timesync, int32_t *out4, float *fine_freq_hz);
+int dabgpu_sync_frame(const uint8_t *frame, int force_timesync, int32_t *out4, double *fine_freq_hz);
 /* FFT + DQPSK + demap of all 76 symbols regardless of the synchronisers (input_sdr.c:114-162):
  * symbols / symbols_d: 76*2048 complex float each (fftshifted like sdr->symbols; row 0 of
  * symbols_d is not written), bits: 230400 bytes (fic 9216 then msc 221184).  Any may be NULL. */
@@ -128,6 +128,12 @@ int dabgpu_engine_submit_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, i
  * valid and unchanged while the engine lives.  Not available with DABGPU_ENGINE_VIRTUAL_TUNER. */
 int dabgpu_engine_attach_capture(dabgpu_engine *e, const uint8_t *iq_device, size_t pitch, size_t len);
 int dabgpu_engine_feed_capture(dabgpu_engine *e, int chunk_len);
+/* Treat the attached capture as one period of an endless signal: feed_capture() wraps around at
+ * its end instead of refusing (FIFO positions are taken modulo the capture length anyway).  A
+ * capture holding a whole number of transmission frames keeps the streams frame-aligned across
+ * the seam; the 15 CIFs after it mix two passes in the time de-interleaver, like any receiver fed
+ * a looped recording.  Used by bench.py for timed regions longer than HBM could hold as samples. */
+int dabgpu_engine_set_capture_cyclic(dabgpu_engine *e, int on);
 int dabgpu_engine_feed_submitted(dabgpu_engine *e);
 /* Back-end only: one demapped transmission frame (fic 9216 + msc 221184 bytes of 0/1, i.e. the
  * payload of demapped_transmission_frame_t) for every stream with mask[s] != 0 (mask NULL = all);

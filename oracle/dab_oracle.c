@@ -870,6 +870,68 @@ long orc_run_iq(const uint8_t *iq, long nbytes, int chunk, uint32_t f0, unsigned
   return sink.n;
 }
 
+/* Streaming form of orc_run_iq (same contract as ref_stream_* in oracle/ref_harness.c): the
+ * receiver state lives across calls so that bench.py can time one bounded sample per step. */
+struct orc_stream {
+  struct eti_sink sink;
+  struct orc_rx *rx;
+  struct orc_sdr *s;
+  struct orc_rand rng;
+  uint8_t *cbuf;
+  uint32_t f0;
+  long pos;
+};
+
+void *orc_stream_open(uint32_t f0, unsigned rand_seed) {
+  struct orc_stream *h = (struct orc_stream *)calloc(1, sizeof *h);
+  h->rx = orc_rx_new(sink_cb, &h->sink);
+  h->s = sdr_new();
+  h->cbuf = (uint8_t *)malloc(262144);
+  orc_srand(&h->rng, rand_seed);
+  h->s->frequency = f0;
+  h->f0 = f0;
+  return h;
+}
+
+long orc_stream_feed(void *hv, const uint8_t *iq, long nbytes, int chunk, uint8_t *eti_out, long eti_cap) {
+  struct orc_stream *h = (struct orc_stream *)hv;
+  struct orc_sdr *s = h->s;
+  h->sink.out = eti_out;
+  h->sink.cap = eti_cap;
+  h->sink.n = 0;
+  if (chunk <= 0 || chunk > 262144) chunk = 262144;
+  for (long pos = 0; pos + chunk <= nbytes; pos += chunk, h->pos += chunk) {
+    double df = (double)s->frequency - (double)h->f0;
+    const uint8_t *src = iq + pos;
+    if (df != 0.0) {
+      for (long b = 0; b < chunk; b += 2) {
+        double n = (double)((h->pos + b) / 2);
+        double ph = -2.0 * M_PI * df * n / 2048000.0;
+        double c = cos(ph), sn = sin(ph);
+        double xr = (double)iq[pos + b] - 127.0, xi = (double)iq[pos + b + 1] - 127.0;
+        double qr = floor(xr * c - xi * sn + 0.5) + 127.0, qi = floor(xr * sn + xi * c + 0.5) + 127.0;
+        h->cbuf[b] = (uint8_t)(qr < 0 ? 0 : qr > 255 ? 255 : qr);
+        h->cbuf[b + 1] = (uint8_t)(qi < 0 ? 0 : qi > 255 ? 255 : qi);
+      }
+      src = h->cbuf;
+    }
+    if (sdr_demod(s, src, chunk, orc_rx_fic_slot(h->rx), orc_rx_msc_slot(h->rx))) orc_rx_process_frame(h->rx);
+    tuner_feedback(s, &h->rng);
+  }
+  h->sink.out = NULL;
+  return h->sink.n;
+}
+
+int orc_stream_locked(void *hv) { return ((struct orc_stream *)hv)->rx->locked; }
+
+void orc_stream_close(void *hv) {
+  struct orc_stream *h = (struct orc_stream *)hv;
+  free(h->cbuf);
+  sdr_free(h->s);
+  orc_rx_free(h->rx);
+  free(h);
+}
+
 /* ==================================================================================
  * 9. Table accessors for the tests
  * ================================================================================== */

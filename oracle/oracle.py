@@ -139,6 +139,24 @@ class _Common:
         return dict(eti=eti[:m].copy(), trace=trace[: n_calls.value], n_tfs=n_tfs.value,
                     tfs=tfs[: min(want_tfs, n_tfs.value)].copy())
 
+    # ---- streaming receive loop (state kept across calls; bench.py --impl reference) -------------
+    def stream_open(self, f0: int = 200_000_000, seed: int = 1):
+        return self._stream_open(f0, seed)
+
+    def stream_feed(self, h, iq: np.ndarray, chunk: int = 262144, want_eti: bool = True):
+        """feed a multiple of `chunk` bytes; returns (n_frames, eti [n][6144] or None)"""
+        iq = np.ascontiguousarray(iq, dtype=np.uint8).ravel()
+        cap = 4 * (iq.size // 393216 + 2)
+        eti = np.zeros((cap, 6144), dtype=np.uint8) if want_eti else None
+        n = self._stream_feed(h, _p(iq), iq.size, chunk, _p(eti) if want_eti else None, eti.size if want_eti else 0)
+        return int(n), (eti[: min(n, cap)].copy() if want_eti else None)
+
+    def stream_locked(self, h) -> bool:
+        return bool(self._stream_locked(h))
+
+    def stream_close(self, h):
+        self._stream_close(h)
+
     def demod_frame(self, frame: np.ndarray, force_timesync: int = 0, want_spectra: bool = True):
         frame = np.ascontiguousarray(frame, dtype=np.uint8).ravel()
         assert frame.size == 393216
@@ -161,6 +179,18 @@ _run_iq_args = [u8p, C.c_long, C.c_int, C.c_uint32, C.c_uint, u8p, C.c_long, C.P
                 C.c_long, C.POINTER(C.c_long), u8p, C.c_long, C.POINTER(C.c_long)]
 _demod_args = [u8p, C.c_int, C.POINTER(C.c_int32), C.POINTER(C.c_int32), C.POINTER(C.c_int32),
                C.POINTER(C.c_double), C.POINTER(C.c_double), C.POINTER(C.c_double), u8p]
+
+
+def _bind_stream(obj, lib, prefix):
+    o, f, l, c = (getattr(lib, prefix + n) for n in ("open", "feed", "locked", "close"))
+    o.argtypes = [C.c_uint32, C.c_uint]
+    o.restype = C.c_void_p
+    f.argtypes = [C.c_void_p, u8p, C.c_long, C.c_int, u8p, C.c_long]
+    f.restype = C.c_long
+    l.argtypes = [C.c_void_p]
+    c.argtypes = [C.c_void_p]
+    c.restype = None
+    obj._stream_open, obj._stream_feed, obj._stream_locked, obj._stream_close = o, f, l, c
 
 
 class Port(_Common):
@@ -198,6 +228,7 @@ class Port(_Common):
         self._run_backend = lib.orc_run_backend
         self._run_iq = lib.orc_run_iq
         self._demod_frame = lib.orc_demod_frame
+        _bind_stream(self, lib, "orc_stream_")
 
     def gen_metrics(self, amp=1, noise=1.0, bias=0.0, scale=4):
         t = np.zeros((2, 256), dtype=np.int32)
@@ -302,6 +333,7 @@ class Ref(_Common):
         self._run_backend = lib.ref_run_backend
         self._run_iq = lib.ref_run_iq
         self._demod_frame = lib.ref_demod_frame
+        _bind_stream(self, lib, "ref_stream_")
 
     def gen_metrics(self, amp=1, noise=1.0, bias=0.0, scale=4):
         t = np.zeros((2, 256), dtype=np.int32)
@@ -360,8 +392,56 @@ class Ref(_Common):
         return int(self.lib.dab_coarse_time_sync(_p(real, C.c_int8), _p(filt, C.c_float), force))
 
 
+class RefSpiral(_Common):
+    """oracle/_ref/libdabref_spiral.so: the reference built with -DENABLE_SPIRAL_VITERBI
+    (viterbi_spiral.c + viterbi_spiral_sse16.c, src/Makefile:8-16).  Whole-path runs and the raw
+    decoder only; it is a CPU baseline and a statistical cross-check, not an oracle: its 8-bit
+    saturating metrics and tie-break differ from viterbi.c."""
+
+    kind = "reference (Spiral SSE2 Viterbi)"
+
+    def __init__(self, so: str):
+        self.lib = lib = C.CDLL(so)
+        lib.ref_run_iq.argtypes = _run_iq_args
+        lib.ref_run_iq.restype = C.c_long
+        lib.ref_run_backend.argtypes = [u8p, C.c_long, u8p, C.c_long, u8p, u8p]
+        lib.ref_run_backend.restype = C.c_long
+        lib.create_viterbi.argtypes = [C.c_int]
+        lib.create_viterbi.restype = C.c_void_p
+        lib.viterbi.argtypes = [C.c_void_p, u8p, u8p, C.c_int]
+        self._run_iq = lib.ref_run_iq
+        self._run_backend = lib.ref_run_backend
+        self._vp = {}
+        _bind_stream(self, lib, "ref_stream_")
+
+    def viterbi_spiral(self, symbols: np.ndarray, nbits: int) -> np.ndarray:
+        """symbols: 4*(nbits+6) bytes in the Spiral alphabet {0, 128 = erasure, 255} (depuncture.c:36-43)"""
+        symbols = np.ascontiguousarray(symbols, dtype=np.uint8)
+        assert symbols.size >= 4 * (nbits + 6)
+        if nbits not in self._vp:
+            self._vp[nbits] = self.lib.create_viterbi(nbits)
+        out = np.zeros((nbits + 7) // 8 + 8, dtype=np.uint8)
+        self.lib.viterbi(self._vp[nbits], _p(symbols), _p(out), nbits)
+        return out[: (nbits + 7) // 8].copy()
+
+
 _port = None
 _ref = None
+_ref_spiral = None
+
+
+def ref_spiral():
+    """The reference built with -DENABLE_SPIRAL_VITERBI (viterbi_spiral*.c): a secondary CPU baseline
+    for whole-path runs only (run_iq / stream_*); NOT an oracle -- its 8-bit metrics and tie-break
+    differ from viterbi.c, and its viterbi() takes a decoder handle."""
+    global _ref_spiral
+    if _ref_spiral is None:
+        build_ref()
+        so = os.path.join(HERE, "_ref", "libdabref_spiral.so")
+        if not os.path.exists(so):
+            return None
+        _ref_spiral = RefSpiral(so)
+    return _ref_spiral
 
 
 def port() -> Port:

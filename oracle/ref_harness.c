@@ -162,6 +162,79 @@ long ref_run_iq(const uint8_t *iq, long nbytes, int chunk, uint32_t f0,
   return g_eti_n;
 }
 
+/* Streaming form of ref_run_iq for per-step timing (bench.py --impl reference): the receiver
+ * state lives across calls, so a warmed-up (locked, window full) stream can be fed one bounded
+ * sample per step.  The reference is not re-entrant (statics in misc.c / viterbi.c): one stream
+ * per process. */
+struct ref_stream {
+  struct dab_state_t *dab;
+  struct sdr_state_t *sdr;
+  uint32_t f0;
+  long pos;  /* bytes fed so far (phase continuity of the virtual tuner) */
+};
+
+void *ref_stream_open(uint32_t f0, unsigned rand_seed) {
+  struct ref_stream *h = calloc(1, sizeof *h);
+  h->sdr = calloc(1, sizeof *h->sdr);
+  h->f0 = f0;
+  srand(rand_seed);
+  init_dab_state(&h->dab, h->sdr, collect_eti);
+  h->dab->device_type = DAB_DEVICE_RTLSDR;
+  h->sdr->frequency = f0;
+  sdr_init(h->sdr);
+  return h;
+}
+
+/* feed nbytes (a multiple of `chunk`) as rtlsdr callbacks; returns the ETI frames produced by
+ * this call, the first eti_cap/6144 of which are stored */
+long ref_stream_feed(void *hv, const uint8_t *iq, long nbytes, int chunk, uint8_t *eti_out, long eti_cap) {
+  struct ref_stream *h = hv;
+  struct sdr_state_t *sdr = h->sdr;
+  struct dab_state_t *dab = h->dab;
+  g_eti_out = eti_out;
+  g_eti_cap = eti_cap;
+  g_eti_n = 0;
+  if (chunk <= 0 || chunk > DEFAULT_BUF_LENGTH) chunk = DEFAULT_BUF_LENGTH;
+  for (long pos = 0; pos + chunk <= nbytes; pos += chunk, h->pos += chunk) {
+    double df = (double)sdr->frequency - (double)h->f0;
+    if (df == 0.0) {
+      memcpy(sdr->input_buffer, iq + pos, chunk);
+    } else {
+      for (long b = 0; b < chunk; b += 2) {
+        double n = (double)((h->pos + b) / 2);
+        double ph = -2.0 * M_PI * df * n / 2048000.0;
+        double c = cos(ph), s = sin(ph);
+        double xr = (double)iq[pos + b] - 127.0, xi = (double)iq[pos + b + 1] - 127.0;
+        double yr = xr * c - xi * s, yi = xr * s + xi * c;
+        double qr = floor(yr + 0.5) + 127.0, qi = floor(yi + 0.5) + 127.0;
+        sdr->input_buffer[b] = (uint8_t)(qr < 0 ? 0 : qr > 255 ? 255 : qr);
+        sdr->input_buffer[b + 1] = (uint8_t)(qi < 0 ? 0 : qi > 255 ? 255 : qi);
+      }
+    }
+    sdr->input_buffer_len = chunk;
+    if (sdr_demod(&dab->tfs[dab->tfidx], sdr)) dab_process_frame(dab);
+    tuner_feedback(sdr);
+  }
+  g_eti_out = NULL;
+  return g_eti_n;
+}
+
+int ref_stream_locked(void *hv) { return ((struct ref_stream *)hv)->dab->locked; }
+
+void ref_stream_close(void *hv) {
+  struct ref_stream *h = hv;
+  struct sdr_state_t *sdr = h->sdr;
+  free(sdr->fifo.elems);
+  fftw_free(sdr->dab_frame);
+  fftw_free(sdr->prs_ifft);
+  fftw_free(sdr->prs_conj_ifft);
+  fftw_free(sdr->prs_syms);
+  fftw_free(sdr->symbols_d);
+  free(sdr);
+  free(h->dab);
+  free(h);
+}
+
 /* Feed n_tf already-demapped transmission frames (fic 9216 bytes + msc 221184
  * bytes each, values 0/1) to dab_process_frame and collect the ETI frames.
  * Optionally returns the decoded FIBs (12*32 per TF) and CRC flags (12 per TF). */

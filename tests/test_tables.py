@@ -36,6 +36,34 @@ def test_lib_and_port_tables_agree(port):
         assert bin(T.puncture_mask(pi)).count("1") == 8 + pi
 
 
+def test_both_builds_of_the_table_accessors_agree():
+    """tables.py reads libdabtables.so (host-only build); libdabgpu.so exports the same dabgpu_tab_*
+    functions from the same header -- both must return the same values."""
+    import ctypes as C
+    from dabtools_b200 import lib
+    L = lib.load()
+    rev = np.zeros(1536, np.uint16)
+    L.dabgpu_tab_freq_deint(rev.ctypes.data_as(C.POINTER(C.c_uint16)))
+    assert np.array_equal(rev, T.freq_deint())
+    q = np.zeros(1536, np.uint8)
+    L.dabgpu_tab_prs(q.ctypes.data_as(C.POINTER(C.c_uint8)))
+    assert np.array_equal(q, T.prs())
+    pr = np.zeros(1152, np.uint8)
+    L.dabgpu_tab_prbs(pr.ctypes.data_as(C.POINTER(C.c_uint8)), 1152)
+    assert np.array_equal(pr, T.prbs(1152))
+    for pi in range(1, 25):
+        assert int(L.dabgpu_tab_puncture_mask(pi)) == T.puncture_mask(pi)
+    u = (C.c_int32 * (64 * 12))()
+    L.dabgpu_tab_uep(u)
+    assert [tuple(np.frombuffer(u, np.int32).reshape(64, 12)[i][:3]) for i in range(64)] == [r[:3] for r in T.UEP]
+    for kind, a, b in [(0, 0, 0)] + [(1, i, 0) for i in range(64)] + [(2, lv, sz) for lv, sz in
+                                                                     [(0, 12), (1, 8), (2, 90), (4, 27), (7, 30)]]:
+        o = (C.c_int32 * 23)()
+        assert L.dabgpu_tab_shape(kind, a, b, o) == 0
+        sh = T.shape_fic() if kind == 0 else T.shape_uep(a) if kind == 1 else T.shape_eep(a, b)
+        assert (o[0], o[1], o[2]) == (sh["nbits"], sh["in_bits"], sh["n_regions"])
+
+
 def test_against_reference_tables(ref, port):
     assert np.array_equal(T.freq_deint(), ref.freq_deint())
     q = T.prs()

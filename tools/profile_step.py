@@ -17,6 +17,7 @@ lib.check(lib.load().dabgpu_set_device(0))
 lib.use_torch_stream()
 setup = bench.SETUP_TFS // 2
 data, ens = bench.generate_dataset(S, 2 * (setup + 1 + NPROF), torch.device("cuda", 0), seed=1)
+bench.CALLS_PER_STEP = bench.CALLS_PER_2TF
 eng = lib.Engine(S)
 eng.set_msc_batch(2)
 step_bytes = 3 * bench.CALL_BYTES

@@ -22,6 +22,7 @@ METRICS = [
     "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread", "launch__block_size",
     "launch__grid_size", "launch__waves_per_multiprocessor", "smsp__inst_executed.sum",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
+    "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
     "smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
     "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
@@ -60,7 +61,27 @@ with open(out_md, "w") as f:
         f.write("\n")
         rd = to_bytes(r[col["dram__bytes_read.sum"]], units[col["dram__bytes_read.sum"]])
         wr = to_bytes(r[col["dram__bytes_write.sum"]], units[col["dram__bytes_write.sum"]])
-        traffic.setdefault(key[0], []).append({"grid": key[1], "dram_bytes_per_launch": rd + wr,
-                                               "duration_ms": float(r[col["gpu__time_duration.sum"]])})
+        def num(m):
+            try:
+                return float(r[col[m]].replace(",", ""))
+            except (KeyError, ValueError):
+                return None
+        dur = num("gpu__time_duration.sum")
+        if units[col["gpu__time_duration.sum"]] in ("us", "usecond"):
+            dur = dur / 1e3
+        elif units[col["gpu__time_duration.sum"]] in ("ns", "nsecond"):
+            dur = dur / 1e6
+        traffic.setdefault(key[0], []).append({
+            "grid": key[1], "dram_bytes_per_launch": rd + wr, "duration_ms_under_ncu": dur,
+            "issue_active_pct": num("smsp__issue_active.avg.pct_of_peak_sustained_active"),
+            "alu_pipe_pct": num("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+            "fma_pipe_pct": num("sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active"),
+            "lsu_pipe_pct": num("sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active"),
+            "smem_data_pipe_pct": num("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
+            "dram_pct": num("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
+            "warps_active_pct": num("sm__warps_active.avg.pct_of_peak_sustained_active"),
+            "registers": num("launch__registers_per_thread"),
+            "smem_bank_conflicts": num("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum"),
+            "warp_instructions": num("smsp__inst_executed.sum")})
 json.dump({"source": rep, "kernels": traffic}, open(out_json, "w"), indent=1)
 print("wrote", out_md, out_json)
