@@ -227,3 +227,52 @@ DABGPU_EXPORT int dabgpu_demod_frame_debug(const uint8_t *frame, float *symbols,
   CUDA_TRY(cudaStreamSynchronize(st));
   return DABGPU_OK;
 }
+
+// ---- ETI consumers (eti2mpa.c:32-67 and the frame check) ------------------------------------------------
+DABGPU_EXPORT int dabgpu_eti_extract_subchannel(const uint8_t *eti, int n_frames, int subchid, uint8_t *out,
+                                                size_t out_pitch, int32_t *out_len, int on_device) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  if (n_frames <= 0) return DABGPU_OK;
+  if (!eti || !out || !out_len || subchid < 0 || subchid > 63 || out_pitch == 0) {
+    set_error(DABGPU_ERR_ARG, "eti_extract_subchannel: null pointer, SubChId outside 0..63 or zero pitch");
+    return DABGPU_ERR_ARG;
+  }
+  cudaStream_t st = current_stream();
+  if (on_device) return launch_eti_extract(eti, n_frames, subchid, out, out_pitch, out_len, st);
+  Workspace &ws = t_ws;
+  const size_t eb = (size_t)n_frames * DABGPU_ETI_BYTES, ob = (size_t)n_frames * out_pitch;
+  if ((rc = ws.in.reserve(eb))) return rc;
+  if ((rc = ws.out.reserve(ob))) return rc;
+  if ((rc = ws.aux.reserve((size_t)n_frames * 4 + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ws.in.p, eti, eb, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(ws.out.p, 0, ob, st));
+  if ((rc = launch_eti_extract(ws.in.as<uint8_t>(), n_frames, subchid, ws.out.as<uint8_t>(), out_pitch,
+                               ws.aux.as<int32_t>(), st)))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(out, ws.out.p, ob, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_len, ws.aux.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return DABGPU_OK;
+}
+
+DABGPU_EXPORT int dabgpu_eti_check(const uint8_t *eti, int n_frames, uint32_t *flags, int on_device) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  if (n_frames <= 0) return DABGPU_OK;
+  if (!eti || !flags) {
+    set_error(DABGPU_ERR_ARG, "eti_check: null pointer");
+    return DABGPU_ERR_ARG;
+  }
+  cudaStream_t st = current_stream();
+  if (on_device) return launch_eti_check(eti, n_frames, flags, st);
+  Workspace &ws = t_ws;
+  const size_t eb = (size_t)n_frames * DABGPU_ETI_BYTES;
+  if ((rc = ws.in.reserve(eb))) return rc;
+  if ((rc = ws.aux.reserve((size_t)n_frames * 4 + 64))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(ws.in.p, eti, eb, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_eti_check(ws.in.as<uint8_t>(), n_frames, ws.aux.as<uint32_t>(), st))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(flags, ws.aux.p, (size_t)n_frames * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return DABGPU_OK;
+}

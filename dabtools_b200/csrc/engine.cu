@@ -297,7 +297,7 @@ void Engine::destroy() {
       for (int j = 0; j < 2; j++) cudaEventDestroy(ev[k][j]);
   DevBuf *db[] = {&d_ring, &d_frames, &d_tails, &d_chunk, &d_ctl, &d_sync, &d_cifs, &d_fibs, &d_crc, &d_ficbits,
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
-                  &d_subjobs, &d_periods, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out};
+                  &d_subjobs, &d_periods, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out, &d_consume, &d_wf_ring, &d_wf_pkts, &d_wf_ctl};
   for (DevBuf *b : db) b->release();
   PinBuf *pb[] = {&h_ctl, &h_stepctl[0], &h_stepctl[1], &h_sync, &h_fic_out[0], &h_fic_out[1], &h_jobs[0], &h_jobs[1], &h_msc[0], &h_msc[1], &h_eti, &h_chunk};
   for (PinBuf *b : pb) b->release();
@@ -772,6 +772,46 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
   return collect_timing(st);
 }
 
+// do_wf_decode's loop body (dab2eti.c:267-270) for every stream with packets: wf_read_frame into
+// dab->tfs[dab->tfidx] (input_wf.c:65-115), then dab_process_frame.  Symbols that did not arrive
+// keep what the slot held five frames ago, like the reference's ring of five frame buffers.
+int Engine::process_wavefinder(const uint8_t *packets, size_t pitch, const int32_t *n_packets) {
+  int rc;
+  cudaStream_t st = current_stream();
+  int maxp = 0;
+  for (int s = 0; s < S; s++) {
+    if (n_packets[s] < 0 || (size_t)n_packets[s] * 524u > pitch) {
+      set_error(DABGPU_ERR_ARG, "process_wavefinder: stream %d: %d packets do not fit the pitch", s, n_packets[s]);
+      return DABGPU_ERR_ARG;
+    }
+    maxp = std::max(maxp, n_packets[s]);
+  }
+  if (!d_wf_ring.p) {
+    if ((rc = d_wf_ring.reserve((size_t)S * 5 * 230400))) return rc;
+    CUDA_TRY(cudaMemsetAsync(d_wf_ring.p, 0, (size_t)S * 5 * 230400, st));  // init_dab_state calloc()s tfs
+  }
+  if ((rc = d_wf_pkts.reserve((size_t)S * pitch + 16))) return rc;
+  if ((rc = d_wf_ctl.reserve((size_t)S * 12 + 16))) return rc;
+  if ((rc = d_tfbytes.reserve((size_t)S * 230400))) return rc;
+  if ((rc = h_chunk.reserve((size_t)S * 9))) return rc;
+  int32_t *h = h_chunk.as<int32_t>();
+  uint8_t *mask = h_chunk.as<uint8_t>() + (size_t)S * 8;
+  CUDA_TRY(cudaStreamSynchronize(st));  // the staging below is reused from call to call
+  for (int s = 0; s < S; s++) {
+    h[s] = n_packets[s];
+    h[S + s] = back[s].tfidx;
+    mask[s] = n_packets[s] > 0;
+  }
+  int32_t *d_n = d_wf_ctl.as<int32_t>(), *d_slot = d_n + S;
+  uint32_t *d_seen = reinterpret_cast<uint32_t *>(d_slot + S);
+  CUDA_TRY(cudaMemcpyAsync(d_n, h, (size_t)S * 8, cudaMemcpyHostToDevice, st));
+  if (maxp) CUDA_TRY(cudaMemcpyAsync(d_wf_pkts.p, packets, (size_t)S * pitch, cudaMemcpyHostToDevice, st));
+  if ((rc = launch_wf_demap(d_wf_pkts.as<uint8_t>(), pitch, d_n, maxp, d_slot, d_wf_ring.as<uint8_t>(), d_seen,
+                            d_tfbytes.as<uint8_t>(), S, st)))
+    return rc;
+  return process_demapped(d_tfbytes.as<uint8_t>(), 230400, mask, true);
+}
+
 int Engine::ensure_frontend() {
   int rc;
   if (d_ctl.p) return DABGPU_OK;
@@ -825,8 +865,18 @@ int Engine::submit_iq(const uint8_t *iq, size_t pitch, int chunk_len) {
     CUDA_TRY(cudaMemcpy2DAsync(d_stage[b].p, chunk_len, iq, pitch, chunk_len, S, cudaMemcpyHostToDevice, st_copy));
   CUDA_TRY(cudaEventRecord(ev_copied[b], st_copy));
   stage_len[b] = chunk_len;
+  stage_seq[b] = ++submit_seq;
   stage_count++;
   return DABGPU_OK;
+}
+
+// copies complete in submission order (one copy stream): the newest stage whose event has fired
+// bounds what is still on its way
+int Engine::uploads_in_flight() {
+  uint64_t done = submit_seq > N_STAGE ? submit_seq - N_STAGE : 0;  // older stages were re-used: their copies are done
+  for (int b = 0; b < N_STAGE; b++)
+    if (stage_seq[b] > done && cudaEventQuery(ev_copied[b]) == cudaSuccess) done = stage_seq[b];
+  return (int)(submit_seq - done);
 }
 
 int Engine::feed_submitted() {
@@ -1113,6 +1163,7 @@ DABGPU_EXPORT int dabgpu_engine_submit_iq(dabgpu_engine *h, const uint8_t *iq, s
   return h->e.submit_iq(iq, pitch, chunk_len);
 }
 DABGPU_EXPORT int dabgpu_engine_feed_submitted(dabgpu_engine *h) { return h->e.feed_submitted(); }
+DABGPU_EXPORT int dabgpu_engine_uploads_in_flight(dabgpu_engine *h) { return h->e.uploads_in_flight(); }
 DABGPU_EXPORT int dabgpu_engine_attach_capture(dabgpu_engine *h, const uint8_t *iq_device, size_t pitch, size_t len) {
   return h->e.attach_capture(iq_device, pitch, len);
 }
@@ -1142,6 +1193,46 @@ DABGPU_EXPORT int dabgpu_engine_fetch_eti(dabgpu_engine *h, uint8_t *eti, int32_
     }
   }
   if (stream_ids) memcpy(stream_ids, e.eti_stream.data(), (size_t)n * sizeof(int32_t));
+  return n;
+}
+// ETI consumers on the frames of the last call, where they lie in HBM (queued on the MSC stream,
+// behind the kernels that produce the frames)
+DABGPU_EXPORT int dabgpu_engine_extract_subchannel(dabgpu_engine *h, int subchid, uint8_t *out_host, size_t out_pitch,
+                                                   int32_t *out_len_host) {
+  Engine &e = h->e;
+  int rc;
+  const int n = e.n_eti;
+  if (n <= 0) return 0;
+  if (!out_host || !out_len_host || subchid < 0 || subchid > 63 || out_pitch == 0) {
+    set_error(DABGPU_ERR_ARG, "engine_extract_subchannel: null pointer, SubChId outside 0..63 or zero pitch");
+    return DABGPU_ERR_ARG;
+  }
+  cudaStream_t st = e.st_msc;
+  const size_t ob = (size_t)n * out_pitch;
+  if ((rc = e.d_consume.reserve(ob + (size_t)n * 4 + 64))) return rc;
+  uint8_t *d_out = e.d_consume.as<uint8_t>();
+  int32_t *d_len = reinterpret_cast<int32_t *>(d_out + ((ob + 15) & ~(size_t)15));
+  CUDA_TRY(cudaMemsetAsync(d_out, 0, ob, st));
+  if ((rc = launch_eti_extract(e.d_eti.as<uint8_t>(), n, subchid, d_out, out_pitch, d_len, st))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(out_host, d_out, ob, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaMemcpyAsync(out_len_host, d_len, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return n;
+}
+DABGPU_EXPORT int dabgpu_engine_check_eti(dabgpu_engine *h, uint32_t *flags_host) {
+  Engine &e = h->e;
+  int rc;
+  const int n = e.n_eti;
+  if (n <= 0) return 0;
+  if (!flags_host) {
+    set_error(DABGPU_ERR_ARG, "engine_check_eti: null pointer");
+    return DABGPU_ERR_ARG;
+  }
+  cudaStream_t st = e.st_msc;
+  if ((rc = e.d_consume.reserve((size_t)n * 4 + 64))) return rc;
+  if ((rc = launch_eti_check(e.d_eti.as<uint8_t>(), n, e.d_consume.as<uint32_t>(), st))) return rc;
+  CUDA_TRY(cudaMemcpyAsync(flags_host, e.d_consume.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
   return n;
 }
 DABGPU_EXPORT int dabgpu_engine_status(dabgpu_engine *h, int stream, dabgpu_stream_status *out) {
@@ -1203,6 +1294,14 @@ DABGPU_EXPORT int dabgpu_engine_set_subchannel_mask(dabgpu_engine *h, int stream
   return DABGPU_OK;
 }
 
+DABGPU_EXPORT int dabgpu_engine_process_wavefinder(dabgpu_engine *h, const uint8_t *packets, size_t pitch,
+                                                   const int32_t *n_packets) {
+  if (!packets || !n_packets) {
+    set_error(DABGPU_ERR_ARG, "process_wavefinder: null pointer");
+    return DABGPU_ERR_ARG;
+  }
+  return h->e.process_wavefinder(packets, pitch, n_packets);
+}
 DABGPU_EXPORT int dabgpu_engine_set_msc_batch(dabgpu_engine *h, int calls) {
   if (calls < 1 || calls > MAX_MSC_BATCH) {
     set_error(DABGPU_ERR_ARG, "msc batch depth must be 1..%d transmission frames", MAX_MSC_BATCH);

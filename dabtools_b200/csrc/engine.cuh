@@ -107,6 +107,8 @@ struct Engine {
   DevBuf d_tfbytes;   // staging of demapped TFs given on the host
   DevBuf d_steps_fic, d_steps_msc;
   DevBuf d_eti;       // [4*S][6144]
+  DevBuf d_wf_ring, d_wf_pkts, d_wf_ctl;  // Wavefinder producer: tfs[5] per stream, packet staging, counts/slots/flags
+  DevBuf d_consume;   // output of the device-side ETI consumers (extract_subchannel / check_eti)
   DevBuf d_ens;       // EnsDev[S]
   DevBuf d_shapes, d_fic_shape;
   DevBuf d_cifjobs, d_subjobs, d_etijobs, d_planeoff, d_gather_idx, d_gather_out;
@@ -133,6 +135,8 @@ struct Engine {
   cudaEvent_t ev_copied[N_STAGE] = {}, ev_consumed[N_STAGE] = {};
   int stage_len[N_STAGE] = {};
   int stage_head = 0, stage_count = 0;  // FIFO of submitted chunks (at most N_STAGE)
+  uint64_t submit_seq = 0, stage_seq[N_STAGE] = {};  // submit_iq calls so far / the call each stage holds
+  int uploads_in_flight();  // submitted chunks whose host->device copy has not completed yet
   int consuming_stage = -1;
   int submit_iq(const uint8_t *iq, size_t pitch, int chunk_len);
   int feed_submitted();
@@ -242,6 +246,8 @@ struct Engine {
   int feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_device);
   // one demapped TF (fic 9216 + msc 221184 bytes of 0/1) for every stream with mask[s] != 0
   int process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *mask, bool on_device);
+  // the Wavefinder packets of one transmission frame per stream (n_packets[s] == 0: no frame)
+  int process_wavefinder(const uint8_t *packets, size_t pitch, const int32_t *n_packets);
 
  private:
   int fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_stride, bool early);

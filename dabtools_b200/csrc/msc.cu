@@ -16,7 +16,47 @@ static uint16_t host_mulmod(uint16_t a, uint16_t b) {
 }
 
 int msc_init_dep_tables();
+// Wavefinder producer (input_wf.c:23-40): carrier order -> frequency de-interleaved position, and the
+// 2304 channel bits of a FIC group that decodes to three NULL FIBs (fic.c:150-175)
+__device__ uint16_t g_rev1536[1536];
+__device__ uint8_t g_null_fic_group[2304];
+
+static void host_null_fic_group(uint8_t out[2304]) {
+  // three NULL FIBs (ff 00 .. 00 a8 a8) -> energy dispersal -> K=7 r=1/4 mother code (viterbi.c:322-347)
+  // -> FIC puncturing (depuncture.c:45-82 in reverse)
+  uint8_t fibs[96], prbs[96];
+  memset(fibs, 0, sizeof fibs);
+  for (int k = 0; k < 3; k++) {
+    fibs[32 * k] = 0xff;
+    fibs[32 * k + 30] = fibs[32 * k + 31] = 0xa8;
+  }
+  dabgpu_build_prbs(prbs, 96);
+  static uint8_t mother[4 * 774];
+  uint32_t sr = 0;
+  for (int t = 0; t < 774; t++) {
+    const int bit = t < 768 ? (((fibs[t >> 3] ^ prbs[t >> 3]) >> (7 - (t & 7))) & 1) : 0;
+    sr = ((sr << 1) | (uint32_t)bit) & 0x7fu;
+    for (int j = 0; j < 4; j++) mother[4 * t + j] = (uint8_t)(__builtin_popcount(sr & DABGPU_POLYS[j]) & 1);
+  }
+  dabgpu_cw_shape sh;
+  dabgpu_shape_fic(&sh);
+  int n = 0;
+  for (int r = 0; r < sh.n_regions; r++) {
+    const uint32_t mask = dabgpu_puncture_mask(sh.r[r].pi);
+    for (int pos = 0; pos < 4 * sh.r[r].steps; pos++)
+      if ((mask >> (pos & 31)) & 1u) out[n++] = mother[4 * sh.r[r].step0 + pos];
+  }
+}
+
 int msc_init_constants() {
+  {
+    uint16_t rev[1536];
+    dabgpu_build_freq_deint(rev);
+    CUDA_TRY(cudaMemcpyToSymbol(g_rev1536, rev, sizeof rev));
+    static uint8_t grp[2304];
+    host_null_fic_group(grp);
+    CUDA_TRY(cudaMemcpyToSymbol(g_null_fic_group, grp, sizeof grp));
+  }
   CUDA_TRY(cudaMemcpyToSymbol(c_tdi_slot, DABGPU_TDI_DELAY, 16));
   uint16_t p[16];
   // x^8 mod P: a CRC register holding 1 shifted by one byte
@@ -433,6 +473,170 @@ int launch_eti_pack(const EtiJob *d_jobs, const EnsDev *d_ens, const uint8_t *d_
                     int n_frames, cudaStream_t st) {
   if (n_frames <= 0) return DABGPU_OK;
   eti_pack_kernel<<<(n_frames + 3) / 4, 128, 0, st>>>(d_jobs, d_ens, d_fibs, d_eti, n_frames);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// ---- Wavefinder producer (input_wf.c:23-115) -----------------------------------------
+// One CTA per 524-byte USB packet: byte 2 is the symbol number (2..4 FIC, 5..76 MSC), bytes 12..395
+// are 192 little-endian words of 8 DQPSK decisions each in carrier order; wf_demap_symbol's combined
+// frequency de-interleave + demap (input_wf.c:23-40) writes them as the common byte-per-bit symbol.
+// tf_ring: [S][5][230400], the reference's dab->tfs[5]; slot[s] = dab->tfidx of stream s.
+__global__ void __launch_bounds__(192) wf_demap_kernel(const uint8_t *__restrict__ packets, uint64_t pitch,
+                                                       const int32_t *__restrict__ n_packets,
+                                                       const int32_t *__restrict__ slot, uint8_t *__restrict__ tf_ring,
+                                                       uint32_t *__restrict__ fic_seen) {
+  const int s = blockIdx.y;
+  if ((int)blockIdx.x >= n_packets[s]) return;
+  const uint8_t *pkt = packets + (uint64_t)s * pitch + (uint64_t)blockIdx.x * 524u;
+  const int sym = pkt[2];
+  if (sym < 2 || sym > 76) return;  // NULL and phase reference symbols carry no data
+  uint8_t *dst = tf_ring + ((uint64_t)s * 5u + (uint32_t)slot[s]) * 230400u + (uint32_t)(sym - 2) * 3072u;
+  const int i = threadIdx.x;
+  const uint32_t k = (uint32_t)pkt[12 + 2 * i] | ((uint32_t)pkt[13 + 2 * i] << 8);
+#pragma unroll
+  for (int p = 0; p < 8; p++) {
+    const uint32_t qq = g_rev1536[8 * i + p];
+    dst[qq] = (uint8_t)((k >> (15 - 2 * p)) & 1u);
+    dst[qq + 1536] = (uint8_t)((k >> (14 - 2 * p)) & 1u);
+  }
+  if (i == 0 && sym <= 4) atomicOr(&fic_seen[s], 1u << (sym - 2));
+}
+// tfs[tfidx] of every stream -> the contiguous frame batch process_demapped() takes; a stream that
+// did not receive all three FIC symbols gets the channel bits of NULL FIBs instead, which the FIC
+// chain then decodes to exactly what fic_decode() substitutes for has_fic == 0 (fic.c:167-175)
+__global__ void __launch_bounds__(256) wf_finish_kernel(const uint8_t *__restrict__ tf_ring,
+                                                        const int32_t *__restrict__ slot,
+                                                        const uint32_t *__restrict__ fic_seen,
+                                                        uint8_t *__restrict__ out) {
+  const int s = blockIdx.y;
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;  // 16-byte vector of the 230400-byte frame
+  if (v >= 230400u / 16u) return;
+  const uint8_t *src = tf_ring + ((uint64_t)s * 5u + (uint32_t)slot[s]) * 230400u;
+  uint4 val = reinterpret_cast<const uint4 *>(src)[v];
+  if (v < 9216u / 16u && fic_seen[s] != 7u) val = reinterpret_cast<const uint4 *>(g_null_fic_group)[v % 144u];
+  reinterpret_cast<uint4 *>(out + (uint64_t)s * 230400u)[v] = val;
+}
+
+int launch_wf_demap(const uint8_t *d_packets, uint64_t pitch, const int32_t *d_n_packets, int max_packets,
+                    const int32_t *d_slot, uint8_t *d_tf_ring, uint32_t *d_fic_seen, uint8_t *d_tf_out, int n_streams,
+                    cudaStream_t st) {
+  if (n_streams <= 0) return DABGPU_OK;
+  CUDA_TRY(cudaMemsetAsync(d_fic_seen, 0, (size_t)n_streams * 4, st));
+  if (max_packets > 0) {
+    wf_demap_kernel<<<dim3(max_packets, n_streams), 192, 0, st>>>(d_packets, pitch, d_n_packets, d_slot, d_tf_ring,
+                                                                   d_fic_seen);
+    LAUNCH_CHECK();
+  }
+  wf_finish_kernel<<<dim3((230400 / 16 + 255) / 256, n_streams), 256, 0, st>>>(d_tf_ring, d_slot, d_fic_seen, d_tf_out);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// ---- ETI consumers on the device ---------------------------------------------------
+// eti2mpa.c:32-67 per frame: FICF / NST from the FC, walk the STC for the SubChId, copy the
+// sub-channel's STL*8 bytes from the MST.  One warp per frame.  Unlike eti2mpa, which latches offset
+// and length from its first frame, every frame is parsed, so a re-organised multiplex is followed.
+// out_len[f] = bytes written for frame f, or -1 when the frame does not carry the sub-channel.
+__global__ void __launch_bounds__(128) eti_extract_kernel(const uint8_t *__restrict__ eti_all, int n_frames,
+                                                          int subchid, uint8_t *__restrict__ out, uint64_t out_pitch,
+                                                          int32_t *__restrict__ out_len) {
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= n_frames) return;
+  const uint8_t *eti = eti_all + (size_t)f * DABGPU_ETI_BYTES;
+  const uint32_t ficf = eti[5] >> 7, nst = eti[5] & 0x7fu;
+  // lane j looks at STC entries j, j+32: SubChId match and the STLs before it
+  uint32_t before = 0;
+  int32_t len = -1, hit = 0x7fffffff;
+  for (uint32_t j = lane; j < nst; j += 32) {
+    const uint8_t *w = eti + 8 + 4 * j;
+    if ((int)(w[0] >> 2) == subchid && (int32_t)j < hit) hit = (int32_t)j;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) hit = min(hit, __shfl_xor_sync(0xffffffffu, hit, o));
+  if (hit != 0x7fffffff) {
+    for (uint32_t j = lane; j < (uint32_t)hit; j += 32) {
+      const uint8_t *w = eti + 8 + 4 * j;
+      before += ((((uint32_t)w[2] & 3u) << 8) | w[3]) * 8u;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) before += __shfl_xor_sync(0xffffffffu, before, o);
+    const uint8_t *w = eti + 8 + 4 * hit;
+    len = (int32_t)(((((uint32_t)w[2] & 3u) << 8) | w[3]) * 8u);
+    const uint32_t src0 = 12u + 4u * nst + ficf * 96u + before;
+    if (src0 + (uint32_t)len > DABGPU_ETI_BYTES || (uint64_t)len > out_pitch) {
+      len = -1;  // a corrupt header must not read or write out of bounds
+    } else {
+      uint8_t *dst = out + (uint64_t)f * out_pitch;
+      // the MST starts 4-byte aligned (12 + 4 NST + 96) and sub-channel sizes are multiples of 8
+      const uint32_t *s4 = reinterpret_cast<const uint32_t *>(eti + src0);
+      if ((out_pitch & 3) == 0 && ((uintptr_t)out & 3) == 0)
+        for (uint32_t i = lane; i < (uint32_t)len / 4; i += 32) reinterpret_cast<uint32_t *>(dst)[i] = s4[i];
+      else
+        for (uint32_t i = lane; i < (uint32_t)len; i += 32) dst[i] = eti[src0 + i];
+    }
+  }
+  if (lane == 0) out_len[f] = len;
+}
+
+int launch_eti_extract(const uint8_t *d_eti, int n_frames, int subchid, uint8_t *d_out, uint64_t out_pitch,
+                       int32_t *d_len, cudaStream_t st) {
+  if (n_frames <= 0) return DABGPU_OK;
+  eti_extract_kernel<<<(n_frames + 3) / 4, 128, 0, st>>>(d_eti, n_frames, subchid, d_out, out_pitch, d_len);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// Frame check ("Check Sync etc", eti2mpa.c:37; TODO.md:10-11): per frame a bit mask of what is wrong
+// with an ETI(NI) frame as misc.c:153-296 builds it -- ERR/FSYNC, header CRC, FL against the STC,
+// end-of-frame CRC over the MST, padding.  0 = frame is consistent.
+__global__ void __launch_bounds__(128) eti_check_kernel(const uint8_t *__restrict__ eti_all, int n_frames,
+                                                        uint32_t *__restrict__ flags) {
+  __shared__ uint16_t crc_tab[256];
+  for (uint32_t b = threadIdx.x; b < 256; b += blockDim.x) crc_tab[b] = (uint16_t)crc_byte(0u, b);
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int f = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (f >= n_frames) return;
+  const uint8_t *eti = eti_all + (size_t)f * DABGPU_ETI_BYTES;
+  uint32_t bad = 0;
+  const uint32_t sync = ((uint32_t)eti[1] << 16) | ((uint32_t)eti[2] << 8) | eti[3];
+  if (eti[0] != 0xff || (sync != 0x073ab6u && sync != 0xf8c549u)) bad |= DABGPU_ETI_BAD_SYNC;
+  if (((sync == 0xf8c549u) ? 1u : 0u) != (eti[4] & 1u)) bad |= DABGPU_ETI_BAD_SYNC;  // FSYNC alternates with FCT
+  const uint32_t ficf = eti[5] >> 7, nst = eti[5] & 0x7fu;
+  const uint32_t fl = (((uint32_t)eti[6] & 7u) << 8) | eti[7];
+  const uint32_t eoh = 8 + 4 * nst;
+  uint32_t stl_sum = 0;
+  for (uint32_t j = lane; j < nst; j += 32) stl_sum += (((uint32_t)eti[8 + 4 * j + 2] & 3u) << 8) | eti[8 + 4 * j + 3];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) stl_sum += __shfl_xor_sync(0xffffffffu, stl_sum, o);
+  const uint32_t mst = ficf * 96u + 8u * stl_sum;
+  if (fl != nst + 1 + ficf * 24u + 2u * stl_sum || ((eti[6] >> 3) & 3u) != 1u) bad |= DABGPU_ETI_BAD_FC;
+  if (eoh + 4 + mst + 8 > DABGPU_ETI_BYTES) {
+    bad |= DABGPU_ETI_BAD_FC;
+  } else {
+    uint32_t crc = 0xffffu;  // header CRC over FC + STC + MNSC (misc.c:207-211)
+    if (lane == 0) {
+      for (uint32_t i = 4; i < eoh + 2; i++) crc = crc_byte_tab(crc_tab, crc, eti[i]);
+      crc = ~crc & 0xffffu;
+      if (crc != (((uint32_t)eti[eoh + 2] << 8) | eti[eoh + 3])) bad |= DABGPU_ETI_BAD_HCRC;
+    }
+    const uint32_t e1 = eoh + 4, e = e1 + mst;
+    const uint32_t c2 = ~warp_crc16(crc_tab, eti + e1, mst, lane) & 0xffffu;
+    if (c2 != (((uint32_t)eti[e] << 8) | eti[e + 1])) bad |= DABGPU_ETI_BAD_EOF_CRC;
+    uint32_t padbad = 0;
+    for (uint32_t i = e + 8 + lane; i < DABGPU_ETI_BYTES; i += 32) padbad |= eti[i] != 0x55;
+    if (__any_sync(0xffffffffu, padbad)) bad |= DABGPU_ETI_BAD_PADDING;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  if (lane == 0) flags[f] = bad;
+}
+
+int launch_eti_check(const uint8_t *d_eti, int n_frames, uint32_t *d_flags, cudaStream_t st) {
+  if (n_frames <= 0) return DABGPU_OK;
+  eti_check_kernel<<<(n_frames + 3) / 4, 128, 0, st>>>(d_eti, n_frames, d_flags);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }

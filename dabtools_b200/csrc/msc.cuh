@@ -72,4 +72,14 @@ struct EtiJob {
 int launch_eti_pack(const EtiJob *d_jobs, const EnsDev *d_ens, const uint8_t *d_fibs, uint8_t *d_eti,
                     int n_frames, cudaStream_t st);
 
+// ---- Wavefinder producer (input_wf.c:23-115): USB packets -> demapped transmission frames --------
+int launch_wf_demap(const uint8_t *d_packets, uint64_t pitch, const int32_t *d_n_packets, int max_packets,
+                    const int32_t *d_slot, uint8_t *d_tf_ring, uint32_t *d_fic_seen, uint8_t *d_tf_out, int n_streams,
+                    cudaStream_t st);
+
+// ---- ETI consumers on the device (eti2mpa.c:32-67; TODO.md:10-11) ---------------------------
+int launch_eti_extract(const uint8_t *d_eti, int n_frames, int subchid, uint8_t *d_out, uint64_t out_pitch,
+                       int32_t *d_len, cudaStream_t st);
+int launch_eti_check(const uint8_t *d_eti, int n_frames, uint32_t *d_flags, cudaStream_t st);
+
 }  // namespace dabgpu

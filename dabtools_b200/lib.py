@@ -98,6 +98,33 @@ def fic_decode_batch_device(fic_bits, fibs, crc_ok):
                                          C.c_void_p(crc_ok.data_ptr()), 1))
 
 
+# ---- ETI consumers on the device ----------------------------------------------------------------------
+ETI_BAD_SYNC, ETI_BAD_FC, ETI_BAD_HCRC, ETI_BAD_EOF_CRC, ETI_BAD_PADDING = 1, 2, 4, 8, 16
+
+
+def eti_extract_subchannel(eti: np.ndarray, subchid: int, pitch: int = 4608):
+    """eti: uint8 [n][6144] (host) -> (data uint8 [n][pitch], lengths int32 [n]; -1 = not carried)"""
+    eti = np.ascontiguousarray(eti, dtype=np.uint8).reshape(-1, 6144)
+    n = eti.shape[0]
+    out = np.zeros((n, pitch), dtype=np.uint8)
+    lens = np.full(n, -1, dtype=np.int32)
+    lib = load()
+    lib.dabgpu_eti_extract_subchannel.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p,
+                                                  C.c_int]
+    check(lib.dabgpu_eti_extract_subchannel(_np_ptr(eti), n, subchid, _np_ptr(out), pitch, _np_ptr(lens), 0))
+    return out, lens
+
+
+def eti_check(eti: np.ndarray) -> np.ndarray:
+    """eti: uint8 [n][6144] (host) -> uint32 [n] masks of ETI_BAD_* (0 = consistent frame)"""
+    eti = np.ascontiguousarray(eti, dtype=np.uint8).reshape(-1, 6144)
+    flags = np.zeros(eti.shape[0], dtype=np.uint32)
+    lib = load()
+    lib.dabgpu_eti_check.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int]
+    check(lib.dabgpu_eti_check(_np_ptr(eti), eti.shape[0], _np_ptr(flags), 0))
+    return flags
+
+
 # ---- single-frame front-end ------------------------------------------------------------------------
 def sync_frame(frame: np.ndarray, force_timesync: int = 0) -> dict:
     frame = np.ascontiguousarray(frame, dtype=np.uint8).ravel()
@@ -180,6 +207,14 @@ class Engine:
         m = None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
         check(self._lib.dabgpu_engine_process_demapped(self._h, _np_ptr(tfs), tfs.shape[1],
                                                        None if m is None else _np_ptr(m), 0))
+        return self._lib.dabgpu_engine_eti_count(self._h)
+
+    def process_wavefinder(self, packets: np.ndarray, n_packets) -> int:
+        """packets: uint8 [n_streams][max_packets*524] (host), n_packets: per-stream packet counts"""
+        packets = np.ascontiguousarray(packets, dtype=np.uint8).reshape(self.n_streams, -1)
+        n = np.ascontiguousarray(n_packets, dtype=np.int32)
+        self._lib.dabgpu_engine_process_wavefinder.argtypes = [C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+        check(self._lib.dabgpu_engine_process_wavefinder(self._h, _np_ptr(packets), packets.shape[1], _np_ptr(n)))
         return self._lib.dabgpu_engine_eti_count(self._h)
 
     # device buffers (torch CUDA tensors) ------------------------------------------------------
@@ -306,6 +341,42 @@ def _engine_feed_capture(self, chunk_len: int) -> int:
     return self._lib.dabgpu_engine_eti_count(self._h)
 
 
+def _engine_extract_subchannel(self, subchid: int, pitch: int = 4608):
+    """sub-channel bytes of the last call's ETI frames, extracted on the device (eti2mpa.c:32-67)"""
+    n = self.eti_count()
+    out = np.zeros((max(n, 1), pitch), dtype=np.uint8)
+    lens = np.full(max(n, 1), -1, dtype=np.int32)
+    self._lib.dabgpu_engine_extract_subchannel.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_size_t, C.c_void_p]
+    got = self._lib.dabgpu_engine_extract_subchannel(self._h, subchid, _np_ptr(out), pitch, _np_ptr(lens))
+    if got < 0:
+        check(got)
+    return out[:n], lens[:n]
+
+
+def _engine_check_eti(self) -> np.ndarray:
+    n = self.eti_count()
+    flags = np.zeros(max(n, 1), dtype=np.uint32)
+    self._lib.dabgpu_engine_check_eti.argtypes = [C.c_void_p, C.c_void_p]
+    got = self._lib.dabgpu_engine_check_eti(self._h, _np_ptr(flags))
+    if got < 0:
+        check(got)
+    return flags[:n]
+
+
+def _engine_pump(self, in_fds, out_fds=None, max_callbacks: int = -1) -> int:
+    """dabgpu_engine_pump: stream every in_fds[s] through the engine into out_fds[s]; returns ETI frames written"""
+    n = self.n_streams
+    assert len(in_fds) == n and (out_fds is None or len(out_fds) == n)
+    a = (C.c_int * n)(*in_fds)
+    b = (C.c_int * n)(*out_fds) if out_fds is not None else None
+    self._lib.dabgpu_engine_pump.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_longlong]
+    self._lib.dabgpu_engine_pump.restype = C.c_longlong
+    got = self._lib.dabgpu_engine_pump(self._h, n, a, b, max_callbacks)
+    if got < 0:
+        check(int(got))
+    return int(got)
+
+
 def _engine_set_capture_cyclic(self, on: bool = True):
     self._lib.dabgpu_engine_set_capture_cyclic.argtypes = [C.c_void_p, C.c_int]
     check(self._lib.dabgpu_engine_set_capture_cyclic(self._h, int(on)))
@@ -319,6 +390,9 @@ def _engine_set_subchannel_mask(self, mask: int, stream: int = -1):
 Engine.set_subchannel_mask = _engine_set_subchannel_mask
 Engine.attach_capture = _engine_attach_capture
 Engine.set_capture_cyclic = _engine_set_capture_cyclic
+Engine.pump = _engine_pump
+Engine.extract_subchannel = _engine_extract_subchannel
+Engine.check_eti = _engine_check_eti
 Engine.feed_capture = _engine_feed_capture
 Engine.submit_iq = _engine_submit_iq
 Engine.feed_submitted = _engine_feed_submitted

@@ -304,6 +304,26 @@ def fic_groups(n_groups: int, seed: int = 0, flips=(0.0, 0.01, 0.04, 0.08)):
     return bits, fibs
 
 
+def wavefinder_packets(bits_tf: np.ndarray, drop=()) -> np.ndarray:
+    """One transmission frame of ideal demapped bits (uint8 [230400]: 3 FIC + 72 MSC symbols of 3072)
+    as the Psion Wavefinder delivers it over USB (input_wf.c:23-115 in reverse): 524-byte packets,
+    byte 2 = symbol number (1 = PRS, 2..76 data, 0 = the NULL symbol that ends the frame), bytes 12..395
+    = 192 little-endian words of 8 DQPSK decisions each in carrier order.  `drop`: symbol numbers lost."""
+    rev = T.freq_deint().astype(np.int64)
+    sym = np.asarray(bits_tf, dtype=np.uint8).reshape(75, 3072)
+    b0 = sym[:, rev].reshape(75, 192, 8).astype(np.uint16)          # carrier order: dst[rev[q]] = b0
+    b1 = sym[:, 1536 + rev].reshape(75, 192, 8).astype(np.uint16)
+    sh0 = (15 - 2 * np.arange(8)).astype(np.uint16)
+    words = np.ascontiguousarray(((b0 << sh0) | (b1 << (sh0 - 1))).sum(axis=2).astype("<u2"))
+    order = [1] + [n for n in range(2, 77) if n not in drop] + [0]
+    pk = np.zeros((len(order), 524), dtype=np.uint8)
+    for i, n in enumerate(order):
+        pk[i, 2] = n
+        if n >= 2:
+            pk[i, 12:396] = words[n - 2].view(np.uint8)
+    return pk
+
+
 def expected_eti_payload(ens: Ensemble, payload: dict, stream: int, logical_cif: int) -> bytes:
     """MST sub-channel bytes of the ETI frame that carries logical CIF `logical_cif`."""
     return b"".join(bytes(payload[s.id][stream, logical_cif].cpu().numpy()) for s in ens.subchannels)

@@ -119,6 +119,9 @@ int dabgpu_engine_feed_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int
  * makes it asynchronous) and returns; feed_submitted() processes the oldest submitted chunk.  At
  * most three chunks may be in flight.  feed_iq(host pointer) == submit_iq + feed_submitted. */
 int dabgpu_engine_submit_iq(dabgpu_engine *e, const uint8_t *iq, size_t pitch, int chunk_len);
+/* how many of the chunks given to submit_iq() are still being copied (their host buffers must not
+ * be overwritten yet); copies complete in submission order */
+int dabgpu_engine_uploads_in_flight(dabgpu_engine *e);
 /* Zero-copy source for samples that already are in device memory as one contiguous capture per
  * stream (a recording loaded into HBM, or the output buffer of a device-side producer): stream s
  * at iq_device + s * pitch, `len` bytes each.  attach_capture() must precede the first samples;
@@ -140,6 +143,18 @@ int dabgpu_engine_feed_submitted(dabgpu_engine *e);
  * equivalent to dab_process_frame per stream. */
 int dabgpu_engine_process_demapped(dabgpu_engine *e, const uint8_t *tfs, size_t pitch, const uint8_t *mask,
                                    int on_device);
+/* Second producer of demapped transmission frames: the Psion Wavefinder's USB packets
+ * (input_wf.c:23-115).  packets + s*pitch holds n_packets[s] packets of 524 bytes -- the symbols of
+ * ONE transmission frame of stream s as the device delivers them between two NULL-symbol packets
+ * (byte 2 = symbol number: 2..4 FIC, 5..76 MSC, others ignored; bytes 12..395 = 192 little-endian
+ * words of DQPSK decisions in carrier order); n_packets[s] == 0: no frame for that stream.  Each
+ * frame is de-interleaved and demapped on the device (wf_demap_symbol) and handed to the same
+ * back-end as process_demapped; a frame without all three FIC symbols gets NULL FIBs like
+ * fic_decode does for has_fic == 0 (fic.c:167-175), symbols that did not arrive keep the content the
+ * frame buffer had five frames earlier (dab->tfs[5]).  The device's own timing/AFC loop
+ * (wf_sync.c) needs the hardware and is not part of this path.  Host pointers. */
+int dabgpu_engine_process_wavefinder(dabgpu_engine *e, const uint8_t *packets, size_t pitch,
+                                     const int32_t *n_packets);
 /* Let the MSC decoding (time de-interleave -> Viterbi -> ETI) lag so that one launch covers the
  * frames of `calls` (1..4) frame-producing feed/process calls: more, better balanced work per
  * launch; frames then come out in bursts.  dabgpu_engine_flush() decodes whatever is queued (call
@@ -176,6 +191,39 @@ int dabgpu_engine_kernel_times(dabgpu_engine *e, double *ms_total, uint64_t *lau
 /* cumulative host wall-clock microseconds: control build, waiting for the GPU, state machines,
  * job construction */
 void dabgpu_engine_host_times(dabgpu_engine *e, double *us4);
+
+/* Streaming ingest front: dab2eti's rtlsdr_read_async + demod_thread_fn pair (dab2eti.c:60-135,
+ * 237-239) for n_streams sources at once.  Reads 262144-byte callbacks from in_fds[s] (recording,
+ * FIFO, `rtl_sdr -` pipe; blocking reads pace a live source), keeps the engine fed through
+ * submit_iq / feed_submitted with uploads two callbacks ahead, and writes every 6144-byte ETI frame
+ * of stream s to out_fds[s] like eti_callback does (out_fds or single entries may be NULL / -1).
+ * Returns at the first source that ends (or after max_callbacks callbacks per stream when >= 0),
+ * after flushing the engine: the number of ETI frames written, or a negative DABGPU_ERR_*. */
+long long dabgpu_engine_pump(dabgpu_engine *e, int n_streams, const int *in_fds, const int *out_fds,
+                             long long max_callbacks);
+
+/* ---- ETI consumers on the device (what follows the path: SURVEY 8f-3) ---------------------------
+ * dabgpu_eti_extract_subchannel: eti2mpa.c:32-67 for a batch of frames -- for every 6144-byte frame
+ * at eti + f*6144 the bytes of sub-channel `subchid` (STL*8 of them, located through the STC) are
+ * copied to out + f*out_pitch and their count to out_len[f] (-1: the frame does not carry it).
+ * eti/out/out_len are device pointers when on_device != 0 (asynchronous on the current stream),
+ * host pointers otherwise.  out_pitch >= the sub-channel's size (at most 4608 = 384 kbit/s).
+ * dabgpu_eti_check: per frame a mask of DABGPU_ETI_BAD_* (0 = consistent frame): ERR/FSYNC and its
+ * alternation with FCT, FC (MID, FL against the STC), header CRC, end-of-frame CRC, 0x55 padding
+ * (misc.c:153-296; the reference's TODO "check the details of the ETI stream"). */
+#define DABGPU_ETI_BAD_SYNC 1u
+#define DABGPU_ETI_BAD_FC 2u
+#define DABGPU_ETI_BAD_HCRC 4u
+#define DABGPU_ETI_BAD_EOF_CRC 8u
+#define DABGPU_ETI_BAD_PADDING 16u
+int dabgpu_eti_extract_subchannel(const uint8_t *eti, int n_frames, int subchid, uint8_t *out, size_t out_pitch,
+                                  int32_t *out_len, int on_device);
+int dabgpu_eti_check(const uint8_t *eti, int n_frames, uint32_t *flags, int on_device);
+/* The same on the ETI frames of the engine's last feed/process/flush call, where they lie in HBM
+ * (dabgpu_engine_eti_device): nothing but the extracted bytes / the flags crosses PCIe. */
+int dabgpu_engine_extract_subchannel(dabgpu_engine *e, int subchid, uint8_t *out_host, size_t out_pitch,
+                                     int32_t *out_len_host);
+int dabgpu_engine_check_eti(dabgpu_engine *e, uint32_t *flags_host);
 
 /* ---- ABI self-description (sizeof / offsetof of include/dabgpu_ref_abi.h's structs) -------- */
 int dabgpu_sizeof_dab_state(void);

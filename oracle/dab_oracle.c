@@ -364,6 +364,7 @@ struct orc_tf {
   uint8_t fibs[384];
   uint8_t crc_ok[12];
   int ok_count;
+  int no_fic; /* Wavefinder frame without all three FIC symbols (tf->has_fic == 0) */
 };
 
 struct orc_rx {
@@ -439,7 +440,17 @@ static void create_eti(struct orc_rx *rx) {
 void orc_rx_process_frame(struct orc_rx *rx) {
   struct orc_tf *tf = &rx->tfs[rx->tfidx];
   rx->last = tf;
-  tf->ok_count = orc_fic_decode(tf->fic, tf->fibs, tf->crc_ok);
+  if (tf->no_fic) { /* fic.c:167-175: no FIC in the received data, replace with NULL FIBs */
+    static const uint8_t null_fib[32] = {0xff, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0,
+                                         0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0xa8, 0xa8};
+    for (int i = 0; i < 12; i++) {
+      memcpy(tf->fibs + 32 * i, null_fib, 32);
+      tf->crc_ok[i] = 1;
+    }
+    tf->ok_count = 12;
+  } else {
+    tf->ok_count = orc_fic_decode(tf->fic, tf->fibs, tf->crc_ok);
+  }
   if (tf->ok_count > 0) orc_fib_decode(&rx->tf_info, tf->fibs, tf->crc_ok, 12);
 
   if (tf->ok_count == 12) {
@@ -866,6 +877,50 @@ long orc_run_iq(const uint8_t *iq, long nbytes, int chunk, uint32_t f0, unsigned
   if (n_tfs) *n_tfs = tfs;
   free(cbuf);
   sdr_free(s);
+  orc_rx_free(rx);
+  return sink.n;
+}
+
+/* Wavefinder producer: input_wf.c:23-40 (wf_demap_symbol), :65-115 (wf_read_frame) and the loop of
+ * do_wf_decode (dab2eti.c:251-272) over a buffer of 524-byte USB packets; the device's timing loop
+ * (wf_sync.c) is taken as locked, as in oracle/ref_harness.c:ref_run_wf */
+static void wf_demap_symbol(uint8_t *dst, const uint8_t *src, const uint16_t *rev) {
+  int q = 0;
+  for (int i = 0; i < 192; i++, src += 2) {
+    const int k = (src[1] << 8) | src[0];
+    for (int j = 15; j > 0; j -= 2, q++) {
+      dst[rev[q]] = (uint8_t)((k >> j) & 1);
+      dst[rev[q] + 1536] = (uint8_t)((k >> (j - 1)) & 1);
+    }
+  }
+}
+/* returns 0 with a complete frame in *tf, 1 at the end of the packets */
+static int wf_read_frame(const uint8_t *packets, long n_packets, long *pos, struct orc_tf *tf, const uint16_t *rev) {
+  int fic_read[3] = {0, 0, 0};
+  while (*pos < n_packets) {
+    const uint8_t *buf = packets + 524 * (*pos)++;
+    const int symbol = buf[2];
+    if (symbol == 1) continue; /* PRS: wf_prs_assemble (hardware loop) */
+    if (symbol == 0) {
+      tf->no_fic = !(fic_read[0] && fic_read[1] && fic_read[2]);
+      return 0;
+    } else if (symbol <= 4) {
+      wf_demap_symbol(tf->fic + 3072 * (symbol - 2), buf + 12, rev);
+      fic_read[symbol - 2] = 1;
+    } else if (symbol <= 76) {
+      wf_demap_symbol(tf->msc + 3072 * (symbol - 5), buf + 12, rev);
+    }
+  }
+  return 1;
+}
+long orc_run_wf(const uint8_t *packets, long n_packets, uint8_t *eti_out, long eti_cap) {
+  struct eti_sink sink = {eti_out, eti_cap, 0};
+  struct orc_rx *rx = orc_rx_new(sink_cb, &sink);
+  uint16_t rev[1536];
+  long pos = 0;
+  dabgpu_build_freq_deint(rev);
+  if (wf_read_frame(packets, n_packets, &pos, &rx->tfs[0], rev) == 0) /* first frame: read and discarded */
+    while (wf_read_frame(packets, n_packets, &pos, &rx->tfs[rx->tfidx], rev) == 0) orc_rx_process_frame(rx);
   orc_rx_free(rx);
   return sink.n;
 }

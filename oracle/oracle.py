@@ -70,9 +70,8 @@ def build_port(force: bool = False) -> str:
 def build_ref(force: bool = False):
     so = os.path.join(HERE, "_ref", "libdabref.so")
     if os.path.isdir(REF_SRC):
-        srcs = [os.path.join(HERE, f) for f in ("ref_harness.c", "ref_shim/fftw_shim.c", "ref_shim/fftw3.h")]
-        if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-            subprocess.check_call(["make", "-C", HERE, "ref"], stdout=subprocess.DEVNULL)
+        # make tracks the dependencies (harness, shims, libdabgpu.so for the dab2eti drop-in build)
+        subprocess.check_call(["make", "-C", HERE, "ref"] + (["-B"] if force else []), stdout=subprocess.DEVNULL)
     return so if os.path.exists(so) else None
 
 
@@ -138,6 +137,13 @@ class _Common:
                          _p(tfs) if want_tfs else None, want_tfs, C.byref(n_tfs))
         return dict(eti=eti[:m].copy(), trace=trace[: n_calls.value], n_tfs=n_tfs.value,
                     tfs=tfs[: min(want_tfs, n_tfs.value)].copy())
+
+    def run_wf(self, packets: np.ndarray) -> np.ndarray:
+        """packets: uint8 [n][524] Wavefinder USB packets -> ETI [m][6144] (do_wf_decode, dab2eti.c:251-272)"""
+        packets = np.ascontiguousarray(packets, dtype=np.uint8).reshape(-1, 524)
+        eti = np.zeros((4 * (packets.shape[0] // 76 + 2), 6144), dtype=np.uint8)
+        m = self._run_wf(_p(packets), packets.shape[0], _p(eti), eti.size)
+        return eti[:m].copy()
 
     # ---- streaming receive loop (state kept across calls; bench.py --impl reference) -------------
     def stream_open(self, f0: int = 200_000_000, seed: int = 1):
@@ -229,6 +235,9 @@ class Port(_Common):
         self._run_iq = lib.orc_run_iq
         self._demod_frame = lib.orc_demod_frame
         _bind_stream(self, lib, "orc_stream_")
+        lib.orc_run_wf.argtypes = [u8p, C.c_long, u8p, C.c_long]
+        lib.orc_run_wf.restype = C.c_long
+        self._run_wf = lib.orc_run_wf
 
     def gen_metrics(self, amp=1, noise=1.0, bias=0.0, scale=4):
         t = np.zeros((2, 256), dtype=np.int32)
@@ -334,6 +343,9 @@ class Ref(_Common):
         self._run_iq = lib.ref_run_iq
         self._demod_frame = lib.ref_demod_frame
         _bind_stream(self, lib, "ref_stream_")
+        lib.ref_run_wf.argtypes = [u8p, C.c_long, u8p, C.c_long]
+        lib.ref_run_wf.restype = C.c_long
+        self._run_wf = lib.ref_run_wf
 
     def gen_metrics(self, amp=1, noise=1.0, bias=0.0, scale=4):
         t = np.zeros((2, 256), dtype=np.int32)

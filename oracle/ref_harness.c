@@ -304,6 +304,46 @@ int ref_demod_frame(const uint8_t *frame, int force_timesync, int32_t *coarse_ti
   return ok;
 }
 
+/* ---- Wavefinder producer: the reference's input_wf.c, unmodified, fed from a file of USB packets ----
+ * wf_read_frame() (input_wf.c:65-115) reads 524-byte packets from wf->fd and returns a frame at every
+ * NULL-symbol packet; do_wf_decode (dab2eti.c:251-272) discards the first frame and hands every
+ * further one to dab_process_frame.  The device's timing/AFC loop (wf_sync.c: wf_prs_assemble talks
+ * to the hardware through ioctls) cannot run without the device: it is stubbed and sync_locked is
+ * set, i.e. the stream is taken as already synchronised. */
+#include <unistd.h>
+#include "input_wf.h"
+int wf_prs_assemble(struct wavefinder_t *wf, unsigned char *buf) { (void)wf; (void)buf; return 0; }
+int wfsyncinit(void) { return 0; }
+
+long ref_run_wf(const uint8_t *packets, long n_packets, uint8_t *eti_out, long eti_cap) {
+  struct dab_state_t *dab = NULL;
+  struct wavefinder_t wf;
+  char path[] = "/tmp/ref_wf_XXXXXX";
+  int fd = mkstemp(path);
+  if (fd < 0) return -1;
+  unlink(path);
+  if (write(fd, packets, n_packets * 524) != n_packets * 524) return -1;
+  lseek(fd, 0, SEEK_SET);
+  memset(&wf, 0, sizeof wf);
+  wf.fd = fd;
+  g_eti_out = eti_out;
+  g_eti_cap = eti_cap;
+  g_eti_n = 0;
+  init_dab_state(&dab, &wf, collect_eti);
+  dab->device_type = DAB_DEVICE_WAVEFINDER;
+  wf_init(&wf);
+  wf.sync_locked = 1;
+  int stderr_copy = dup(2);  /* wf_read_frame reports the end of the file as a read error */
+  if (wf_read_frame(&wf, &dab->tfs[0]) == 0) {
+    while (wf_read_frame(&wf, &dab->tfs[dab->tfidx]) == 0) dab_process_frame(dab);
+  }
+  (void)stderr_copy;
+  close(fd);
+  free(dab);
+  g_eti_out = NULL;
+  return g_eti_n;
+}
+
 /* Accessors for file-static / extern tables the tests want to pin. */
 extern const uint16_t rev_freq_deint_tab[1536];
 extern fftw_complex prs_static[1536];

@@ -231,3 +231,78 @@ def test_subchannel_filter(gpu, port):
     nsts = [_parse_eti(fr)[0] for fr in mixed[0]]
     assert nsts[:8] == [3] * 8 and nsts[-4:] == [2] * 4 and sorted(set(nsts)) == [2, 3]
     assert all(_parse_eti(fr)[3] for fr in mixed[0])
+
+
+@pytest.mark.parametrize("batch", [1, 2, 4])
+def test_multiplex_reorganisation_mid_stream(gpu, port, batch):
+    """SURVEY 8f-2 / TODO.md:3.  The sub-channel table changes while the receiver is locked and (with
+    batch > 1) while ETI frames of the old layout are still queued for a deferred MSC launch: one
+    sub-channel moves and changes protection, a new one appears, two streams switch at different
+    transmission frames and a third never does.  The reference has no reconfiguration handling: FIG
+    0/1 entries overwrite ens_info as they arrive (fic.c:62-93, misc.c:14-27) and every ETI frame is
+    built with the table of the moment (misc.c:153-278) -- the engine must do exactly that, frame
+    for frame, so the oracle fed the same FIBs is the expected output."""
+    A = synth.small_ensemble()
+    B = synth.Ensemble([synth.SubChannel(id=3, start_cu=0, uep_index=35),
+                        synth.SubChannel(id=7, start_cu=250, eep_level=1, size_cu=64),
+                        synth.SubChannel(id=20, start_cu=400, uep_index=16)])
+    n_a = (22, 19, 36)
+    n_tf = 36
+    rows = []
+    for s, na in enumerate(n_a):
+        ga = synth.ModeITransmitter(A).generate(1, na, seed=51 + s, want_iq=False)
+        parts = [ga["bits"][0].numpy()]
+        if na < n_tf:
+            gb = synth.ModeITransmitter(B).generate(1, n_tf - na, seed=61 + s, want_iq=False, first_cif=4 * na)
+            parts.append(gb["bits"][0].numpy())
+        rows.append(np.concatenate(parts))
+    bits = np.stack(rows)
+    got, st = _run_engine(gpu, bits, msc_batch=batch)
+    for s in range(3):
+        want, _, _ = port.run_backend(bits[s])
+        assert got[s].shape == want.shape and want.shape[0] == 4 * (n_tf - 13), (s, got[s].shape, want.shape)
+        assert np.array_equal(got[s], want), s
+    nst = [[int(f[5] & 0x7F) for f in g] for g in got]
+    assert set(nst[0]) == {3, 4} and set(nst[1]) == {3, 4} and set(nst[2]) == {3}     # the switch happened
+    assert nst[0].index(4) != nst[1].index(4)
+    assert all(x.locked == 1 for x in st)
+
+
+def test_wavefinder_packets_as_second_producer(gpu, port):
+    """the Psion Wavefinder's USB packets (input_wf.c:23-115) as a producer of demapped
+    transmission frames for the same back-end.  Stream 0 loses a FIC symbol in one frame (has_fic = 0
+    -> NULL FIBs, fic.c:167-175), two MSC symbols in another (the frame buffer keeps what it held
+    five frames earlier) and all FIC symbols in a third; stream 1 is clean; stream 2 skips a frame
+    altogether.  ETI byte for byte as do_wf_decode (dab2eti.c:251-272) produces it in the oracle,
+    which tests/test_oracle_vs_ref.py pins against the reference's unmodified input_wf.c."""
+    ens = synth.small_ensemble()
+    S, n_tf = 3, 23
+    g = synth.ModeITransmitter(ens).generate(S, n_tf, seed=71, want_iq=False)
+    bits = g["bits"].numpy()
+    drops = {0: {16: (3,), 18: (40, 41), 19: (2, 3, 4)}, 1: {}, 2: {}}
+    skip = {2: {17}}                                    # stream 2 delivers no frame in call 17
+    per_stream = [[None if t in skip.get(s, ()) else synth.wavefinder_packets(bits[s, t], drop=drops[s].get(t, ()))
+                   for t in range(n_tf)] for s in range(S)]
+    eng = gpu.Engine(S)
+    out = [[] for _ in range(S)]
+    for t in range(1, n_tf):                            # the first frame is read and discarded (dab2eti.c:262)
+        pk = np.zeros((S, 77 * 524), np.uint8)
+        n = np.zeros(S, np.int32)
+        for s in range(S):
+            p = per_stream[s][t]
+            if p is None:
+                continue
+            n[s] = p.shape[0]
+            pk[s, : p.size] = p.reshape(-1)
+        k = eng.process_wavefinder(pk, n)
+        eti, ids = eng.fetch_eti()
+        assert eti.shape[0] == k
+        for f, s in zip(eti, ids):
+            out[s].append(f.copy())
+    eng.close()
+    for s in range(S):
+        stream = np.concatenate([p for p in per_stream[s] if p is not None])
+        want = port.run_wf(stream)
+        got = np.array(out[s], dtype=np.uint8).reshape(-1, 6144)
+        assert got.shape == want.shape and want.shape[0] >= 28, (s, got.shape, want.shape)
+        assert np.array_equal(got, want), s

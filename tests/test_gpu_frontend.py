@@ -232,3 +232,55 @@ def test_virtual_tuner_converges_like_the_reference(gpu, port, cfo):
     # final tuner frequency within 60 Hz of the true offset for both
     assert abs((trace[0][-1][6] - 200_000_000) - cfo) < 60
     assert abs((int(want["trace"][-1]["frequency"]) - 200_000_000) - cfo) < 60
+
+
+def test_streaming_pump_from_file_descriptors(gpu, port, tmp_path):
+    """dabgpu_engine_pump: three recordings read from file descriptors like
+    rtlsdr_read_async would deliver them, ETI written to one descriptor per stream like eti_callback:
+    the files hold exactly the oracle's frames; a pipe works as a source too."""
+    import os
+    import threading
+    ens = synth.small_ensemble()
+    S, n_tf = 3, 21
+    g = synth.ModeITransmitter(ens).generate(S, n_tf, seed=29, snr_db=30, tail_samples=262144)
+    iq_full = g["iq"].numpy()
+    cuts = [0, 99000, 31000]
+    n = min(iq_full.shape[1] - 2 * c for c in cuts) // 262144 * 262144
+    iq = np.stack([iq_full[s, 2 * c: 2 * c + n] for s, c in enumerate(cuts)])
+    for batch in (1, 4):
+        ins, outs, fds = [], [], []
+        for s in range(S):
+            p = tmp_path / f"cap{s}.iq"
+            iq[s].tofile(p)
+            o = tmp_path / f"out{batch}_{s}.eti"
+            outs.append(o)
+            fds.append(os.open(o, os.O_WRONLY | os.O_CREAT | os.O_TRUNC))
+            ins.append(os.open(p, os.O_RDONLY))
+        # stream 1 comes through a pipe fed by a thread (a live source: short reads, blocking)
+        r, w = os.pipe()
+        os.close(ins[1])
+        ins[1] = r
+
+        def feeder():
+            data = iq[1].tobytes()
+            for pos in range(0, len(data), 100000):
+                os.write(w, data[pos: pos + 100000])
+            os.close(w)
+
+        th = threading.Thread(target=feeder)
+        th.start()
+        eng = gpu.Engine(S)
+        eng.set_msc_batch(batch)
+        total = eng.pump(ins, fds)
+        eng.close()
+        th.join()
+        for fd in ins + fds:
+            os.close(fd)
+        got_total = 0
+        for s in range(S):
+            want = port.run_iq(iq[s])["eti"]
+            got = np.fromfile(outs[s], dtype=np.uint8).reshape(-1, 6144)
+            assert got.shape == want.shape and want.shape[0] >= 16, (batch, s, got.shape, want.shape)
+            assert np.array_equal(got, want), (batch, s)
+            got_total += got.shape[0]
+        assert total == got_total

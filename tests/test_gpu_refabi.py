@@ -130,3 +130,76 @@ def test_c_host_program_is_a_drop_in(gpu, port, tmp_path):
     want = port.run_iq(iq[:n])["eti"]
     assert eti.shape == want.shape and eti.shape[0] >= 8
     assert np.array_equal(eti, want)
+
+
+def test_unmodified_reference_dab2eti_links_and_runs_on_libdabgpu(gpu, port, tmp_path):
+    """oracle/_ref/dab2eti_gpu is the reference's own src/dab2eti.c, unmodified and compiled against the
+    reference's own headers, linked with libdabgpu.so INSTEAD of the reference's objects (plus a
+    file-backed librtlsdr, oracle/ref_shim/rtlsdr_file.c; see oracle/Makefile).  Same capture in,
+    same ETI bytes out as the same dab2eti.c linked with the reference's objects (dab2eti_ref) and
+    as the oracle.  Built in the build container (needs /root/reference); skipped where absent."""
+    import os
+    import subprocess
+    from conftest import ROOT
+    exe_gpu = os.path.join(ROOT, "oracle", "_ref", "dab2eti_gpu")
+    exe_ref = os.path.join(ROOT, "oracle", "_ref", "dab2eti_ref")
+    if not os.path.exists(exe_gpu):
+        pytest.skip("oracle/_ref/dab2eti_gpu was not built (no /root/reference at build time)")
+    ens = synth.small_ensemble()
+    g = synth.ModeITransmitter(ens).generate(1, 19, seed=25, snr_db=30, tail_samples=262144)
+    iq = g["iq"][0].numpy()[2 * 4321:]
+    n = iq.size // 262144 * 262144
+    cap = tmp_path / "capture.iq"
+    iq[:n].tofile(cap)
+    env = dict(os.environ, RTLSDR_FILE=str(cap))
+    r = subprocess.run([exe_gpu, "200000000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=300)
+    assert r.returncode == 0, r.stderr.decode()[-2000:]
+    eti = np.frombuffer(r.stdout, dtype=np.uint8).reshape(-1, 6144)
+    want = port.run_iq(iq[:n])["eti"]
+    assert eti.shape == want.shape and eti.shape[0] >= 12
+    assert np.array_equal(eti, want)
+    assert b"Locked" in r.stderr and b"ENSEMBLE_INFO" in r.stderr      # the reference's own diagnostics
+    if os.path.exists(exe_ref):
+        r2 = subprocess.run([exe_ref, "200000000"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, env=env,
+                            timeout=300)
+        assert r2.returncode == 0 and r2.stdout == r.stdout
+
+
+def test_spiral_mode_callers(api, port):
+    """a20: a host built with -DENABLE_SPIRAL_VITERBI calls create_viterbi() and passes the Spiral
+    alphabet {0, 128 = erasure, 255} (depuncture.c:36-43, dab.c:27-30).  libdabgpu serves that
+    signature with the same decoder (viterbi.c's maximum-likelihood decisions): identical to the
+    reference's Spiral SSE2 decoder on clean input, identical to viterbi.c on the same hard decisions
+    always, and in agreement with the Spiral decoder on most noisy code words (its 8-bit metrics and
+    tie-break differ, SURVEY 3.4 -- it is a CPU baseline, not an oracle)."""
+    import ctypes as C
+    from oracle import oracle
+    lib = api.lib
+    lib.create_viterbi.restype = C.c_void_p
+    lib.create_viterbi.argtypes = [C.c_int]
+    assert lib.create_viterbi(768)
+    sp = oracle.ref_spiral()
+    rng = np.random.default_rng(12)
+    same_sp = n = 0
+    for p_flip in (0.0, 0.0, 0.04, 0.04, 0.04, 0.04, 0.04, 0.04):
+        for nbits in (768, 3072):
+            data = rng.integers(0, 256, nbits // 8, dtype=np.uint8)
+            sym = port.encode(data)
+            s = sym ^ (rng.random(sym.size) < p_flip).astype(np.uint8)
+            erase = rng.random(sym.size) < 0.25
+            soft_s = (255 * s).astype(np.uint8)
+            soft_s[erase] = 128
+            soft_k = (127 + 2 * s).astype(np.uint8)
+            soft_k[erase] = 128
+            got = api.viterbi(soft_s, nbits)
+            assert np.array_equal(got, port.viterbi(soft_k, nbits))
+            if p_flip == 0:
+                assert np.array_equal(got, data)
+            if sp is not None:
+                ds = sp.viterbi_spiral(soft_s, nbits)
+                if p_flip == 0:
+                    assert np.array_equal(got, ds)
+                n += 1
+                same_sp += np.array_equal(got, ds)
+    if sp is not None:
+        assert same_sp >= 0.75 * n, (same_sp, n)

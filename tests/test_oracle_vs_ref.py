@@ -121,3 +121,54 @@ def test_full_path_iq(ref, port, cut, cfo):
     assert a["eti"].shape == b["eti"].shape and np.array_equal(a["eti"], b["eti"])
     if cfo == 0.0:
         assert a["eti"].shape[0] >= 16
+
+
+def test_wavefinder_producer(port, ref):
+    """oracle port of the Wavefinder packet path against the reference's unmodified input_wf.c
+    (compiled into oracle/_ref with the hardware timing loop stubbed): missing FIC symbols -> NULL
+    FIBs, missing MSC symbols -> stale frame-buffer content, first frame discarded."""
+    import numpy as np
+    from dabtools_b200 import synth
+    ens = synth.small_ensemble()
+    g = synth.ModeITransmitter(ens).generate(1, 22, seed=71, want_iq=False)
+    bits = g["bits"][0].numpy()
+    drops = {16: (3,), 18: (40, 41), 19: (2, 3, 4)}
+    pk = np.concatenate([synth.wavefinder_packets(bits[t], drop=drops.get(t, ())) for t in range(22)])
+    a, b = ref.run_wf(pk), port.run_wf(pk)
+    assert a.shape == b.shape and a.shape[0] >= 28 and np.array_equal(a, b)
+    clean = np.concatenate([synth.wavefinder_packets(bits[t]) for t in range(22)])
+    assert np.array_equal(port.run_wf(clean), port.run_backend(bits[1:])[0])
+    assert not np.array_equal(a, port.run_wf(clean))          # the losses are visible in the ETI
+
+
+def test_spiral_build_agrees_on_clean_input_and_is_close_on_noisy_input(port, ref):
+    """a20: the reference's Spiral SSE2 decoder (viterbi_spiral*.c, libdabref_spiral.so) is a secondary
+    CPU baseline, not an oracle (8-bit saturating metrics, other tie-break: SURVEY 3.4).  Clean input:
+    identical ETI.  Noisy codewords: it decodes the transmitted data about as often as viterbi.c."""
+    import numpy as np
+    from dabtools_b200 import synth
+    from oracle import oracle
+    sp = oracle.ref_spiral()
+    if sp is None:
+        pytest.skip("libdabref_spiral.so not available")
+    ens = synth.small_ensemble()
+    g = synth.ModeITransmitter(ens).generate(1, 16, seed=72, want_iq=False)
+    bits = g["bits"][0].numpy()
+    assert np.array_equal(sp.run_backend(bits)[0], ref.run_backend(bits)[0])
+    rng = np.random.default_rng(9)
+    ok_k = ok_s = same = 0
+    n = 60
+    for _ in range(n):
+        data = rng.integers(0, 256, 96, dtype=np.uint8)
+        sym = ref.encode(data)
+        s = sym ^ (rng.random(sym.size) < 0.05).astype(np.uint8)
+        erase = rng.random(sym.size) < 0.25
+        soft_k = (127 + 2 * s).astype(np.uint8)
+        soft_k[erase] = 128
+        soft_s = (255 * s).astype(np.uint8)                   # to_viterbi() of the Spiral build (depuncture.c:36-43)
+        soft_s[erase] = 128
+        dk, ds = ref.viterbi(soft_k, 768), sp.viterbi_spiral(soft_s, 768)
+        ok_k += np.array_equal(dk, data)
+        ok_s += np.array_equal(ds, data)
+        same += np.array_equal(dk, ds)
+    assert ok_k >= 0.9 * n and ok_s >= 0.85 * n and same >= 0.8 * n, (ok_k, ok_s, same)
