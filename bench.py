@@ -870,7 +870,7 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         # NCCL is only used for the barrier and the max-over-ranks; keep its version banner (printed to
         # stdout under NCCL_DEBUG=VERSION) away from the one JSON line
-        if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        if os.environ.get("NCCL_DEBUG", "").upper() in ("", "VERSION"):
             os.environ["NCCL_DEBUG"] = "WARN"
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     out = run_ours(args, rank, world, local_rank)

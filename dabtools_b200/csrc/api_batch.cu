@@ -11,7 +11,7 @@ namespace {
 // per-thread workspace of the stateless batched calls
 struct Workspace {
   DevBuf in, steps, out, aux, shape;
-  VitBatch vb;
+  VitBatch vb, vb_soft;
   uint64_t last_steps = 0;
 };
 thread_local Workspace t_ws;
@@ -126,6 +126,59 @@ DABGPU_EXPORT int dabgpu_viterbi_batch(const uint8_t *soft, size_t soft_pitch, i
     CUDA_TRY(cudaStreamSynchronize(st));
   }
   return DABGPU_OK;
+}
+
+// Soft-decision variant: `soft` really is soft -- any symbol value, weighted with the reference's own
+// metric table (viterbi.c:126-191; defined for 121..135, saturating beyond) -- instead of being sliced
+// to 0 / erasure / 1.  Bit-exact with the reference's viterbi() for symbols inside the table.
+DABGPU_EXPORT int dabgpu_viterbi_soft_batch(const uint8_t *soft, size_t soft_pitch, int n, int nbits,
+                                            uint8_t *out, size_t out_pitch, int descramble, int on_device) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  if (n < 0 || nbits <= 0 || !soft || !out) {
+    set_error(DABGPU_ERR_ARG, "dabgpu_viterbi_soft_batch: bad argument");
+    return DABGPU_ERR_ARG;
+  }
+  const uint32_t nsteps = (uint32_t)nbits + 6;
+  const size_t out_row = 4 * (((size_t)nbits + 31) / 32);
+  if (soft_pitch < 4ull * nsteps || (descramble && nbits > 9216) ||
+      (on_device && (out_pitch < out_row || (out_pitch & 3)))) {
+    set_error(DABGPU_ERR_ARG, "dabgpu_viterbi_soft_batch: pitch/size constraint violated");
+    return DABGPU_ERR_ARG;
+  }
+  if (n == 0) return DABGPU_OK;
+  cudaStream_t st = current_stream();
+  Workspace &ws = t_ws;
+  ws.vb_soft.soft = true;
+  const uint32_t row = vit_soft_row_bytes(nsteps);
+  if ((rc = ws.steps.reserve((size_t)n * row))) return rc;
+  const uint8_t *d_soft = soft;
+  uint8_t *d_out = out;
+  size_t d_out_pitch = out_pitch;
+  if (!on_device) {
+    if ((rc = ws.in.reserve((size_t)n * soft_pitch))) return rc;
+    CUDA_TRY(cudaMemcpyAsync(ws.in.p, soft, (size_t)n * soft_pitch, cudaMemcpyHostToDevice, st));
+    d_soft = ws.in.as<uint8_t>();
+    d_out_pitch = out_row;
+    if ((rc = ws.out.reserve((size_t)n * d_out_pitch))) return rc;
+    d_out = ws.out.as<uint8_t>();
+  }
+  if ((rc = launch_soft_rows(d_soft, soft_pitch, ws.steps.as<uint8_t>(), n, nsteps, st))) return rc;
+  ws.vb_soft.clear();
+  for (int i = 0; i < n; i++)
+    ws.vb_soft.add((uint64_t)i * row, (uint64_t)i * d_out_pitch, (uint32_t)nbits, descramble ? VIT_DESCRAMBLE : 0);
+  if ((rc = ws.vb_soft.run(ws.steps.as<uint8_t>(), d_out, st))) return rc;
+  ws.last_steps = ws.vb_soft.total_steps;
+  if (!on_device) {
+    const size_t nbytes = ((size_t)nbits + 7) / 8;
+    CUDA_TRY(cudaMemcpy2DAsync(out, out_pitch ? out_pitch : nbytes, d_out, d_out_pitch, nbytes, n,
+                               cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(cudaStreamSynchronize(st));
+  }
+  return DABGPU_OK;
+}
+DABGPU_EXPORT void dabgpu_tab_soft_metrics(int32_t *out2x256) {
+  viterbi_soft_metrics(reinterpret_cast<int32_t(*)[256]>(out2x256));
 }
 
 // ---- FIC decode batch ------------------------------------------------------------------------------

@@ -26,6 +26,7 @@ struct VitBatch {
   int n_ctas = 0;
   bool small_ctas = false;  // one single-warp CTA per group instead of the persistent layout
   bool one_warp_ctas = false;  // what plan() chose
+  bool soft = false;           // rows are 4 symbols per step, decoded by viterbi_soft_kernel
   double reserve_scale = 1.0;  // allocate this much more than the current job list needs (the
                                // caller's ratio of a full batch to this one), so stores never grow
 
@@ -60,7 +61,7 @@ struct VitBatch {
     }
     // sparse batches (fewer than two groups per warp scheduler) are latency-bound: one single-warp
     // CTA per group lets the hardware spread them, whatever else is running
-    one_warp_ctas = small_ctas || g0.size() < (size_t)device_sm_count() * 8;
+    one_warp_ctas = soft || small_ctas || g0.size() < (size_t)device_sm_count() * 8;
     if (one_warp_ctas) {
       groups.swap(g0);
       n_ctas = (int)groups.size();
@@ -142,6 +143,9 @@ struct VitBatch {
   }
   // launch again with the descriptors of the last run() (identical job list by construction)
   int relaunch(const uint8_t *d_steps, uint8_t *d_out, cudaStream_t st) {
+    if (soft)
+      return launch_viterbi_soft(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
+                                 (int)groups.size(), st);
     return launch_viterbi(d_steps, d_out, d_dec.as<uint2>(), d_jobs.as<VitJob>(), d_groups.as<VitGroup>(),
                           d_bins.as<uint32_t>(), n_ctas, one_warp_ctas ? 1 : VIT_WARPS, st);
   }

@@ -35,12 +35,16 @@
 #include "viterbi.cuh"
 
 #include <algorithm>
+#include <cmath>
 
 namespace dabgpu {
 
 __constant__ uint32_t c_prbs_le[288];  // 1152 PRBS bytes as little-endian words
 
+int viterbi_soft_init_constants();
 int viterbi_init_constants() {
+  int rc0 = viterbi_soft_init_constants();
+  if (rc0) return rc0;
   uint8_t prbs[1152];
   dabgpu_build_prbs(prbs, 1152);
   uint32_t w[288];
@@ -582,6 +586,240 @@ int launch_descramble(uint8_t *d_buf, uint64_t stride, int n_rows, int nbytes, c
   const uint64_t total = (uint64_t)n_rows * (uint64_t)nbytes;
   if (!total) return DABGPU_OK;
   descramble_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_buf, stride, n_rows, nbytes);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// =================================================================================================
+// Soft-decision decoder (opt-in, the default path above is untouched)
+// =================================================================================================
+// The reference's viterbi() is a soft-decision decoder fed with three-valued input: its metric table
+// gen_met(amp = 1, noise = 1.0, bias = 0, scale = 4) (viterbi.c:126-191, :455-462) is defined for the
+// received symbols 121..135 around the erasure value 128 -- 4,4,4,4,4,4,3,0,-7,-17,...,-73 for a
+// transmitted 0, mirrored for a 1, i.e. a log-likelihood ratio of about 10.7 per LSB -- and overflows
+// to INT_MIN beyond.  This kernel decodes arbitrary symbols in that range with exactly the
+// reference's arithmetic, so the unmodified viterbi.c is its oracle:
+//   * per-symbol cost c_b(s) = 4 - mettab[b][s] in 0..77; a branch costs the sum over the four
+//     generators (0..308).  Minimising the cost is maximising the reference's metric, and the
+//     reference's "take predecessor i/2+32 iff m1 > m0" is "iff cost1 < cost0";
+//   * the start bias (-999999) only marks states unreachable in the first six steps: 16384 here;
+//   * any two path costs differ by at most 6 x 308 once all states are reachable, so 16-bit costs
+//     with a common subtraction every 16 steps are exact.
+// One codeword per lane like the hard-decision kernel; 64 costs as 2 x u16 in 32 registers, register r
+// = states (2r, 2r+1).  The butterflies 2k and 2k+1 (predecessors p, p+32 -> successors 2p, 2p+1) are
+// done together on the packed halves of registers k and k+16.  Symbols outside 121..135 saturate.
+enum { SOFT_LO = 121, SOFT_HI = 135 };
+
+static void host_gen_metrics(int mettab[2][256]) {
+  // viterbi.c:126-191 with amp = 1, noise = 1.0, bias = 0, scale = 4
+  auto phi = [](double x) { return 0.5 + 0.5 * erf(x / M_SQRT2); };
+  for (int s = 0; s < 256; s++) {
+    const double lo = s - 128 - 0.5, hi = s - 128 + 0.5;
+    double p0, p1;
+    if (s == 0) {
+      p1 = phi(hi - 1);
+      p0 = phi(hi + 1);
+    } else if (s == 255) {
+      p1 = 1 - phi(lo - 1);
+      p0 = 1 - phi(lo + 1);
+    } else {
+      p1 = phi(hi - 1) - phi(lo - 1);
+      p0 = phi(hi + 1) - phi(lo + 1);
+    }
+    const double m0 = log(2 * p0 / (p1 + p0)) * M_LOG2E, m1 = log(2 * p1 / (p1 + p0)) * M_LOG2E;
+    mettab[0][s] = (s >= SOFT_LO && s <= SOFT_HI) ? (int)floor(m0 * 4 + 0.5) : INT32_MIN;
+    mettab[1][s] = (s >= SOFT_LO && s <= SOFT_HI) ? (int)floor(m1 * 4 + 0.5) : INT32_MIN;
+  }
+}
+void viterbi_soft_metrics(int32_t out[2][256]) {
+  int t[2][256];
+  host_gen_metrics(t);
+  for (int b = 0; b < 2; b++)
+    for (int s = 0; s < 256; s++) out[b][s] = t[b][s];
+}
+
+__device__ uint32_t g_soft_cost[256];  // cost of (0-bit | 1-bit << 16) for the saturated symbol
+
+int viterbi_soft_init_constants() {
+  int t[2][256];
+  host_gen_metrics(t);
+  uint32_t c[256];
+  for (int s = 0; s < 256; s++) {
+    const int q = s < SOFT_LO ? SOFT_LO : s > SOFT_HI ? SOFT_HI : s;
+    c[s] = (uint32_t)(4 - t[0][q]) | ((uint32_t)(4 - t[1][q]) << 16);
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(g_soft_cost, c, sizeof c));
+  return DABGPU_OK;
+}
+
+// expected symbols on the branch into state `s` taken with decision `d`: the encoder register is
+// s | d << 6 (viterbi.c:322-347); generators 0 and 3 are equal, so (g0, g1, g2) index 8 cost sums
+__host__ __device__ constexpr int sx_combo(int reg7) {
+  return cx_parity(reg7 & 0x6d) | (cx_parity(reg7 & 0x4f) << 1) | (cx_parity(reg7 & 0x53) << 2);
+}
+
+template <int K>
+__device__ __forceinline__ void soft_pair(const uint32_t (&M)[32], const uint32_t (&cst)[8], uint32_t (&N)[32],
+                                          uint32_t &accE, uint32_t &accO) {
+  // butterflies p = 2K (low halves) and 2K+1 (high halves); X = cost of p -> 2p and p+32 -> 2p+1,
+  // Y = cost of the complementary symbols (p -> 2p+1, p+32 -> 2p)
+  constexpr int c0 = sx_combo(2 * (2 * K)), c1 = sx_combo(2 * (2 * K + 1));
+  const uint32_t X = prmt(cst[c0], cst[c1], 0x5410u), Y = prmt(cst[c0 ^ 7], cst[c1 ^ 7], 0x5410u);
+  const uint32_t A = M[K], B = M[K + 16];
+  const uint32_t a0 = A + X, b0 = B + Y, a1 = A + Y, b1 = B + X;
+  // bit 15 / 31 of t: b >= a, i.e. predecessor p (decision 0) is kept; all costs stay below 32768
+  const uint32_t t0 = b0 + 0x80008000u - a0, t1 = b1 + 0x80008000u - a1;
+  const uint32_t m0 = prmt(t0, 0u, 0xbb99u), m1 = prmt(t1, 0u, 0xbb99u);  // 0xffff where a is kept
+  const uint32_t E = (a0 & m0) | (b0 & ~m0), O = (a1 & m1) | (b1 & ~m1);
+  // decisions: after all 16 pairs bit K = butterfly 2K, bit 16 + K = butterfly 2K + 1
+  accE = (accE >> 1) | (~t0 & 0x80008000u);
+  accO = (accO >> 1) | (~t1 & 0x80008000u);
+  N[2 * K] = prmt(E, O, 0x5410u);      // states 4K, 4K+1
+  N[2 * K + 1] = prmt(E, O, 0x7632u);  // states 4K+2, 4K+3
+}
+
+__device__ __forceinline__ uint2 soft_step(uint32_t (&M)[32], const uint32_t *cost, uint32_t sym4) {
+  // per-generator costs -> the 8 sums over (g0 = g3, g1, g2)
+  const uint32_t q0 = cost[sym4 & 0xffu], q1 = cost[(sym4 >> 8) & 0xffu];
+  const uint32_t q2 = cost[(sym4 >> 16) & 0xffu], q3 = cost[sym4 >> 24];
+  const uint32_t u = q0 + q3;  // (u_0 | u_1 << 16): generators 0 and 3 carry the same bit
+  uint32_t cst[8];
+#pragma unroll
+  for (int c = 0; c < 8; c++)
+    cst[c] = ((c & 1) ? u >> 16 : u & 0xffffu) + ((c & 2) ? q1 >> 16 : q1 & 0xffffu) +
+             ((c & 4) ? q2 >> 16 : q2 & 0xffffu);
+  uint32_t N[32], accE = 0, accO = 0;
+  soft_pair<0>(M, cst, N, accE, accO);
+  soft_pair<1>(M, cst, N, accE, accO);
+  soft_pair<2>(M, cst, N, accE, accO);
+  soft_pair<3>(M, cst, N, accE, accO);
+  soft_pair<4>(M, cst, N, accE, accO);
+  soft_pair<5>(M, cst, N, accE, accO);
+  soft_pair<6>(M, cst, N, accE, accO);
+  soft_pair<7>(M, cst, N, accE, accO);
+  soft_pair<8>(M, cst, N, accE, accO);
+  soft_pair<9>(M, cst, N, accE, accO);
+  soft_pair<10>(M, cst, N, accE, accO);
+  soft_pair<11>(M, cst, N, accE, accO);
+  soft_pair<12>(M, cst, N, accE, accO);
+  soft_pair<13>(M, cst, N, accE, accO);
+  soft_pair<14>(M, cst, N, accE, accO);
+  soft_pair<15>(M, cst, N, accE, accO);
+#pragma unroll
+  for (int i = 0; i < 32; i++) M[i] = N[i];
+  return make_uint2(accE, accO);
+}
+
+// decision of state s in the words of its step: word = s & 1 (E / O), butterfly p = s >> 1
+__device__ __forceinline__ uint32_t soft_decision(uint2 d, uint32_t s) {
+  const uint32_t w = (s & 1u) ? d.y : d.x, p = s >> 1;
+  return (w >> (16u * (p & 1u) + (p >> 1))) & 1u;
+}
+
+// input rows: 4 symbols per step (one 32-bit word), rows 16-byte aligned, padded to whole 16-step chunks
+__global__ void __launch_bounds__(128) viterbi_soft_kernel(const uint8_t *__restrict__ sym, uint8_t *__restrict__ out,
+                                                           uint2 *__restrict__ dec, const VitJob *__restrict__ jobs,
+                                                           const VitGroup *__restrict__ groups, int n_groups) {
+  __shared__ uint32_t cost[256];
+  for (int i = threadIdx.x; i < 256; i += blockDim.x) cost[i] = g_soft_cost[i];
+  __syncthreads();
+  const int lane = threadIdx.x & 31;
+  const int gi = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (gi >= n_groups) return;
+  const VitGroup g = groups[gi];
+  const bool active = lane < (int)g.nlanes;
+  const VitJob job = jobs[g.job0 + (active ? lane : 0)];
+  const uint4 *row = reinterpret_cast<const uint4 *>(sym + job.in_off);
+  uint2 *decp = dec + g.dec_off + lane;
+  const uint32_t nsteps = g.nsteps, nchunks = (nsteps + 15u) >> 4;
+  uint32_t M[32];
+#pragma unroll
+  for (int i = 0; i < 32; i++) M[i] = 0x40004000u;  // unreachable
+  M[0] = 0x40000000u;                               // start state 0
+  for (uint32_t c = 0; c < nchunks; c++) {
+#pragma unroll 1
+    for (int q = 0; q < 4; q++) {
+      const uint4 w = row[4 * c + q];
+      const uint2 d0 = soft_step(M, cost, w.x), d1 = soft_step(M, cost, w.y), d2 = soft_step(M, cost, w.z), d3 = soft_step(M, cost, w.w);
+      if (active) {
+        uint2 *dq = decp + (size_t)(16 * c + 4 * q) * 32;
+        dq[0] = d0;
+        dq[32] = d1;
+        dq[64] = d2;
+        dq[96] = d3;
+      }
+    }
+    // common subtraction: every cost is within 1848 of state 0's once all states are reachable
+    const uint32_t m0 = M[0] & 0xffffu;
+    const uint32_t sub = (m0 > 2048u ? m0 - 2048u : 0u) * 0x00010001u;
+#pragma unroll
+    for (int i = 0; i < 32; i++) M[i] -= sub;
+  }
+  if (!active) return;
+  // traceback from state 0 (viterbi.c:443-450): information bit i is the decision read at step i + 6
+  const uint32_t nbits = job.nbits;
+  uint8_t *dst = out + job.out_off;
+  const bool scr = job.flags & VIT_DESCRAMBLE;
+  uint32_t state = 0, acc = 0;
+  int i = (int)nbits - 1;
+  while (i >= 0) {
+    const int n = min(16, i + 1);
+    uint2 buf[16];
+#pragma unroll
+    for (int j = 0; j < 16; j++)
+      if (j < n) buf[j] = decp[(size_t)(i - j + 6) * 32];
+#pragma unroll
+    for (int j = 0; j < 16; j++) {
+      if (j < n) {
+        const int b = i - j;
+        const uint32_t bit = soft_decision(buf[j], state);
+        state = (state >> 1) | (bit << 5);
+        acc |= bit << (31 - (b & 31));
+        if ((b & 31) == 0 || b == 0) {
+          uint32_t w = prmt(acc, 0u, 0x0123u);
+          if (scr) w ^= c_prbs_le[b >> 5];
+          const uint32_t nb = min(4u, (nbits + 7u) / 8u - 4u * (uint32_t)(b >> 5));  // bytes of this word
+          if (nb == 4)
+            *reinterpret_cast<uint32_t *>(dst + 4 * (b >> 5)) = w;
+          else
+            for (uint32_t k = 0; k < nb; k++) dst[4 * (b >> 5) + k] = (uint8_t)(w >> (8 * k));
+          acc = 0;
+        }
+      }
+    }
+    i -= n;
+  }
+}
+
+// caller's symbol rows (4 bytes per step at any pitch) -> aligned, padded rows (padding = erasures)
+__global__ void soft_rows_kernel(const uint8_t *__restrict__ soft, uint64_t soft_stride, uint32_t *__restrict__ rows,
+                                 uint32_t row_words, int n_cw, uint32_t nsteps) {
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t cw = idx / row_words;
+  const uint32_t t = (uint32_t)(idx % row_words);
+  if (cw >= (uint64_t)n_cw) return;
+  uint32_t w = 0x80808080u;
+  if (t < nsteps) {
+    const uint8_t *p = soft + cw * soft_stride + 4ull * t;
+    w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+  }
+  rows[cw * row_words + t] = w;
+}
+int launch_soft_rows(const uint8_t *d_soft, uint64_t soft_stride, uint8_t *d_rows, int n_cw, uint32_t nsteps,
+                     cudaStream_t st) {
+  const uint32_t row_words = vit_soft_row_bytes(nsteps) / 4;
+  const uint64_t total = (uint64_t)n_cw * row_words;
+  if (!total) return DABGPU_OK;
+  soft_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_soft, soft_stride, reinterpret_cast<uint32_t *>(d_rows),
+                                                                    row_words, n_cw, nsteps);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+int launch_viterbi_soft(const uint8_t *d_sym, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
+                        const VitGroup *d_groups, int n_groups, cudaStream_t st) {
+  if (n_groups <= 0) return DABGPU_OK;
+  viterbi_soft_kernel<<<(n_groups + 3) / 4, 128, 0, st>>>(d_sym, d_out, d_dec, d_jobs, d_groups, n_groups);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }

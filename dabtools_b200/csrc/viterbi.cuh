@@ -58,6 +58,17 @@ int launch_viterbi(const uint8_t *d_steps, uint8_t *d_out, uint2 *d_dec, const V
                    const VitGroup *d_groups, const uint32_t *d_bin_start, int n_ctas, int warps_per_cta,
                    cudaStream_t st);
 
+// Soft-decision decoder (opt-in): rows of 4 received symbols per trellis step (one 32-bit word per step,
+// rows 16-byte aligned and padded to whole 16-step chunks = 64 bytes), decoded with the reference's own
+// metric table gen_met(1, 1.0, 0, 4) (viterbi.c:126-191); symbols outside 121..135 saturate.
+// Same jobs / groups / decision scratch as the hard-decision kernel; one group per warp, no work lists.
+__host__ __device__ static inline uint32_t vit_soft_row_bytes(uint32_t nsteps) { return 4u * ((nsteps + 15u) & ~15u); }
+int launch_viterbi_soft(const uint8_t *d_sym, uint8_t *d_out, uint2 *d_dec, const VitJob *d_jobs,
+                        const VitGroup *d_groups, int n_groups, cudaStream_t st);
+int launch_soft_rows(const uint8_t *d_soft, uint64_t soft_stride, uint8_t *d_rows, int n_cw, uint32_t nsteps,
+                     cudaStream_t st);
+void viterbi_soft_metrics(int32_t out[2][256]);  // the table the kernel uses (INT32_MIN outside 121..135)
+
 // step-byte producers -------------------------------------------------------------------
 // (a) from the reference's soft-symbol bytes (4 per step; <128 -> 0, 128 -> erasure, >128 -> 1)
 int launch_prep_soft(const uint8_t *d_soft, uint64_t soft_stride, uint8_t *d_steps, uint64_t row_stride,

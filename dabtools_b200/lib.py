@@ -80,6 +80,25 @@ def viterbi_batch(soft: np.ndarray, nbits: int, descramble: bool = False) -> np.
     return out
 
 
+def viterbi_soft_batch(soft: np.ndarray, nbits: int, descramble: bool = False) -> np.ndarray:
+    """like viterbi_batch, but the symbols are weighted with the reference's metric table (soft decisions)"""
+    soft = np.ascontiguousarray(soft, dtype=np.uint8)
+    n = soft.shape[0]
+    out = np.zeros((n, (nbits + 7) // 8), dtype=np.uint8)
+    lib = load()
+    lib.dabgpu_viterbi_soft_batch.argtypes = [C.c_void_p, C.c_size_t, C.c_int, C.c_int, C.c_void_p, C.c_size_t,
+                                              C.c_int, C.c_int]
+    check(lib.dabgpu_viterbi_soft_batch(_np_ptr(soft), soft.shape[1], n, nbits, _np_ptr(out), out.shape[1],
+                                        int(descramble), 0))
+    return out
+
+
+def soft_metrics() -> np.ndarray:
+    t = np.zeros((2, 256), dtype=np.int32)
+    load().dabgpu_tab_soft_metrics(_np_ptr(t))
+    return t
+
+
 def fic_decode_batch(fic_bits: np.ndarray):
     """fic_bits: uint8 [n][2304] hard bits (host) -> (fibs uint8 [n][96], crc_ok uint8 [n][3])"""
     fic_bits = np.ascontiguousarray(fic_bits, dtype=np.uint8).reshape(-1, 2304)

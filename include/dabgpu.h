@@ -69,6 +69,15 @@ void dabgpu_tab_prbs(uint8_t *out, int nbytes);  /* energy-dispersal sequence, m
  * (needs nbits <= 9216).  Batched form of viterbi(), viterbi.c:352-452. */
 int dabgpu_viterbi_batch(const uint8_t *soft, size_t soft_pitch, int n, int nbits, uint8_t *out,
                          size_t out_pitch, int descramble, int on_device);
+/* Soft-decision variant (opt-in): the symbols are NOT sliced; each is weighted with the
+ * reference's own metric table gen_met(amp 1, noise 1.0, bias 0, scale 4) (viterbi.c:126-191,
+ * :455-462), which is defined for 121..135 around the erasure value 128 (log-likelihood ratio about
+ * 10.7 per LSB) and overflows beyond -- values outside saturate to 121 / 135 here.  Same arguments
+ * as dabgpu_viterbi_batch; bit-exact with the reference's viterbi() for symbols inside the table
+ * (the hard-decision alphabet 127 / 128 / 129 is a special case). */
+int dabgpu_viterbi_soft_batch(const uint8_t *soft, size_t soft_pitch, int n, int nbits, uint8_t *out,
+                              size_t out_pitch, int descramble, int on_device);
+void dabgpu_tab_soft_metrics(int32_t *out2x256); /* that table; INT32_MIN outside 121..135 */
 
 /* n_groups FIC groups of 2304 hard bits (one byte per bit, values 0/1; 4 groups = the 3
  * FIC symbols of one transmission frame) -> 96 descrambled bytes (3 FIBs) + 3 CRC flags
