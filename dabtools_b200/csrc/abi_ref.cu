@@ -112,8 +112,19 @@ DABGPU_EXPORT void *create_viterbi(int len) {  // viterbi_spiral.c:163, for -DEN
 DABGPU_EXPORT int viterbi(void *p, unsigned char *symbols, unsigned char *data, unsigned int framebits) {
   (void)p;
   if (!data) return 0;  // viterbi.c:437-438
-  if (dabgpu_viterbi_batch(symbols, 4ull * (framebits + 6), 1, (int)framebits, data, (framebits + 7) / 8, 0, 0))
-    report("viterbi");
+  // The reference's callers only ever pass to_viterbi()'s alphabet (127 / 128 / 129, or 0 / 128 / 255 when
+  // built for the Spiral decoder), which the hard-decision kernel decodes.  Anything else is a real
+  // soft symbol and is weighted with the reference's metric table like viterbi.c does (soft kernel;
+  // values beyond the table's range 121..135 saturate, where the reference's table overflows).
+  const size_t nsym = 4ull * (framebits + 6);
+  bool hard = true;
+  for (size_t i = 0; i < nsym && hard; i++) {
+    const unsigned v = symbols[i];
+    hard = v == 127 || v == 128 || v == 129 || v == 0 || v == 255;
+  }
+  const int rc = hard ? dabgpu_viterbi_batch(symbols, nsym, 1, (int)framebits, data, (framebits + 7) / 8, 0, 0)
+                      : dabgpu_viterbi_soft_batch(symbols, nsym, 1, (int)framebits, data, (framebits + 7) / 8, 0, 0);
+  if (rc) report("viterbi");
   return 0;
 }
 

@@ -281,6 +281,41 @@ DABGPU_EXPORT int dabgpu_demod_frame_debug(const uint8_t *frame, float *symbols,
   return DABGPU_OK;
 }
 
+// Soft demapper on one frame (the DABGPU_ENGINE_SOFT demodulator, batch of one): 393216 bytes of uint8 I/Q
+// as sdr_read_fifo leaves them -> 230400 symbols (fic 9216 + msc 221184, the layout of
+// demapped_transmission_frame_t) 128 -+ round(8 x), 121..135.  No synchronisers: the frame is taken as is.
+DABGPU_EXPORT int dabgpu_demod_frame_soft(const uint8_t *frame, uint8_t *soft230400) {
+  int rc;
+  if ((rc = ensure_device_ready())) return rc;
+  if (!frame || !soft230400) {
+    set_error(DABGPU_ERR_ARG, "demod_frame_soft: null pointer");
+    return DABGPU_ERR_ARG;
+  }
+  cudaStream_t st = current_stream();
+  Workspace &ws = t_ws;
+  if ((rc = ws.in.reserve(DABGPU_TF_BYTES))) return rc;
+  if ((rc = ws.out.reserve(230400))) return rc;
+  if ((rc = ws.aux.reserve(sizeof(StepCtl) + sizeof(SyncOut) + 64))) return rc;
+  StepCtl ctl;
+  memset(&ctl, 0, sizeof ctl);
+  ctl.run = 1;
+  for (int k = 0; k < 4; k++) ctl.cif_off[k] = (uint64_t)k * CIF_BYTES;  // slot k of the soft store
+  SyncOut so;
+  memset(&so, 0, sizeof so);
+  so.ok = 1;
+  CUDA_TRY(cudaMemcpyAsync(ws.in.p, frame, DABGPU_TF_BYTES, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemcpyAsync(ws.aux.p, &ctl, sizeof ctl, cudaMemcpyHostToDevice, st));
+  SyncOut *d_so = reinterpret_cast<SyncOut *>(ws.aux.as<uint8_t>() + ((sizeof ctl + 15) & ~(size_t)15));
+  CUDA_TRY(cudaMemcpyAsync(d_so, &so, sizeof so, cudaMemcpyHostToDevice, st));
+  CUDA_TRY(cudaMemsetAsync(ws.out.p, 128, 230400, st));
+  if ((rc = launch_demod(RingGeom{nullptr, 0, IQ_RING_BYTES}, nullptr, ws.in.as<uint8_t>(), ws.aux.as<StepCtl>(), d_so,
+                         ws.out.as<uint8_t>(), ws.out.as<uint8_t>() + 9216, 1, 0, 5, true, st)))
+    return rc;
+  CUDA_TRY(cudaMemcpyAsync(soft230400, ws.out.p, 230400, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(cudaStreamSynchronize(st));
+  return DABGPU_OK;
+}
+
 // ---- ETI consumers (eti2mpa.c:32-67 and the frame check) ------------------------------------------------
 DABGPU_EXPORT int dabgpu_eti_extract_subchannel(const uint8_t *eti, int n_frames, int subchid, uint8_t *out,
                                                 size_t out_pitch, int32_t *out_len, int on_device) {

@@ -93,6 +93,8 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   f0 = tuner_hz;
   quiet = !(flags & DABGPU_ENGINE_VERBOSE);
   virtual_tuner = flags & DABGPU_ENGINE_VIRTUAL_TUNER;
+  soft = flags & DABGPU_ENGINE_SOFT;
+  vb_fic.soft = vb_msc.soft = soft;
   subch_mask.assign(S, ~0ull);
   front.assign(S, FrontState());
   back.resize(S);
@@ -113,7 +115,8 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   if ((rc = d_cifs.reserve((size_t)S * CIF_SLOTS * CIF_BYTES))) return rc;
   if ((rc = d_fibs.reserve((size_t)S * TF_SLOTS * FIBS_PER_TF))) return rc;
   if ((rc = d_ficbits.reserve((size_t)S * 9216))) return rc;
-  if ((rc = d_steps_fic.reserve((size_t)S * 4 * FIC_ROW))) return rc;
+  if ((rc = d_steps_fic.reserve((size_t)S * 4 * FIC_ROW * (soft ? 4 : 1)))) return rc;
+  if (soft && (rc = d_cifs_soft.reserve((size_t)S * CIF_SLOTS * 55296))) return rc;
   // ETI output of one call: up to MAX_MSC_BATCH TFs per flush, plus one extra TF for the rare
   // call that has to flush twice
   if ((rc = d_eti.reserve((size_t)S * 4 * (MAX_MSC_BATCH + 1) * DABGPU_ETI_BYTES))) return rc;
@@ -297,7 +300,7 @@ void Engine::destroy() {
       for (int j = 0; j < 2; j++) cudaEventDestroy(ev[k][j]);
   DevBuf *db[] = {&d_ring, &d_frames, &d_tails, &d_chunk, &d_ctl, &d_sync, &d_cifs, &d_fibs, &d_crc, &d_ficbits,
                   &d_tfbytes, &d_steps_fic, &d_steps_msc, &d_eti, &d_ens, &d_shapes, &d_fic_shape, &d_cifjobs,
-                  &d_subjobs, &d_periods, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out, &d_consume, &d_wf_ring, &d_wf_pkts, &d_wf_ctl};
+                  &d_subjobs, &d_periods, &d_etijobs, &d_planeoff, &d_gather_idx, &d_gather_out, &d_consume, &d_wf_ring, &d_wf_pkts, &d_wf_ctl, &d_cifs_soft};
   for (DevBuf *b : db) b->release();
   PinBuf *pb[] = {&h_ctl, &h_stepctl[0], &h_stepctl[1], &h_sync, &h_fic_out[0], &h_fic_out[1], &h_jobs[0], &h_jobs[1], &h_msc[0], &h_msc[1], &h_eti, &h_chunk};
   for (PinBuf *b : pb) b->release();
@@ -450,7 +453,8 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
     h_idx[a] = (uint32_t)s;
     h_dst[a] = ((uint64_t)s * TF_SLOTS + (uint64_t)frame_slot[s]) * FIBS_PER_TF;
     for (int k = 0; k < 4; k++)
-      vb_fic.add(((uint64_t)a * 4 + k) * FIC_ROW, (uint64_t)a * FIBS_PER_TF + 96 * k, 768, VIT_DESCRAMBLE);
+      vb_fic.add(((uint64_t)a * 4 + k) * FIC_ROW * (soft ? 4u : 1u), (uint64_t)a * FIBS_PER_TF + 96 * k, 768,
+                 VIT_DESCRAMBLE);
   }
   if ((rc = d_gather_idx.reserve((size_t)S * 12 + 8))) return rc;
   if ((rc = ctl_transfer(d_gather_idx.p, hj.p, idx_bytes + (size_t)na * 8, cudaMemcpyHostToDevice, st))) return rc;
@@ -459,8 +463,12 @@ int Engine::fic_launch(cudaStream_t st, const uint8_t *d_fic_src, uint64_t fic_s
   const uint32_t *d_idx = d_gather_idx.as<uint32_t>();
   const uint64_t *d_dst = reinterpret_cast<const uint64_t *>(d_gather_idx.as<uint8_t>() + idx_bytes);
   t0(K_FIC_PREP, st);
-  if ((rc = launch_prep_hard(d_fic_src, 2304, 4, fic_stride, d_idx, d_steps_fic.as<uint8_t>(), FIC_ROW, 4 * na,
-                             d_fic_shape.as<ShapeDev>(), 774, st)))
+  if (soft) {
+    if ((rc = launch_fic_soft_rows(d_fic_src, fic_stride, d_idx, d_steps_fic.as<uint8_t>(), 4 * na,
+                                   d_fic_shape.as<ShapeDev>(), st)))
+      return rc;
+  } else if ((rc = launch_prep_hard(d_fic_src, 2304, 4, fic_stride, d_idx, d_steps_fic.as<uint8_t>(), FIC_ROW, 4 * na,
+                                    d_fic_shape.as<ShapeDev>(), 774, st)))
     return rc;
   t1(K_FIC_PREP, st);
   if (early) {  // the next frame's FIC symbols may overwrite d_ficbits from here on
@@ -654,8 +662,8 @@ int Engine::flush_msc(cudaStream_t user) {
       const EnsLayout &L = layout[pend_stream[f]];
       frame_row.push_back(row_base);
       for (int u = 0; u < L.nsub; u++)
-        vb_msc.add(row_base + L.sub[u].row_off, (uint64_t)(base + f) * DABGPU_ETI_BYTES + L.sub[u].eti_off,
-                   L.sub[u].nbits, VIT_DESCRAMBLE);
+        vb_msc.add((row_base + L.sub[u].row_off) * (soft ? 4u : 1u),
+                   (uint64_t)(base + f) * DABGPU_ETI_BYTES + L.sub[u].eti_off, L.sub[u].nbits, VIT_DESCRAMBLE);
       row_base += L.rows_bytes;
     }
     cached_sig = pend_sig;
@@ -677,7 +685,8 @@ int Engine::flush_msc(cudaStream_t user) {
   CUDA_TRY(cudaEventSynchronize(ev_up[msc_buf]));
   if (hm.cap < b_cif + b_eti && (rc = hm.reserve(full(b_cif + b_eti)))) return rc;
   if (d_cifjobs.cap < b_cif + b_eti && (rc = d_cifjobs.reserve(full(b_cif + b_eti)))) return rc;
-  if (d_steps_msc.cap < row_base + 64 && (rc = d_steps_msc.reserve(full(row_base + 64)))) return rc;
+  const uint64_t steps_bytes = (row_base + 64) * (soft ? 4u : 1u);
+  if (d_steps_msc.cap < steps_bytes && (rc = d_steps_msc.reserve(full(steps_bytes)))) return rc;
   vb_msc.reserve_scale = scale;
   if ((size_t)n_eti * DABGPU_ETI_BYTES > d_eti.cap) {
     set_error(DABGPU_ERR_STATE, "engine: more ETI frames in one call than the output store holds");
@@ -693,8 +702,12 @@ int Engine::flush_msc(cudaStream_t user) {
   const EtiJob *de = reinterpret_cast<const EtiJob *>(d_cifjobs.as<uint8_t>() + b_cif);
   host_us[H_JOBS] += now_us() - tw;
   t0(K_MSC_GATHER, st);
-  if ((rc = launch_msc_gather_periods(d_cifs.as<uint8_t>(), dj, d_periods.as<PeriodDesc>(),
-                                      d_steps_msc.as<uint8_t>(), n_new, st)))
+  if (soft) {
+    if ((rc = launch_msc_soft_gather(d_cifs_soft.as<uint8_t>(), dj, d_periods.as<PeriodDesc>(),
+                                     d_steps_msc.as<uint8_t>(), n_new, st)))
+      return rc;
+  } else if ((rc = launch_msc_gather_periods(d_cifs.as<uint8_t>(), dj, d_periods.as<PeriodDesc>(),
+                                             d_steps_msc.as<uint8_t>(), n_new, st)))
     return rc;
   t1(K_MSC_GATHER, st);
   t0(K_MSC_VIT, st);
@@ -750,7 +763,8 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
     for (int s = 0; s < S; s++)
       for (int k = 0; k < 4; k++) off[4 * s + k] = ((uint64_t)s * CIF_SLOTS + frame_slot[s] * 4 + k) * CIF_BYTES;
     CUDA_TRY(cudaMemcpyAsync(d_planeoff.p, off, (size_t)S * 4 * sizeof(uint64_t), cudaMemcpyHostToDevice, st));
-    if ((rc = launch_pack_planes(d_tf + 9216, pitch, d_planeoff.as<uint64_t>(), d_cifs.as<uint8_t>(), S, st)))
+    if ((rc = soft ? launch_soft_store(d_tf + 9216, pitch, d_planeoff.as<uint64_t>(), d_cifs_soft.as<uint8_t>(), S, st)
+                   : launch_pack_planes(d_tf + 9216, pitch, d_planeoff.as<uint64_t>(), d_cifs.as<uint8_t>(), S, st)))
       return rc;
   } else {
     // masked call: pack stream by stream (not a throughput path)
@@ -762,8 +776,10 @@ int Engine::process_demapped(const uint8_t *tfs, size_t pitch, const uint8_t *ma
         off[4 * a + k] = ((uint64_t)active[a] * CIF_SLOTS + frame_slot[active[a]] * 4 + k) * CIF_BYTES;
     CUDA_TRY(cudaMemcpyAsync(d_planeoff.p, off, 4 * sizeof(uint64_t) * (size_t)na, cudaMemcpyHostToDevice, st));
     for (int a = 0; a < na; a++)
-      if ((rc = launch_pack_planes(d_tf + (size_t)active[a] * pitch + 9216, pitch,
-                                   d_planeoff.as<uint64_t>() + 4 * a, d_cifs.as<uint8_t>(), 1, st)))
+      if ((rc = soft ? launch_soft_store(d_tf + (size_t)active[a] * pitch + 9216, pitch,
+                                         d_planeoff.as<uint64_t>() + 4 * a, d_cifs_soft.as<uint8_t>(), 1, st)
+                     : launch_pack_planes(d_tf + (size_t)active[a] * pitch + 9216, pitch,
+                                          d_planeoff.as<uint64_t>() + 4 * a, d_cifs.as<uint8_t>(), 1, st)))
         return rc;
   }
   if ((rc = fic_launch(st, d_tf, pitch, false))) return rc;
@@ -1096,12 +1112,12 @@ int Engine::feed_iq(const uint8_t *iq, size_t pitch, int chunk_len, bool on_devi
       t0(K_DEMOD, st);
       if ((rc = launch_demod(rg, d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
                              d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), d_ficbits.as<uint8_t>(),
-                             d_cifs.as<uint8_t>(), S, 0, 1, st)))
+                             soft ? d_cifs_soft.as<uint8_t>() : d_cifs.as<uint8_t>(), S, 0, 1, soft, st)))
         return rc;
       CUDA_TRY(cudaEventRecord(ev_fic_ready, st));
       if ((rc = launch_demod(rg, d_tails.as<uint8_t>(), d_frames.as<uint8_t>(),
                              d_ctl.as<StepCtl>(), d_sync.as<SyncOut>(), d_ficbits.as<uint8_t>(),
-                             d_cifs.as<uint8_t>(), S, 1, 4, st)))
+                             soft ? d_cifs_soft.as<uint8_t>() : d_cifs.as<uint8_t>(), S, 1, 4, soft, st)))
         return rc;
       t1(K_DEMOD, st);
       demod_ev = demod_ev_next;

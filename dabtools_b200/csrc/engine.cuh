@@ -76,6 +76,7 @@ struct Engine {
   uint32_t f0 = 0;
   bool quiet = true;
   bool virtual_tuner = false;
+  bool soft = false;  // DABGPU_ENGINE_SOFT: symbols instead of bits from the demapper to the Viterbi decoder
   std::vector<FrontState> front;
   std::vector<BackendState> back;
   std::vector<EnsLayout> layout;
@@ -101,6 +102,7 @@ struct Engine {
   // device stores
   DevBuf d_ring, d_frames, d_tails, d_chunk, d_ctl, d_sync;
   DevBuf d_cifs;      // [S][20][CIF_BYTES]
+  DevBuf d_cifs_soft; // soft engines: [S][CIF_SLOTS][55296] symbols in logical order
   DevBuf d_fibs;      // [S][5][384]
   DevBuf d_crc;       // [S][5][12]
   DevBuf d_ficbits;   // [S][9216]

@@ -16,6 +16,7 @@ static uint16_t host_mulmod(uint16_t a, uint16_t b) {
 }
 
 int msc_init_dep_tables();
+int msc_soft_init_constants();
 // Wavefinder producer (input_wf.c:23-40): carrier order -> frequency de-interleaved position, and the
 // 2304 channel bits of a FIC group that decodes to three NULL FIBs (fic.c:150-175)
 __device__ uint16_t g_rev1536[1536];
@@ -58,6 +59,10 @@ int msc_init_constants() {
     CUDA_TRY(cudaMemcpyToSymbol(g_null_fic_group, grp, sizeof grp));
   }
   CUDA_TRY(cudaMemcpyToSymbol(c_tdi_slot, DABGPU_TDI_DELAY, 16));
+  {
+    int rc_soft = msc_soft_init_constants();
+    if (rc_soft) return rc_soft;
+  }
   uint16_t p[16];
   // x^8 mod P: a CRC register holding 1 shifted by one byte
   uint16_t v = 1;
@@ -473,6 +478,129 @@ int launch_eti_pack(const EtiJob *d_jobs, const EnsDev *d_ens, const uint8_t *d_
                     int n_frames, cudaStream_t st) {
   if (n_frames <= 0) return DABGPU_OK;
   eti_pack_kernel<<<(n_frames + 3) / 4, 128, 0, st>>>(d_jobs, d_ens, d_fibs, d_eti, n_frames);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// ---- soft-decision data path (opt-in: DABGPU_ENGINE_SOFT) ------------------------------
+// The same receiver with one byte per channel bit instead of one bit: a received symbol value around
+// the erasure level 128 (what the reference's depuncturers would hand to viterbi() if its demapper
+// did not slice, depuncture.c:36-43).  CIFs are stored as 55296 bytes in logical order; the time
+// de-interleaver + depuncturer below produce rows of four symbols per trellis step for
+// viterbi_soft_kernel, with the same job / period descriptors as the hard-decision gather.
+enum { SOFT_CIF_BYTES = 55296 };
+__constant__ uint32_t c_pmask[25];  // puncturing vectors PI = 1..24 (dab_tables.c:102-127)
+
+int msc_soft_init_constants() {
+  uint32_t m[25] = {0};
+  for (int pi = 1; pi <= 24; pi++) m[pi] = dabgpu_puncture_mask(pi);
+  CUDA_TRY(cudaMemcpyToSymbol(c_pmask, m, sizeof m));
+  return DABGPU_OK;
+}
+
+// the 4 CIFs of a demapped soft transmission frame -> their slots of the soft CIF store
+__global__ void __launch_bounds__(256) soft_store_kernel(const uint8_t *__restrict__ msc, uint64_t tf_stride,
+                                                         const uint64_t *__restrict__ dst_off,
+                                                         uint8_t *__restrict__ cifs_soft) {
+  const int cif = blockIdx.y;  // 4 * tf + c
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  if (v >= SOFT_CIF_BYTES / 16) return;
+  const uint8_t *src = msc + (uint64_t)(cif >> 2) * tf_stride + (uint64_t)(cif & 3) * SOFT_CIF_BYTES;
+  // hard-store offsets (slot * CIF_BYTES) address the soft store slot by slot
+  uint8_t *dst = cifs_soft + dst_off[cif] / CIF_BYTES * SOFT_CIF_BYTES;
+  reinterpret_cast<uint4 *>(dst)[v] = reinterpret_cast<const uint4 *>(src)[v];
+}
+int launch_soft_store(const uint8_t *d_msc_bytes, uint64_t tf_stride, const uint64_t *d_dst_off, uint8_t *d_cifs_soft,
+                      int n_tf, cudaStream_t st) {
+  if (n_tf <= 0) return DABGPU_OK;
+  soft_store_kernel<<<dim3((SOFT_CIF_BYTES / 16 + 255) / 256, 4 * n_tf), 256, 0, st>>>(d_msc_bytes, tf_stride,
+                                                                                       d_dst_off, d_cifs_soft);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// time_deinterleave + uep/eep_depuncture (misc.c:29-39, depuncture.c:84-132) on symbols: one thread
+// per puncturing period (8 trellis steps -> 8 words of 4 symbols; punctured positions = 128)
+__global__ void __launch_bounds__(128) msc_soft_gather_kernel(const uint8_t *__restrict__ cifs_soft,
+                                                              const CifJob *__restrict__ jobs,
+                                                              const PeriodDesc *__restrict__ periods,
+                                                              uint8_t *__restrict__ rows) {
+  const CifJob &job = jobs[blockIdx.x];
+  for (uint32_t p = threadIdx.x; p < job.nper; p += blockDim.x) {
+    const PeriodDesc d = periods[job.per0 + p];
+    const uint32_t idx = d.in_tab >> 16, in = d.in_tab & 0xffffu;
+    uint32_t w[8];
+#pragma unroll
+    for (int s = 0; s < 8; s++) w[s] = 0x80808080u;
+    if (idx != 0xffu) {
+      const uint32_t mask = c_pmask[idx & 31u];
+      const int nst = idx >= 32u ? 6 : 8;
+      uint32_t i = in;
+#pragma unroll
+      for (int s = 0; s < 8; s++) {
+        if (s < nst) {
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            if ((mask >> (4 * s + j)) & 1u) {
+              const uint8_t *slot = cifs_soft + job.slot_off[c_tdi_slot[i & 15u]] / CIF_BYTES * SOFT_CIF_BYTES;
+              const uint32_t v = i < (uint32_t)DABGPU_CIF_BITS ? slot[i] : 128u;
+              w[s] = (w[s] & ~(0xffu << (8 * j))) | (v << (8 * j));
+              i++;
+            }
+          }
+        }
+      }
+    }
+    uint4 *dst = reinterpret_cast<uint4 *>(rows + 4ull * (job.row_base + 8ull * d.row_off8));
+    dst[0] = make_uint4(w[0], w[1], w[2], w[3]);
+    dst[1] = make_uint4(w[4], w[5], w[6], w[7]);
+  }
+}
+int launch_msc_soft_gather(const uint8_t *d_cifs_soft, const CifJob *d_jobs, const PeriodDesc *d_periods,
+                           uint8_t *d_rows, int n_jobs, cudaStream_t st) {
+  if (n_jobs <= 0) return DABGPU_OK;
+  msc_soft_gather_kernel<<<n_jobs, 128, 0, st>>>(d_cifs_soft, d_jobs, d_periods, d_rows);
+  LAUNCH_CHECK();
+  return DABGPU_OK;
+}
+
+// fic_depuncture (depuncture.c:45-82) on symbols: codeword cw = 4 * (frame index) + group reads its
+// 2304 symbols at fic + d_index[frame] * stride + group * 2304
+__global__ void __launch_bounds__(256) fic_soft_rows_kernel(const uint8_t *__restrict__ fic, uint64_t stride,
+                                                            const uint32_t *__restrict__ index,
+                                                            uint32_t *__restrict__ rows, int n_cw,
+                                                            const ShapeDev *__restrict__ shape) {
+  const uint32_t row_words = vit_soft_row_bytes(774) / 4;
+  const uint64_t idx = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const uint64_t cw = idx / row_words;
+  const uint32_t t = (uint32_t)(idx % row_words);
+  if (cw >= (uint64_t)n_cw) return;
+  uint32_t w = 0x80808080u;
+  if (t < 774u) {
+    int r = 0;
+    while (r + 1 < shape->n_regions && (int)t >= shape->r[r + 1].step0) r++;
+    const uint32_t mask = shape->r[r].mask;
+    const uint32_t rel = 4u * (t - (uint32_t)shape->r[r].step0), per = rel >> 5, pos0 = rel & 31u;
+    const uint64_t frame = index ? (uint64_t)index[cw >> 2] : cw >> 2;
+    const uint8_t *src = fic + frame * stride + (cw & 3u) * 2304u + (uint32_t)shape->r[r].in0 +
+                         per * (uint32_t)shape->r[r].ones;
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      const uint32_t pos = pos0 + j;
+      if ((mask >> pos) & 1u) {
+        const uint32_t v = src[__popc(mask & ((1u << pos) - 1u))];
+        w = (w & ~(0xffu << (8 * j))) | (v << (8 * j));
+      }
+    }
+  }
+  rows[cw * row_words + t] = w;
+}
+int launch_fic_soft_rows(const uint8_t *d_fic, uint64_t stride, const uint32_t *d_index, uint8_t *d_rows, int n_cw,
+                         const ShapeDev *d_shape, cudaStream_t st) {
+  const uint64_t total = (uint64_t)n_cw * (vit_soft_row_bytes(774) / 4);
+  if (!total) return DABGPU_OK;
+  fic_soft_rows_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(d_fic, stride, d_index,
+                                                                        reinterpret_cast<uint32_t *>(d_rows), n_cw, d_shape);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }

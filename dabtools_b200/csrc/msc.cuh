@@ -72,6 +72,14 @@ struct EtiJob {
 int launch_eti_pack(const EtiJob *d_jobs, const EnsDev *d_ens, const uint8_t *d_fibs, uint8_t *d_eti,
                     int n_frames, cudaStream_t st);
 
+// ---- soft-decision data path (opt-in): CIFs as 55296 symbol bytes, rows of 4 symbols per step ----
+int launch_soft_store(const uint8_t *d_msc_bytes, uint64_t tf_stride, const uint64_t *d_dst_off, uint8_t *d_cifs_soft,
+                      int n_tf, cudaStream_t st);
+int launch_msc_soft_gather(const uint8_t *d_cifs_soft, const CifJob *d_jobs, const PeriodDesc *d_periods,
+                           uint8_t *d_rows, int n_jobs, cudaStream_t st);
+int launch_fic_soft_rows(const uint8_t *d_fic, uint64_t stride, const uint32_t *d_index, uint8_t *d_rows, int n_cw,
+                         const ShapeDev *d_shape, cudaStream_t st);
+
 // ---- Wavefinder producer (input_wf.c:23-115): USB packets -> demapped transmission frames --------
 int launch_wf_demap(const uint8_t *d_packets, uint64_t pitch, const int32_t *d_n_packets, int max_packets,
                     const int32_t *d_slot, uint8_t *d_tf_ring, uint32_t *d_fic_seen, uint8_t *d_tf_out, int n_streams,

@@ -655,7 +655,7 @@ __device__ __forceinline__ void fft2048_pair(C2 *v, const float2 *tw1, DemodSmem
 
 // Grid (segments, streams): segment 0 = PRS + the three FIC symbols, segment c = 1..4 = CIF c-1
 // (its 18 symbols and the one before them).  A CTA walks its symbols two at a time.
-template <bool DEBUG>
+template <bool DEBUG, bool SOFT>
 __global__ void __launch_bounds__(FFT_THREADS, DEMOD_CTAS_PER_SM)
     demod_kernel(RingGeom ring, const uint8_t *__restrict__ tails, const uint8_t *__restrict__ frames,
                  const StepCtl *__restrict__ ctl, const SyncOut *__restrict__ sync, uint8_t *__restrict__ fic_bits,
@@ -706,7 +706,7 @@ __global__ void __launch_bounds__(FFT_THREADS, DEMOD_CTAS_PER_SM)
   // the place of thread 0's DC bin: slot k <-> m = k (k < 6) or k + 4.  A carrier's four bits of a
   // symbol pair go to one byte of sm.nib whose position is constant over symbols: plane order for
   // the MSC (msc.cuh), n itself for the FIC symbols.
-  const bool plane_order = !(seg == 0 || DEBUG);
+  const bool plane_order = !(seg == 0 || DEBUG || SOFT);
   uint32_t pos[N_SLOTS];
 #pragma unroll
   for (int k = 0; k < N_SLOTS; k++) {
@@ -776,17 +776,47 @@ __global__ void __launch_bounds__(FFT_THREADS, DEMOD_CTAS_PER_SM)
             dbg_symd[(size_t)(la + 1) * 2048 + bin] = make_float2((xb * xa + yb * ya) / db, (xb * ya - yb * xa) / db);
         }
       }
-      uint32_t nb = __funnelshift_l(__float_as_uint(qb), 0u, 1);
-      nb = __funnelshift_l(__float_as_uint(rb), nb, 1);
-      nb = __funnelshift_l(__float_as_uint(qa), nb, 1);
-      nb = __funnelshift_l(__float_as_uint(ra), nb, 1);
-      sm.nib[pos[k]] = (uint8_t)nb;
+      if (SOFT) {
+        // Soft decisions (opt-in): instead of the signs, the normalised differential product itself
+        // (what input_sdr.c:139-142 computes and :157-158 slices), as a symbol 128 -+ round(8 x)
+        // clipped to 121..135: < 128 says "bit 0", like the reference's 127 / 129.
+        uint8_t *sb = reinterpret_cast<uint8_t *>(sm.planes);  // [4][1536]: A.b0, A.b1, B.b0, B.b1 by n
+        const float da = px[k] * px[k] + py[k] * py[k], db = xa * xa + ya * ya;
+        const float ga = da > 0.f ? 8.f / da : 0.f, gb = db > 0.f ? 8.f / db : 0.f;
+        const float ea = xa * px[k] + ya * py[k], fa = xa * py[k] - ya * px[k];
+        const float eb = xb * xa + yb * ya, fb = xb * ya - yb * xa;
+        const uint32_t n = pos[k];
+        sb[n] = (uint8_t)(128 - (int)fminf(fmaxf(rintf(ea * ga), -7.f), 7.f));
+        sb[1536 + n] = (uint8_t)(128 + (int)fminf(fmaxf(rintf(fa * ga), -7.f), 7.f));
+        sb[3072 + n] = (uint8_t)(128 - (int)fminf(fmaxf(rintf(eb * gb), -7.f), 7.f));
+        sb[4608 + n] = (uint8_t)(128 + (int)fminf(fmaxf(rintf(fb * gb), -7.f), 7.f));
+      } else {
+        uint32_t nb = __funnelshift_l(__float_as_uint(qb), 0u, 1);
+        nb = __funnelshift_l(__float_as_uint(rb), nb, 1);
+        nb = __funnelshift_l(__float_as_uint(qa), nb, 1);
+        nb = __funnelshift_l(__float_as_uint(ra), nb, 1);
+        sm.nib[pos[k]] = (uint8_t)nb;
+      }
       px[k] = xb;
       py[k] = yb;
     }
     __syncthreads();
     // rows: symbol A is data symbol la - 1 of the frame, B is la
-    if (!plane_order) {
+    if (SOFT) {
+      // symbols in logical order: FIC as 3 rows of 3072 per stream, a CIF as 18 rows in its slot of the
+      // soft CIF store (55296 bytes; the hard store's offsets address it slot by slot)
+      uint8_t *out = seg == 0 ? fic_bits + (uint64_t)s * 9216
+                              : cifs + ctl[s].cif_off[seg - 1] / CIF_BYTES * 55296ull;
+      const int row_a = seg == 0 ? la - 1 : 2 * i - 1;
+      const uint4 *sb = reinterpret_cast<const uint4 *>(sm.planes);
+      for (int c = p; c < 384; c += FFT_THREADS) {  // 4 kinds x 96 vectors of 16 bytes
+        const int kind = c / 96, v = c % 96;
+        const bool is_b = kind >= 2;
+        if (is_b ? !b_valid : i == 0) continue;
+        const int row = row_a + (is_b ? 1 : 0);
+        reinterpret_cast<uint4 *>(out + (size_t)row * 3072 + (kind & 1) * 1536)[v] = sb[c];
+      }
+    } else if (!plane_order) {
       uint8_t *out = DEBUG ? dbg_bits : fic_bits + (uint64_t)s * 9216;
       const bool a_valid = i > 0;  // the first symbol of a segment is only the phase reference
       for (int c = p; c < 384; c += FFT_THREADS) {
@@ -839,18 +869,25 @@ __global__ void __launch_bounds__(FFT_THREADS, DEMOD_CTAS_PER_SM)
 
 int launch_demod(RingGeom d_ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
                  const SyncOut *d_sync, uint8_t *d_fic_bits, uint8_t *d_cifs, int n_streams, int seg_first,
-                 int seg_count, cudaStream_t st) {
+                 int seg_count, bool soft, cudaStream_t st) {
   if (n_streams <= 0) return DABGPU_OK;
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(demod_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(demod_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  (int)sizeof(DemodSmem)));
+    CUDA_TRY(cudaFuncSetAttribute(demod_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(DemodSmem)));
     attr_set = true;
   }
   dim3 grid(seg_count, n_streams);
-  demod_kernel<false><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_ring, d_tails, d_frames, d_ctl, d_sync,
-                                                                   d_fic_bits, d_cifs, nullptr, nullptr, nullptr,
-                                                                   seg_first);
+  if (soft)
+    demod_kernel<false, true><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_ring, d_tails, d_frames, d_ctl, d_sync,
+                                                                            d_fic_bits, d_cifs, nullptr, nullptr,
+                                                                            nullptr, seg_first);
+  else
+    demod_kernel<false, false><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(d_ring, d_tails, d_frames, d_ctl, d_sync,
+                                                                             d_fic_bits, d_cifs, nullptr, nullptr,
+                                                                             nullptr, seg_first);
   LAUNCH_CHECK();
   return DABGPU_OK;
 }
@@ -859,14 +896,14 @@ int launch_demod_debug(const uint8_t *d_frame, float2 *d_symbols, float2 *d_symb
                        cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    CUDA_TRY(cudaFuncSetAttribute(demod_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    CUDA_TRY(cudaFuncSetAttribute(demod_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                   (int)sizeof(DemodSmem)));
     attr_set = true;
   }
   // one "segment" walking all 76 symbols is what the debug variant needs: reuse seg 0 semantics
   // by launching the five segments; each writes its own rows
   dim3 grid(5, 1);
-  demod_kernel<true><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(RingGeom{nullptr, 0, IQ_RING_BYTES}, nullptr, d_frame, nullptr, nullptr,
+  demod_kernel<true, false><<<grid, FFT_THREADS, sizeof(DemodSmem), st>>>(RingGeom{nullptr, 0, IQ_RING_BYTES}, nullptr, d_frame, nullptr, nullptr,
                                                                   nullptr, nullptr, d_symbols, d_symbols_d, d_bits, 0);
   LAUNCH_CHECK();
   return DABGPU_OK;

@@ -71,9 +71,11 @@ int launch_sync(RingGeom ring, const uint8_t *d_tails, const uint8_t *d_frames, 
                 SyncOut *d_out, int n_streams, cudaStream_t st);
 // fic_bits: [n_streams][9216] one byte per bit (reference layout); MSC goes to the CIF store as planes
 // segments: 0 = PRS + the 3 FIC symbols, 1..4 = the 4 CIFs; launched as [seg_first, seg_first+seg_count)
+// soft: symbols (128 -+ round(8 x), 121..135) instead of bits: fic_bits gets 9216 symbol bytes, d_cifs is the
+// soft CIF store (55296 bytes per CIF, logical order)
 int launch_demod(RingGeom ring, const uint8_t *d_tails, const uint8_t *d_frames, const StepCtl *d_ctl,
                  const SyncOut *d_sync, uint8_t *d_fic_bits, uint8_t *d_cifs, int n_streams, int seg_first,
-                 int seg_count, cudaStream_t st);
+                 int seg_count, bool soft, cudaStream_t st);
 
 // debug / parity variants on a single frame buffer: raw spectra (fftshifted, 76x2048 complex
 // float), DQPSK products (rows 1..75) and the reference's byte-per-bit demapped output

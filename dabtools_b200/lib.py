@@ -165,6 +165,14 @@ def demod_frame_debug(frame: np.ndarray) -> dict:
     return dict(symbols=sym, symbols_d=symd, bits=bits)
 
 
+def demod_frame_soft(frame: np.ndarray) -> np.ndarray:
+    frame = np.ascontiguousarray(frame, dtype=np.uint8).ravel()
+    assert frame.size == 393216
+    out = np.zeros(230400, dtype=np.uint8)
+    check(load().dabgpu_demod_frame_soft(_np_ptr(frame), _np_ptr(out)))
+    return out
+
+
 # ---- batched receiver ---------------------------------------------------------------------------------
 class StreamStatus(C.Structure):
     _fields_ = [("locked", C.c_int32), ("okcount", C.c_int32), ("ncifs", C.c_int32), ("tfidx", C.c_int32),
@@ -176,6 +184,7 @@ class StreamStatus(C.Structure):
 
 ENGINE_VERBOSE = 1
 ENGINE_VIRTUAL_TUNER = 2
+ENGINE_SOFT = 4
 
 
 class Engine:

@@ -69,6 +69,10 @@ void dabgpu_tab_prbs(uint8_t *out, int nbytes);  /* energy-dispersal sequence, m
  * (needs nbits <= 9216).  Batched form of viterbi(), viterbi.c:352-452. */
 int dabgpu_viterbi_batch(const uint8_t *soft, size_t soft_pitch, int n, int nbits, uint8_t *out,
                          size_t out_pitch, int descramble, int on_device);
+/* The soft demapper (see DABGPU_ENGINE_SOFT) on one frame, without the synchronisers: 393216 bytes of
+ * uint8 I/Q as sdr_read_fifo leaves them -> 230400 symbol bytes in the layout of
+ * demapped_transmission_frame_t (fic 9216 + msc 221184). */
+int dabgpu_demod_frame_soft(const uint8_t *frame393216, uint8_t *soft230400);
 /* Soft-decision variant (opt-in): the symbols are NOT sliced; each is weighted with the
  * reference's own metric table gen_met(amp 1, noise 1.0, bias 0, scale 4) (viterbi.c:126-191,
  * :455-462), which is defined for 121..135 around the erasure value 128 (log-likelihood ratio about
@@ -107,6 +111,14 @@ typedef struct dabgpu_engine dabgpu_engine;
 
 #define DABGPU_ENGINE_VERBOSE 1        /* print the reference's stderr messages (Locked, ...) */
 #define DABGPU_ENGINE_VIRTUAL_TUNER 2  /* apply the tuner feedback as a software NCO on ingest */
+/* Soft-decision receiver (opt-in; the default is the reference's hard-decision demapper, bit-exact
+ * with it).  The demapper hands symbols instead of bits to the channel decoder: for every channel bit
+ * a byte 128 -+ round(8 x), clipped to 121..135, where x is the real / negated imaginary part of the
+ * normalised differential product s_l conj(s_l-1) / |s_l-1|^2 that input_sdr.c:132-158 slices at 0;
+ * depuncturing inserts 128, and the Viterbi decoder weights each symbol with the reference's own
+ * metric table (dabgpu_viterbi_soft_batch).  process_demapped() of a soft engine takes such symbol
+ * bytes (230400 per frame) instead of 0/1 bytes.  Worth about 2 dB at the decoder input. */
+#define DABGPU_ENGINE_SOFT 4
 
 typedef struct {
   int32_t locked, okcount, ncifs, tfidx;          /* dab_state_t, dab.h:83-86 */

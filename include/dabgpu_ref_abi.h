@@ -153,7 +153,11 @@ int init_viterbi(void);
  * with -DENABLE_SPIRAL_VITERBI.  Returns an opaque non-null handle; the decoder behind viterbi() is
  * the same (plain viterbi.c tie-breaking, the alphabet of either to_viterbi() variant is accepted) */
 void *create_viterbi(int len);
-/* viterbi.h:8 declares void, viterbi.c:352 defines int(...unsigned); int is ABI-compatible */
+/* viterbi.h:8 declares void, viterbi.c:352 defines int(...unsigned); int is ABI-compatible.
+ * Symbols: to_viterbi()'s alphabet (127 / 128 / 129, or 0 / 128 / 255 of the Spiral build) goes to the
+ * hard-decision kernel; any other value makes the call a soft-decision decode with the reference's
+ * metric table gen_met(1, 1.0, 0, 4), exact for symbols in 121..135 and saturating beyond (the
+ * reference's table overflows to INT_MIN there, viterbi.c:126-191). */
 int viterbi(void *p, unsigned char *symbols, unsigned char *data, unsigned int framebits);
 void dab_descramble_bytes(uint8_t *buf, int32_t nbytes);
 int check_fib_crc(uint8_t *data);

@@ -140,6 +140,14 @@ int orc_viterbi(const uint8_t *symbols, uint8_t *data, unsigned nbits) {
  * 2. Depuncturing                                   (src/depuncture.c)
  * ================================================================================== */
 
+/* Soft-decision extension (NOT in the reference, whose demapper slices): with
+ * orc_set_soft(1) the "bits" handed to the depuncturers are received symbol values around 128 and
+ * are passed through to viterbi() as they are -- saturated to 121..135, the range in which the
+ * reference's metric table gen_met(1, 1.0, 0, 4) is defined (viterbi.c:126-191) -- instead of being
+ * mapped by to_viterbi().  viterbi() itself is the reference's algorithm unchanged. */
+static int g_soft;
+void orc_set_soft(int on) { g_soft = on; }
+
 /* depuncture.c:36-43 to_viterbi(): hard bit -> 127/129, punctured -> 128 */
 static int depuncture_shape(const dabgpu_cw_shape *sh, uint8_t *out, const uint8_t *in) {
   int k = 0, j = 0;
@@ -147,9 +155,10 @@ static int depuncture_shape(const dabgpu_cw_shape *sh, uint8_t *out, const uint8
     uint32_t mask = dabgpu_puncture_mask(sh->r[r].pi);
     int nbits = 4 * sh->r[r].steps;
     for (int i = 0; i < nbits; i++) {
-      if ((mask >> (i & 31)) & 1u)
-        out[k++] = (uint8_t)(127 + 2 * in[j++]);
-      else
+      if ((mask >> (i & 31)) & 1u) {
+        const int v = in[j++];
+        out[k++] = g_soft ? (uint8_t)(v < 121 ? 121 : v > 135 ? 135 : v) : (uint8_t)(127 + 2 * v);
+      } else
         out[k++] = 128;
     }
   }

@@ -244,6 +244,10 @@ class Port(_Common):
         self.lib.orc_gen_metrics(_p(t, C.c_int), amp, noise, bias, scale)
         return t
 
+    def set_soft(self, on: bool):
+        """soft-decision extension: depuncturers pass symbol values (saturated to 121..135) through"""
+        self.lib.orc_set_soft(int(on))
+
     def fic_depuncture(self, bits2304):
         bits = np.ascontiguousarray(bits2304, dtype=np.uint8)
         out = np.empty(3096, dtype=np.uint8)

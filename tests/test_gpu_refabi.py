@@ -203,3 +203,18 @@ def test_spiral_mode_callers(api, port):
                 same_sp += np.array_equal(got, ds)
     if sp is not None:
         assert same_sp >= 0.75 * n, (same_sp, n)
+
+
+def test_viterbi_signature_with_real_soft_symbols(api, port):
+    """a caller of the reference-signature viterbi() who passes real soft values gets the
+    reference's soft-decision decode (its own metric table), not a sliced one."""
+    rng = np.random.default_rng(31)
+    nbits = 768
+    data = rng.integers(0, 256, nbits // 8, dtype=np.uint8)
+    sym = port.encode(data).astype(np.float64)
+    v = np.clip(np.rint(128 + (2 * sym - 1) * 3 + rng.normal(0, 2.5, sym.size)), 121, 135).astype(np.uint8)
+    got = api.viterbi(v, nbits)
+    assert np.array_equal(got, port.viterbi(v, nbits))
+    sliced = (127 + 2 * (v > 128)).astype(np.uint8)
+    sliced[v == 128] = 128
+    assert not np.array_equal(port.viterbi(sliced, nbits), got) or np.array_equal(got, data)
