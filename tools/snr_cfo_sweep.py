@@ -85,17 +85,23 @@ def main():
     n = min(r.size for r in iq_rows) // 262144 * 262144
     iq = np.stack([r[:n] for r in iq_rows])
 
-    # ---- GPU engine ----
+    # ---- GPU engine: hard decisions (the reference's behaviour), then the opt-in soft-decision mode ----
     lib.check(lib.load().dabgpu_set_device(0))
-    eng = lib.Engine(S, 200_000_000, lib.ENGINE_VIRTUAL_TUNER)
-    got = [[] for _ in range(S)]
-    for pos in range(0, n, 262144):
-        eng.feed_iq(iq[:, pos:pos + 262144])
-        eti, ids = eng.fetch_eti()
-        for f, s in zip(eti, ids):
-            got[s].append(f.copy())
-    st = [eng.status(s) for s in range(S)]
-    eng.close()
+
+    def run_engine(flags):
+        eng = lib.Engine(S, 200_000_000, flags)
+        out = [[] for _ in range(S)]
+        for pos in range(0, n, 262144):
+            eng.feed_iq(iq[:, pos:pos + 262144])
+            eti, ids = eng.fetch_eti()
+            for f, s in zip(eti, ids):
+                out[s].append(f.copy())
+        status = [eng.status(s) for s in range(S)]
+        eng.close()
+        return out, status
+
+    got, st = run_engine(lib.ENGINE_VIRTUAL_TUNER)
+    got_soft, st_soft = run_engine(lib.ENGINE_VIRTUAL_TUNER | lib.ENGINE_SOFT)
 
     # ---- CPU oracle, one stream per process ----
     tmp = tempfile.NamedTemporaryFile(suffix=".npy", delete=False, dir="/dev/shm")
@@ -109,9 +115,11 @@ def main():
     lines = ["# BASELINE config 4: SNR x CFO sweep, GPU engine vs CPU oracle (reference receive loop)\n",
              f"{S} streams, {a.tfs - 1} TFs each, small_ensemble (3 sub-channels), virtual tuner on both sides.\n",
              "Per cell: streams locked at the end / ETI frames / post-Viterbi BER (GPU | oracle), identical = "
-             "streams whose ETI bytes are equal.\n\n",
-             "| SNR dB | CFO Hz | locked GPU | locked ref | frames GPU | frames ref | BER GPU | BER ref | identical |\n",
-             "|---|---|---|---|---|---|---|---|---|\n"]
+             "streams whose ETI bytes are equal; last three columns: the same captures through a "
+             "DABGPU_ENGINE_SOFT engine (opt-in soft decisions, no reference counterpart).\n\n",
+             "| SNR dB | CFO Hz | locked GPU | locked ref | frames GPU | frames ref | BER GPU | BER ref | identical "
+             "| locked soft | frames soft | BER soft |\n",
+             "|---|---|---|---|---|---|---|---|---|---|---|---|\n"]
     tot_same = 0
     for snr, cfo in cells:
         ss = [s for s in range(S) if cell_of[s] == (snr, cfo)]
@@ -119,8 +127,10 @@ def main():
         lr = sum(ref[s][1] for s in ss)
         fg = sum(len(got[s]) for s in ss)
         fr = sum(ref[s][0].shape[0] for s in ss)
-        eg = bg = er = br = 0
+        eg = bg = er = br = es = bs = 0
         same = 0
+        ls = sum(st_soft[s].locked for s in ss)
+        fs = sum(len(got_soft[s]) for s in ss)
         for s in ss:
             ge = np.array(got[s], dtype=np.uint8).reshape(-1, 6144)
             e, b = payload_ber(ens, payloads[s], 0, ge)
@@ -129,10 +139,14 @@ def main():
             e, b = payload_ber(ens, payloads[s], 0, ref[s][0])
             er += e
             br += b
+            e, b = payload_ber(ens, payloads[s], 0, np.array(got_soft[s], dtype=np.uint8).reshape(-1, 6144))
+            es += e
+            bs += b
             same += int(ge.shape == ref[s][0].shape and np.array_equal(ge, ref[s][0]))
         tot_same += same
         lines.append(f"| {snr} | {cfo} | {lg}/{len(ss)} | {lr}/{len(ss)} | {fg} | {fr} | "
-                     f"{eg / bg if bg else float('nan'):.2e} | {er / br if br else float('nan'):.2e} | {same}/{len(ss)} |\n")
+                     f"{eg / bg if bg else float('nan'):.2e} | {er / br if br else float('nan'):.2e} | {same}/{len(ss)} | "
+                     f"{ls}/{len(ss)} | {fs} | {es / bs if bs else float('nan'):.2e} |\n")
     lines.append(f"\nStreams with byte-identical ETI: {tot_same}/{S}\n")
     text = "".join(lines)
     print(text)
