@@ -533,7 +533,10 @@ __device__ __forceinline__ void dft16p(C2 *v) {
 }
 
 
-enum { SYM_BYTES = 4096, STAGE_BYTES = SYM_BYTES + 16, N_STAGES = 3, DEMOD_CTAS_PER_SM = 3 };
+#ifndef DABGPU_DEMOD_CTAS
+#define DABGPU_DEMOD_CTAS 3  // launch bound: 3 -> up to 168 registers, 4 -> 128 (kernel experiments: build.py --variant)
+#endif
+enum { SYM_BYTES = 4096, STAGE_BYTES = SYM_BYTES + 16, N_STAGES = 3, DEMOD_CTAS_PER_SM = DABGPU_DEMOD_CTAS };
 enum { N_SLOTS = 12 };  // carriers per thread and symbol
 
 struct DemodSmem {
