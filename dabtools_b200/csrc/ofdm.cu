@@ -737,10 +737,6 @@ __global__ void __launch_bounds__(FFT_THREADS, DEMOD_CTAS_PER_SM)
       load_pair(v, a, ah, b, bh, p);
     }
     fft2048_pair(v, tw1, sm, p);  // (its first barrier also says: staging buffer consumed)
-    if (p == 0 && i + N_STAGES < npair) {
-      fence_proxy_async();
-      issue_pair(i + N_STAGES, st);
-    }
     if (DEBUG) {
 #pragma unroll
       for (int m = 0; m < 16; m++) {
@@ -804,6 +800,13 @@ __global__ void __launch_bounds__(FFT_THREADS, DEMOD_CTAS_PER_SM)
       py[k] = yb;
     }
     __syncthreads();
+    // Refill the staging buffers this pair was read from (every thread is past the FFT's barriers).
+    // Issued from the fourth warp, which has no part in the bit packing below, so that the ~100
+    // instructions of address arithmetic and copy issue do not sit on the packing warps' path.
+    if (p == 96 && i + N_STAGES < npair) {
+      fence_proxy_async();
+      issue_pair(i + N_STAGES, st);
+    }
     // rows: symbol A is data symbol la - 1 of the frame, B is la
     if (SOFT) {
       // symbols in logical order: FIC as 3 rows of 3072 per stream, a CIF as 18 rows in its slot of the

@@ -33,17 +33,43 @@ static struct rtlsdr_dev g_dev;
 
 static pthread_mutex_t g_mu = PTHREAD_MUTEX_INITIALIZER;
 static pthread_cond_t g_cv = PTHREAD_COND_INITIALIZER;
-static long g_waits;      /* times the consumer has gone back to sem_wait */
+/* sem_wait() entries per semaphore: other threads of the process (the CUDA driver's, a profiler's) use
+ * semaphores too, so only the ones on dab2eti's `data_ready` may count.  Its address is learnt from the
+ * sem_post() the callback makes on the producer thread (dab2eti.c:127-129). */
+static struct { sem_t *s; long waits; } g_sems[1024];
+static sem_t *g_data_ready;
 static pthread_t g_producer;
 static int g_have_producer;
+
+static long waits_on(sem_t *s) {
+  for (int i = 0; i < 1024 && g_sems[i].s; i++)
+    if (g_sems[i].s == s) return g_sems[i].waits;
+  return 0;
+}
 
 int sem_wait(sem_t *s) {
   static int (*real)(sem_t *);
   if (!real) real = (int (*)(sem_t *))dlsym(RTLD_NEXT, "sem_wait");
-  if (!g_have_producer || !pthread_equal(pthread_self(), g_producer)) {
+  pthread_mutex_lock(&g_mu);
+  for (int i = 0; i < 1024; i++) {
+    if (g_data_ready && s != g_data_ready) break;  /* once known, only dab2eti's semaphore is tracked */
+    if (g_sems[i].s == s || !g_sems[i].s) {
+      g_sems[i].s = s;
+      g_sems[i].waits++;
+      break;
+    }
+  }
+  pthread_cond_broadcast(&g_cv);
+  pthread_mutex_unlock(&g_mu);
+  return real(s);
+}
+
+int sem_post(sem_t *s) {
+  static int (*real)(sem_t *);
+  if (!real) real = (int (*)(sem_t *))dlsym(RTLD_NEXT, "sem_post");
+  if (g_have_producer && pthread_equal(pthread_self(), g_producer)) {
     pthread_mutex_lock(&g_mu);
-    g_waits++;
-    pthread_cond_broadcast(&g_cv);
+    g_data_ready = s;
     pthread_mutex_unlock(&g_mu);
   }
   return real(s);
@@ -93,10 +119,6 @@ int rtlsdr_read_async(rtlsdr_dev_t *dev, rtlsdr_read_async_cb_t cb, void *ctx, u
   g_producer = pthread_self();
   g_have_producer = 1;
   long delivered = 0;
-  /* the consumer thread was created just before this call: wait until it sits in its first sem_wait */
-  pthread_mutex_lock(&g_mu);
-  while (g_waits < 1) pthread_cond_wait(&g_cv, &g_mu);
-  pthread_mutex_unlock(&g_mu);
   while (!dev->cancel && fread(buf, 1, buf_len, dev->f) == buf_len) {
     const double df = (double)dev->freq - (double)dev->f0;
     if (df != 0.0) {
@@ -111,10 +133,12 @@ int rtlsdr_read_async(rtlsdr_dev_t *dev, rtlsdr_read_async_cb_t cb, void *ctx, u
       }
     }
     dev->pos += buf_len;
-    cb(buf, buf_len, ctx);
+    cb(buf, buf_len, ctx);   /* memcpy + sem_post(&data_ready): tells us which semaphore it is */
     delivered++;
-    pthread_mutex_lock(&g_mu);  /* the consumer is done with this buffer when it waits again */
-    while (g_waits < 1 + delivered) pthread_cond_wait(&g_cv, &g_mu);
+    /* The consumer enters sem_wait(&data_ready) once before its first buffer and once after each
+     * buffer it has processed: buffer k is done when it has entered delivered + 1 times. */
+    pthread_mutex_lock(&g_mu);
+    while (!g_data_ready || waits_on(g_data_ready) < 1 + delivered) pthread_cond_wait(&g_cv, &g_mu);
     pthread_mutex_unlock(&g_mu);
   }
   free(buf);
