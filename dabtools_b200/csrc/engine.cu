@@ -94,6 +94,7 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
   quiet = !(flags & DABGPU_ENGINE_VERBOSE);
   virtual_tuner = flags & DABGPU_ENGINE_VIRTUAL_TUNER;
   soft = flags & DABGPU_ENGINE_SOFT;
+  follow_reconfig = flags & DABGPU_ENGINE_FOLLOW_RECONFIG;
   vb_fic.soft = vb_msc.soft = soft;
   subch_mask.assign(S, ~0ull);
   front.assign(S, FrontState());
@@ -104,6 +105,7 @@ int Engine::init(int n_streams, uint32_t tuner_hz, int flags) {
     front[s].frequency = tuner_hz;
     front[s].rng.seed(1);
     back[s].reset();
+    back[s].follow = follow_reconfig;
   }
   {
     const char *env = getenv("DABGPU_HOST_THREADS");
@@ -311,9 +313,12 @@ void Engine::destroy() {
 // (re)derive the ETI/MSC layout of stream s from its ens_info (misc.c:153-213, :246-278)
 int Engine::refresh_layout(int s) {
   EnsLayout &L = layout[s];
-  const ens_info_t &ei = back[s].ens_info;
-  if (L.version == back[s].ens_version) return DABGPU_OK;
-  L.version = back[s].ens_version;
+  // (follow mode: the table that was current for the frames' own CIFs, see hostlogic.cuh)
+  const bool fol = back[s].follow && back[s].emit_sub;
+  const subchannel_info_t *subchans = fol ? back[s].emit_sub : back[s].ens_info.subchans;
+  const uint64_t want_version = fol ? back[s].emit_version : back[s].ens_version;
+  if (L.version == want_version) return DABGPU_OK;
+  L.version = want_version;
   L.epoch = ++layout_epoch;
   L.nsub = 0;
   memset(&L.dev, 0, sizeof L.dev);
@@ -326,7 +331,7 @@ int Engine::refresh_layout(int s) {
   dabgpu_cw_shape shp[64];
   bool usable[64];
   for (int j = 0; j < 64; j++) {
-    const subchannel_info_t &sc = ei.subchans[j];
+    const subchannel_info_t &sc = subchans[j];
     usable[j] = false;
     if (sc.id < 0 || !((keep >> j) & 1)) continue;
     if (host_subch_shape(&sc, &shp[j]) || shp[j].nbits <= 0 || shp[j].nbits > 9216 ||
@@ -341,7 +346,7 @@ int Engine::refresh_layout(int s) {
   L.e1 = 12 + 4 * nst;
   uint32_t e = L.e1 + 96;
   for (int j = 0; j < 64; j++) {
-    const subchannel_info_t &sc = ei.subchans[j];
+    const subchannel_info_t &sc = subchans[j];
     if (!usable[j]) continue;
     const dabgpu_cw_shape &sh = shp[j];
     EnsLayout::Sub &u = L.sub[L.nsub];
@@ -581,7 +586,7 @@ int Engine::backend_host(cudaStream_t st) {
     const FrameWork &work = works[a];
     if (!work.n_eti) continue;
     const int s = lag.active[a];
-    if (layout[s].version != back[s].ens_version) {
+    if (layout[s].version != (back[s].follow && back[s].emit_sub ? back[s].emit_version : back[s].ens_version)) {
       // the multiplex description changed: frames of this stream that are still queued were
       // produced under the old layout and must be decoded first
       if (pend_of_stream[s]) {

@@ -76,6 +76,7 @@ struct Engine {
   uint32_t f0 = 0;
   bool quiet = true;
   bool virtual_tuner = false;
+  bool follow_reconfig = false;  // DABGPU_ENGINE_FOLLOW_RECONFIG (hostlogic.cuh)
   bool soft = false;  // DABGPU_ENGINE_SOFT: symbols instead of bits from the demapper to the Viterbi decoder
   std::vector<FrontState> front;
   std::vector<BackendState> back;

@@ -4,7 +4,13 @@
 namespace dabgpu {
 
 // FIG 0/0, 0/1 and 0/2 extraction, behaviour of fic.c:47-130 fib_parse()
-static void parse_fib(tf_info_t *info, const uint8_t *fib, bool quiet) {
+// what the reference's parser does not look at (fic.c:56-70): the C/N flag of FIG type 0 and the
+// change flags / occurrence change of FIG 0/0 (EN 300 401 clause 6.4); only filled when asked for
+struct ReconfigInfo {
+  subchannel_info_t next_sub[64];  // FIG 0/1 entries of the next configuration (C/N = 1)
+  int change_flags, occurrence;
+};
+static void parse_fib(tf_info_t *info, const uint8_t *fib, bool quiet, ReconfigInfo *rc = nullptr) {
   int pos = 0;
   while (fib[pos] != 0xff && pos < 30) {
     const int fig_type = fib[pos] >> 5;
@@ -13,14 +19,19 @@ static void parse_fib(tf_info_t *info, const uint8_t *fib, bool quiet) {
     if (fig_type == 0) {
       const int ext = fib[pos] & 0x1f;
       const int pd = (fib[pos] >> 5) & 1;
+      const bool next_cfg = rc && (fib[pos] >> 7);
       if (ext == 0) {  // ensemble information
         info->EId = (uint16_t)((fib[pos + 1] << 8) | fib[pos + 2]);
         info->CIFCount_hi = fib[pos + 3] & 0x1f;
         info->CIFCount_lo = fib[pos + 4];
+        if (rc) {
+          rc->change_flags = fib[pos + 3] >> 6;
+          if (rc->change_flags && fig_len >= 6) rc->occurrence = fib[pos + 5];
+        }
       } else if (ext == 1) {  // sub-channel organisation
         for (int j = pos + 1; j < pos + fig_len;) {
           const int id = fib[j] >> 2;
-          subchannel_info_t *sc = &info->subchans[id];
+          subchannel_info_t *sc = next_cfg ? &rc->next_sub[id] : &info->subchans[id];
           sc->id = id;
           sc->start_cu = ((fib[j] & 3) << 8) | fib[j + 1];
           sc->slForm = fib[j + 2] >> 7;
@@ -66,6 +77,18 @@ void host_fib_decode(tf_info_t *info, const uint8_t *fibs, const uint8_t *crc_ok
   for (int i = 0; i < 64; i++) info->subchans[i].id = info->subchans[i].ASCTy = -1;
   for (int i = 0; i < nfibs; i++)
     if (crc_ok[i]) parse_fib(info, fibs + 32 * i, quiet);
+}
+static void host_fib_decode_follow(tf_info_t *info, ReconfigInfo *rc, const uint8_t *fibs, const uint8_t *crc_ok,
+                                   int nfibs, bool quiet) {
+  memset(info, 0, sizeof *info);
+  for (int i = 0; i < 64; i++) {
+    info->subchans[i].id = info->subchans[i].ASCTy = -1;
+    rc->next_sub[i].id = rc->next_sub[i].ASCTy = -1;
+  }
+  rc->change_flags = 0;
+  rc->occurrence = -1;
+  for (int i = 0; i < nfibs; i++)
+    if (crc_ok[i]) parse_fib(info, fibs + 32 * i, quiet, rc);
 }
 
 // misc.c:14-27
@@ -119,6 +142,13 @@ void BackendState::reset() {
   ncifs = tfidx = locked = okcount = ens_info_shown = 0;
   phys = 0;
   ens_version = 1;
+  for (int i = 0; i < 64; i++) next_sub[i].id = next_sub[i].ASCTy = -1;
+  change_flags = 0;
+  occurrence = newest_cif_lo = -1;
+  for (auto &h : hist) h.version = 0;
+  hist_head = 0;
+  emit_version = 0;
+  emit_sub = nullptr;
 }
 
 // misc.c:14-27, additionally reporting whether the sub-channel table changed
@@ -147,7 +177,13 @@ void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *cr
   out->n_eti = 0;
   int ok_count = 0;
   for (int i = 0; i < 12; i++) ok_count += crc_ok[i] ? 1 : 0;
-  if (ok_count > 0) host_fib_decode(&st.tf_info, fibs, crc_ok, 12, quiet);
+  ReconfigInfo rcf;
+  if (ok_count > 0) {
+    if (st.follow)
+      host_fib_decode_follow(&st.tf_info, &rcf, fibs, crc_ok, 12, quiet);
+    else
+      host_fib_decode(&st.tf_info, fibs, crc_ok, 12, quiet);
+  }
 
   if (ok_count == 12) {
     st.okcount++;
@@ -162,12 +198,49 @@ void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *cr
       if (!quiet) fprintf(stderr, "Lock lost, resetting ringbuffer\n");
       st.ncifs = 0;
       st.tfidx = 0;
+      st.hist_head = 0;
       return;
     }
   }
   if (!st.locked) return;
 
+  if (st.follow && ok_count > 0) {
+    // The configuration announced for CIF count `occurrence` becomes current with the transmission
+    // frame that carries that CIF (in Mode I a reconfiguration starts a transmission frame): the
+    // collected next table replaces the current one -- before this frame's own FIG 0/1 entries,
+    // which already describe the new configuration as the current one, are merged below.
+    const int first_lo = (st.tf_info.CIFCount_lo + 250 - 3) % 250;  // count of this frame's first CIF
+    if (st.occurrence >= 0 && ((st.occurrence - first_lo + 250) % 250) < 4) {
+      bool any = false;
+      for (int i = 0; i < 64; i++) any |= st.next_sub[i].id >= 0;
+      if (any) {
+        for (int i = 0; i < 64; i++) {
+          st.ens_info.subchans[i] = st.next_sub[i];
+          st.next_sub[i].id = st.next_sub[i].ASCTy = -1;
+        }
+        st.ens_version++;
+      }
+      st.occurrence = -1;
+      st.change_flags = 0;
+    }
+    for (int i = 0; i < 64; i++)
+      if (rcf.next_sub[i].id >= 0) st.next_sub[i] = rcf.next_sub[i];
+    if (rcf.change_flags && rcf.occurrence >= 0) {
+      st.change_flags = rcf.change_flags;
+      st.occurrence = rcf.occurrence;
+    }
+    st.newest_cif_lo = st.tf_info.CIFCount_lo;
+  }
   if (merge_and_diff(&st.ens_info, &st.tf_info)) st.ens_version++;
+  if (st.follow) {
+    // remember which table this transmission frame's CIFs were sent under; frames are emitted with the
+    // table of their own (oldest) CIF, i.e. of the oldest transmission frame of the window
+    BackendState::TableSnap &h = st.hist[(st.hist_head + (st.ncifs < 16 ? st.ncifs / 4 : 4)) % 5];
+    if (h.version != st.ens_version) {
+      h.version = st.ens_version;
+      memcpy(h.sub, st.ens_info.subchans, sizeof h.sub);
+    }
+  }
 
   if (st.ncifs < 16) {
     for (int k = 0; k < 4; k++) st.win[st.ncifs++] = slot * 4 + k;
@@ -177,6 +250,11 @@ void host_process_frame(BackendState &st, const uint8_t *fibs, const uint8_t *cr
       st.ens_info_shown = 1;
     }
     out->n_eti = 4;
+    if (st.follow) {  // the table of the oldest transmission frame of the window; its slot is reused in 4 frames
+      st.emit_version = st.hist[st.hist_head].version;
+      st.emit_sub = st.hist[st.hist_head].sub;
+      st.hist_head = (st.hist_head + 1) % 5;
+    }
     for (int k = 0; k < 4; k++) {
       memcpy(out->win[k], st.win, sizeof st.win);
       out->cif_hi[k] = st.ens_info.CIFCount_hi;

@@ -41,6 +41,24 @@ struct BackendState {
                     // reference's 5 (PHYS_TF_SLOTS) that the engine advances with every frame it
                     // stores, so that FIG parsing and MSC decoding can trail the front-end
   uint64_t ens_version;  // bumped whenever ens_info's sub-channel table changes
+  // ---- opt-in: follow multiplex reconfigurations the way EN 300 401 signals them (TODO.md:3; the
+  // reference merges every FIG 0/1 entry as it arrives, also those of the *next* configuration, and
+  // applies the table of the newest CIF to a frame that is 15-16 CIFs old).  With `follow`:
+  //   * FIG 0/1 entries with the C/N flag set describe the next configuration and are collected apart;
+  //   * FIG 0/0's change flags + occurrence change give the CIF count at which it becomes current: at
+  //     that CIF the current table is REPLACED by the collected one (sub-channels can disappear);
+  //   * an ETI frame is built with the table that was current for its own (oldest) CIF: the tables of
+  //     the 4 transmission frames of the window are kept (hist) and `emit_*` is the oldest one's.
+  bool follow = false;
+  subchannel_info_t next_sub[64];
+  int change_flags = 0, occurrence = -1, newest_cif_lo = -1;
+  struct TableSnap {
+    uint64_t version;
+    subchannel_info_t sub[64];
+  } hist[5];                 // ring by window position: hist[(hist_head + ncifs/4) % 5] is the incoming frame's table
+  int hist_head = 0;
+  uint64_t emit_version = 0; // version / table the frames emitted by the last host_process_frame use
+  const subchannel_info_t *emit_sub = nullptr;
   void reset();
 };
 

@@ -185,6 +185,7 @@ class StreamStatus(C.Structure):
 ENGINE_VERBOSE = 1
 ENGINE_VIRTUAL_TUNER = 2
 ENGINE_SOFT = 4
+ENGINE_FOLLOW_RECONFIG = 8
 
 
 class Engine:

@@ -111,10 +111,7 @@ def _fib(figs: bytes) -> bytes:
     return bytes(body) + bytes([crc >> 8, crc & 0xFF])
 
 
-def build_fibs(ens: Ensemble, cif_count: int) -> bytes:
-    """3 FIBs (96 bytes) for one CIF: FIG 0/0 + FIG 0/1 sub-channel organisation."""
-    hi, lo = (cif_count // 250) % 20, cif_count % 250
-    fig00 = bytes([0x05, 0x00, ens.eid >> 8, ens.eid & 0xFF, hi, lo])
+def _fig01_entries(ens: Ensemble):
     entries = []
     for s in ens.subchannels:
         b0, b1 = (s.id << 2) | (s.start_cu >> 8), s.start_cu & 0xFF
@@ -123,27 +120,82 @@ def build_fibs(ens: Ensemble, cif_count: int) -> bytes:
         else:
             opt, lvl = s.eep_level >> 2, s.eep_level & 3
             entries.append(bytes([b0, b1, 0x80 | (opt << 4) | (lvl << 2) | (s.size_cu >> 8), s.size_cu & 0xFF]))
-    fibs, cur, room = [], bytearray(fig00), 30 - len(fig00)
-    group = bytearray()
+    return entries
 
-    def flush_group():
-        nonlocal cur, group
+
+def build_fibs(ens: Ensemble, cif_count: int, next_ens: Optional[Ensemble] = None,
+               occurrence: Optional[int] = None) -> bytes:
+    """3 FIBs (96 bytes) for one CIF: FIG 0/0 + FIG 0/1 sub-channel organisation.  With `next_ens` /
+    `occurrence` the CIF also announces a multiplex reconfiguration the way EN 300 401 clause 6.4
+    does: change flags and occurrence change (lower CIF count at which it takes effect) in FIG 0/0,
+    and the next configuration's sub-channel organisation as FIG 0/1 with the C/N flag set."""
+    hi, lo = (cif_count // 250) % 20, cif_count % 250
+    if occurrence is None:
+        fig00 = bytes([0x05, 0x00, ens.eid >> 8, ens.eid & 0xFF, hi, lo])
+    else:
+        fig00 = bytes([0x06, 0x00, ens.eid >> 8, ens.eid & 0xFF, 0x40 | hi, lo, occurrence % 250])
+    groups = [(0x01, _fig01_entries(ens))]
+    if next_ens is not None:
+        groups.append((0x81, _fig01_entries(next_ens)))          # C/N = 1: next configuration
+    fibs, cur = [], bytearray(fig00)
+    for hdr, entries in groups:
+        group = bytearray()
+        for e in entries:
+            if len(cur) + 2 + len(group) + len(e) > 30:
+                if group:
+                    cur.extend(bytes([len(group) + 1, hdr]) + group)
+                    group = bytearray()
+                fibs.append(_fib(bytes(cur)))
+                cur = bytearray()
+            group.extend(e)
         if group:
-            cur.extend(bytes([len(group) + 1, 0x01]) + group)
-            group = bytearray()
-
-    for e in entries:
-        if len(cur) + 2 + len(group) + len(e) > 30:
-            flush_group()
-            fibs.append(_fib(bytes(cur)))
-            cur = bytearray()
-        group.extend(e)
-    flush_group()
+            if len(cur) + 2 + len(group) > 30:
+                fibs.append(_fib(bytes(cur)))
+                cur = bytearray()
+            cur.extend(bytes([len(group) + 1, hdr]) + group)
     fibs.append(_fib(bytes(cur)))
     while len(fibs) < 3:
         fibs.append(_fib(b""))
     assert len(fibs) == 3, "ensemble does not fit 3 FIBs"
     return b"".join(fibs)
+
+
+def generate_reconfiguration(ens_a: Ensemble, ens_b: Ensemble, n_streams: int, n_tf: int, switch_tf: int,
+                             seed: int = 0, announce_tfs: int = 6):
+    """Demapped transmission frames (bits, no IQ) of a multiplex that changes from `ens_a` to `ens_b` at the
+    first CIF of transmission frame `switch_tf`, signalled like a real one: for `announce_tfs` frames
+    before the change FIG 0/0 carries change flags + occurrence change and FIG 0/1 also lists the next
+    configuration (C/N = 1).  Logical frames before the change are coded with ens_a's layout, the
+    others with ens_b's; the time interleaver runs across the change (each logical frame's bits keep
+    their own positions).  Returns dict(bits [S][n_tf][230400], payload_a, payload_b, fibs, switch_cif)."""
+    ta, tb = ModeITransmitter(ens_a), ModeITransmitter(ens_b)
+    S, n_cif, N = n_streams, 4 * n_tf, 4 * switch_tf
+    rng = np.random.default_rng(0xDAB0000 + seed)
+    logical = torch.zeros((S, n_cif, 55296), dtype=torch.uint8)
+    payloads = []
+    for tx, ens, lo, hi in ((ta, ens_a, 0, N), (tb, ens_b, N, n_cif)):
+        pl = {}
+        for s in ens.subchannels:
+            p = torch.from_numpy(rng.integers(0, 256, (S, n_cif, s.nbytes), dtype=np.uint8))
+            pl[s.id] = p
+            coded = tx._code_block(p[:, lo:hi], s.id)
+            logical[:, lo:hi, s.start_cu * 64: s.start_cu * 64 + coded.shape[-1]] = coded
+        payloads.append(pl)
+    tx_bits = torch.zeros_like(logical)
+    for m in range(16):
+        dl = int(T.TDI_DELAY[m])
+        tx_bits[:, dl:, m::16] = logical[:, : n_cif - dl, m::16]
+    fib_rows = []
+    for c in range(n_cif):
+        if c < N:
+            ann = c >= N - 4 * announce_tfs
+            fib_rows.append(build_fibs(ens_a, c, ens_b if ann else None, N if ann else None))
+        else:
+            fib_rows.append(build_fibs(ens_b, c))
+    fibs = torch.from_numpy(np.frombuffer(b"".join(fib_rows), dtype=np.uint8).reshape(n_cif, 96).copy())
+    fic = ta._code_block(fibs, "fic").reshape(n_tf, 9216).unsqueeze(0).expand(S, n_tf, 9216)
+    bits = torch.cat([fic, tx_bits.reshape(S, n_tf, 4 * 55296)], dim=-1).contiguous()
+    return dict(bits=bits, payload_a=payloads[0], payload_b=payloads[1], fibs=fibs, switch_cif=N)
 
 
 # --------------------------------------------------------------------------------------

@@ -119,6 +119,15 @@ typedef struct dabgpu_engine dabgpu_engine;
  * metric table (dabgpu_viterbi_soft_batch).  process_demapped() of a soft engine takes such symbol
  * bytes (230400 per frame) instead of 0/1 bytes.  Worth about 2 dB at the decoder input. */
 #define DABGPU_ENGINE_SOFT 4
+/* Follow multiplex reconfigurations the way EN 300 401 signals them (opt-in; the reference's open TODO,
+ * TODO.md:3).  The reference -- and the default mode, bit-exact with it -- merges every FIG 0/1 entry
+ * into the sub-channel table as it arrives, including the entries that announce the NEXT configuration
+ * (C/N flag, sent for about six seconds before a change), never removes a sub-channel, and builds an
+ * ETI frame with the table of the newest CIF although the frame is 15-16 CIFs older.  With this flag
+ * the C/N flag, FIG 0/0's change flags and its occurrence-change field are honoured: the announced
+ * table replaces the current one at the signalled CIF, and every ETI frame is decoded and described
+ * (STC) with the table that was current for its own CIF. */
+#define DABGPU_ENGINE_FOLLOW_RECONFIG 8
 
 typedef struct {
   int32_t locked, okcount, ncifs, tfidx;          /* dab_state_t, dab.h:83-86 */

@@ -306,3 +306,63 @@ def test_wavefinder_packets_as_second_producer(gpu, port):
         got = np.array(out[s], dtype=np.uint8).reshape(-1, 6144)
         assert got.shape == want.shape and want.shape[0] >= 28, (s, got.shape, want.shape)
         assert np.array_equal(got, want), s
+
+
+@pytest.mark.parametrize("batch", [1, 4])
+def test_follow_signalled_reconfiguration(gpu, port, batch):
+    """SURVEY 8f-2, the part the reference does not have (TODO.md:3): DABGPU_ENGINE_FOLLOW_RECONFIG.
+    The multiplex announces a reconfiguration the way EN 300 401 does (FIG 0/0 change flags +
+    occurrence change, next configuration in FIG 0/1 with C/N = 1) six frames ahead; at the signalled
+    CIF one sub-channel moves and changes protection, one disappears and a new one appears.  A
+    following engine decodes EVERY logical frame -- also the 16 around the change, whose bits are
+    spread over CIFs of both configurations -- with the table that was current for that frame: payload
+    equal to what was transmitted, NST / STC of the right configuration.  The default engine (= the
+    reference: merges the announcement at once, never drops a sub-channel, applies the newest table to
+    15-CIF-old frames) garbles the frames around the change, which is what the mode is for."""
+    A = synth.small_ensemble()
+    B = synth.Ensemble([synth.SubChannel(id=3, start_cu=0, uep_index=35),
+                        synth.SubChannel(id=7, start_cu=250, eep_level=1, size_cu=64),
+                        synth.SubChannel(id=20, start_cu=400, uep_index=16)])
+    S, n_tf, sw = 2, 34, 22
+    g = synth.generate_reconfiguration(A, B, S, n_tf, sw, seed=3)
+    bits = g["bits"].numpy()
+    N = g["switch_cif"]
+
+    def run(flags):
+        eng = gpu.Engine(S, 200_000_000, flags)
+        eng.set_msc_batch(batch)
+        out = [[] for _ in range(S)]
+        for t in range(n_tf + 1):
+            n = eng.process_demapped(bits[:, t]) if t < n_tf else eng.flush()
+            eti, ids = eng.fetch_eti()
+            for f, s in zip(eti, ids):
+                out[s].append(f.copy())
+        eng.close()
+        return [np.array(o, dtype=np.uint8).reshape(-1, 6144) for o in out]
+
+    def check(frames, s):
+        """-> (frames whose header and payload are right for their own CIF, total)"""
+        good = 0
+        for f in frames:
+            cif = (int(f[4]) - 3) % 250                         # FCT leads the content by 3 (SURVEY 8a)
+            ens, pl = (A, g["payload_a"]) if cif < N else (B, g["payload_b"])
+            nst = int(f[5] & 0x7F)
+            ids = [int(f[8 + 4 * i] >> 2) for i in range(nst)]
+            off = 12 + 4 * nst + 96
+            want = synth.expected_eti_payload(ens, pl, s, cif)
+            ok = ids == [sc.id for sc in ens.subchannels] and f[off: off + len(want)].tobytes() == want
+            good += ok
+        return good, frames.shape[0]
+
+    got = run(gpu.ENGINE_FOLLOW_RECONFIG)
+    for s in range(S):
+        good, total = check(got[s], s)
+        assert total == 4 * (n_tf - 13) and good == total, (s, good, total)
+        assert not gpu.eti_check(got[s]).any()
+        cifs = [(int(f[4]) - 3) % 250 for f in got[s]]
+        assert min(cifs) < N - 16 and max(cifs) > N + 16        # frames on both sides and across the change
+    ref_like = run(0)
+    want = port.run_backend(bits[0])[0]
+    assert np.array_equal(ref_like[0], want)                    # default mode: still the reference, byte for byte
+    good, total = check(ref_like[0], 0)
+    assert good < total - 16                                    # ... which loses the frames around the change
