@@ -119,3 +119,24 @@ def test_engine_consumers_work_where_the_frames_lie(gpu, port):
         seen += n
     eng.close()
     assert seen >= 4 * S * 3
+
+
+def test_empty_and_degenerate_inputs(gpu, tmp_path):
+    """empty batches, a source that ends before its first callback, frames without packets: no frames, no error"""
+    import os
+    assert gpu.eti_check(np.zeros((0, 6144), np.uint8)).size == 0
+    assert gpu.viterbi_soft_batch(np.zeros((0, 4 * 774), np.uint8), 768).shape == (0, 96)
+    garbage = np.full((3, 6144), 0xA5, np.uint8)                      # not ETI at all: flagged, nothing extracted
+    assert (gpu.eti_check(garbage) & gpu.ETI_BAD_SYNC).all()
+    data, lens = gpu.eti_extract_subchannel(garbage, 5)
+    assert (lens == -1).all() and not data.any()
+    eng = gpu.Engine(2)
+    short = tmp_path / "short.iq"
+    np.zeros(1000, np.uint8).tofile(short)
+    fds = [os.open(short, os.O_RDONLY) for _ in range(2)]
+    assert eng.pump(fds, None) == 0
+    for fd in fds:
+        os.close(fd)
+    assert eng.process_wavefinder(np.zeros((2, 524), np.uint8), np.zeros(2, np.int32)) == 0
+    assert eng.extract_subchannel(3)[1].size == 0 and eng.check_eti().size == 0
+    eng.close()
