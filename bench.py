@@ -679,6 +679,32 @@ def run_ours(args, rank, world, local_rank):
                                                   for q in range(4)]
         del fic_bits, fibs, okf
 
+    # ---------------- opt-in soft-decision mode: same call path, a short pass ----------------
+    soft_cfg = None
+    if rank == 0 and not args.no_soft:
+        eng = lib.Engine(S, 200_000_000, lib.ENGINE_SOFT)
+        eng.set_msc_batch(args.msc_batch)
+        for c in range(setup_calls + 6):
+            eng.feed_iq_device(chunk(c))
+        eng.flush()
+        eng.join()
+        torch.cuda.synchronize()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        n_soft = 0
+        for c in range(setup_calls + 6, setup_calls + 6 + 8 * CALLS_PER_2TF):
+            n_soft += eng.feed_iq_device(chunk(c))
+        n_soft += eng.flush()
+        eng.join()
+        s1.record()
+        torch.cuda.synchronize()
+        soft_cfg = {"value": n_soft / (s0.elapsed_time(s1) * 1e-3), "unit": "frames/s", "frames": n_soft,
+                    "locked_streams": sum(eng.status(s).locked for s in range(S)),
+                    "note": "DABGPU_ENGINE_SOFT (soft demapper, symbol data path, 16-bit-metric Viterbi), copying "
+                            "feed_iq path, 16 TF per stream; not the headline configuration"}
+        eng.close()
+        del eng
+
     # ---------------- BASELINE config 3 parity on this very dataset ----------------
     parity = None
     if rank == 0 and not args.no_parity:
@@ -772,6 +798,7 @@ def run_ours(args, rank, world, local_rank):
             "ncu": vit_ncu,   # ALU-pipe / issue-slot utilisation: hardware counters of the committed capture
         },
         "fic_only": fic_cfg,
+        "soft_mode": soft_cfg,
         "parity": parity,
         "host_ms_per_2tf": {k: (host_t[k] - host_t0[k]) / 1e3 / (K * TFS / 2) for k in host_t},
         "kernel_ms_per_launch": {k: (v["ms"] / v["launches"] if v["launches"] else None) for k, v in kt.items()},
@@ -848,6 +875,7 @@ def main():
     ap.add_argument("--parity-streams", type=int, default=8)
     ap.add_argument("--no-parity", action="store_true")
     ap.add_argument("--no-spiral", action="store_true")
+    ap.add_argument("--no-soft", action="store_true", help="skip the short pass in the opt-in soft-decision mode")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
