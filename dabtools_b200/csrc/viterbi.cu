@@ -31,7 +31,9 @@
 // Branch distances: generators 0 and 3 are equal, so only the 4 symbol classes {c, ~c} occur, and
 // over the 8 register pairs of a step only 8 distinct 4-byte distance patterns do.  A shared-memory
 // table indexed by the step byte delivers all 8 with two 128-bit loads per step and layout.
-// 112 SASS instructions per 64-state step (1.75 per add-compare-select).
+// 123 SASS instructions per 64-state step, 66 of them on the half-rate ALU pipe (LOP3, PRMT, IADD3)
+// and the rest on the FMA pipe (IMAD): the ALU pipe is what bounds the kernel, so work is placed on
+// the FMA pipe where that is possible even at the price of an instruction (pair_acs).
 #include "viterbi.cuh"
 
 #include <algorithm>
@@ -127,8 +129,13 @@ __host__ __device__ constexpr uint32_t cx_dec_mask(int k) {
 struct Metrics {
   uint32_t r[16];
 };
+#ifndef DABGPU_VIT_COMPARE
+#define DABGPU_VIT_COMPARE 1
+#endif
+__constant__ uint32_t c_two = 2;
 struct Patterns {
   uint32_t p[8];
+  uint32_t ks, two;  // (0x7f - e) in every byte; 2
 };
 
 // add-compare-select of register pair K: E = successors 2p, O = successors 2p+1
@@ -141,11 +148,24 @@ __device__ __forceinline__ void pair_acs(const Metrics &m, const Patterns &P, ui
   const uint32_t X = P.p[ix], Y = P.p[iy];       // distance of p -> 2p, and its complement
   const uint32_t a0 = A + X, b0 = B + Y;         // into even state: via p / via p+32
   const uint32_t a1 = A + Y, b1 = B + X;         // into odd state
+#if DABGPU_VIT_COMPARE == 1
+  // bit 7 of a byte of t = (a > b), a, b < 128.  a0 - b0 = (A - B) + (X - Y) and X + Y = e (the
+  // number of transmitted symbols of the step), so with D = A - B + 0x7f - e (one three-input add on
+  // the half-rate ALU pipe, shared by both compares, independent of a0 .. b1) the compares are
+  // t0 = 2 X + D and t1 = 2 Y + D: multiply-adds, which run on the FMA pipe (c_two is a run-time 2
+  // so that ptxas cannot turn them back into LEA / IADD3).  |A - B| <= 72 at any time, so no byte of
+  // D or t borrows or overflows.
+  const uint32_t D = A + P.ks - B;
+  const uint32_t t0 = X * P.two + D;
+  const uint32_t t1 = Y * P.two + D;
+#else
   const uint32_t t0 = a0 + 0x7f7f7f7fu - b0;
   const uint32_t t1 = a1 + 0x7f7f7f7fu - b1;
-  // Measured on B200, both slower or within 2 %: (1) mask/record on the FMA pipe (f = umulhi(t &
-  // 0x80808080, 1 << 25), m = f * 255, dec = f * 2^k + dec): -10 %; (2) the compare on the FMA pipe
-  // (t = b * -1 + (a * 1 + K) with run-time factors so that ptxas cannot fold them back into IADD3).
+#endif
+  // Measured on B200 (tools/demod_time.py, S = 1024, MSC batch of 2): t = a + 0x7f7f7f7f - b as two
+  // IADD3 1.198 ms per launch, the form above 1.165 ms.  Slower or within 2 %: (1) mask/record on the
+  // FMA pipe (f = umulhi(t & 0x80808080, 1 << 25), m = f * 255, dec = f * 2^k + dec): -10 %; (2) the
+  // compare as t = b * -1 + (a * 1 + K) with run-time factors (two dependent multiply-adds per compare).
   const uint32_t m0 = prmt(t0, 0u, 0xba98u);
   const uint32_t m1 = prmt(t1, 0u, 0xba98u);
   decE |= m0 & C;
@@ -228,6 +248,9 @@ __device__ __forceinline__ Patterns lut_get(const VitLut &L, uint32_t sb) {
   Patterns P;
   P.p[0] = a.x, P.p[1] = a.y, P.p[2] = a.z, P.p[3] = a.w;
   P.p[4] = b.x, P.p[5] = b.y, P.p[6] = b.z, P.p[7] = b.w;
+  // patterns 2 K and 2 K + 1 of a pair are complements: their sum is e in every byte
+  P.ks = 0x7f7f7f7fu - P.p[cx_slot(PH, 0)] - P.p[cx_slot(PH, 1)];
+  P.two = c_two;
   return P;
 }
 
