@@ -19,6 +19,7 @@ namespace dabgpu {
 
 // ---- constant tables ---------------------------------------------------------------------------
 __device__ float2 g_tw2048[2048];    // exp(-2*pi*i*k/2048)
+__device__ float2 g_tw1536[1536];    // exp(-2*pi*i*k/1536)
 __device__ uint16_t g_bin_dst[2048]; // FFT bin -> n = rev_freq_deint_tab[c] (0xffff: unused bin)
 __device__ uint8_t g_prs_q[1536];    // phase reference symbol, quarter turns, by carrier index c
 
@@ -29,6 +30,11 @@ int ofdm_init_constants() {
     tw[k] = make_float2((float)cos(a), (float)sin(a));
   }
   CUDA_TRY(cudaMemcpyToSymbol(g_tw2048, tw, sizeof tw));
+  for (int k = 0; k < 1536; k++) {
+    const double a = -2.0 * M_PI * (double)k / 1536.0;
+    tw[k] = make_float2((float)cos(a), (float)sin(a));
+  }
+  CUDA_TRY(cudaMemcpyToSymbol(g_tw1536, tw, 1536 * sizeof(float2)));
   uint16_t rev[1536];
   static uint16_t dst[2048];
   dabgpu_build_freq_deint(rev);
@@ -918,60 +924,100 @@ int launch_demod_debug(const uint8_t *d_frame, float2 *d_symbols, float2 *d_symb
 // =================================================================================================
 // synchronisers: one CTA of 128 threads per stream
 // =================================================================================================
-// `batch` independent in-place radix-2 FFTs of n = 2^logn points, stored back to back in shared
-// memory, by the whole CTA; sign = -1 forward, +1 backward; unnormalised
-__device__ void block_fft_pow2(float2 *d, int logn, int sign, int batch) {
-  const int n = 1 << logn;
-  for (int i = threadIdx.x; i < batch * n; i += blockDim.x) {
-    const int base = i & ~(n - 1), ii = i & (n - 1);
-    const int j = (int)(__brev((unsigned)ii) >> (32 - logn));
-    if (ii < j) {
-      const float2 t = d[base + ii];
-      d[base + ii] = d[base + j];
-      d[base + j] = t;
-    }
+// Three forward 512-point FFTs (transform r at d + FFT512_PITCH * r, natural order in and out, in
+// place) by the whole CTA, in registers: 512 = 8 x 8 x 8, decimation in frequency, 64 "virtual
+// threads" of 8 points per transform, so 192 of them over 128 threads (vt = p and p + 128).
+//   stage 1: vt (r, t):          DFT8 over y[t + 64 j]               -> k1, twiddle W512^(t k1)
+//   stage 2: vt (r, k1, u):      DFT8 over z_k1[u + 8 j2]            -> k2, twiddle W64^(u k2)
+//   stage 3: vt (r, q = k1 + 8 k2): DFT8 over u                      -> bin q + 64 k3
+// Every stage reads all its inputs, then (barrier) writes its outputs into the same region; the row
+// pitches 72 and 66 make the 64-bit accesses of both sides of each exchange conflict-free.
+enum { FFT512_PITCH = 576 };
+__device__ void block_fft512x3(float2 *d) {
+  const int p = threadIdx.x;
+  const bool two = p < 64;  // threads 0..63 also run virtual threads 128..191 (transform 2)
+  float2 *d0 = d + FFT512_PITCH * (p >> 6), *d1 = d + FFT512_PITCH * 2;
+  const int t = p & 63;
+  float2 a[8], b[8];
+  // stage 1
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = d0[t + 64 * j];
+    if (two) b[j] = d1[t + 64 * j];
   }
   __syncthreads();
-  for (int len = 2; len <= n; len <<= 1) {
-    const int half = len >> 1;
-    for (int bb = threadIdx.x; bb < batch * (n / 2); bb += blockDim.x) {
-      const int base = (bb >> (logn - 1)) << logn, b = bb & (n / 2 - 1);
-      const int k = b & (half - 1);
-      const int i0 = base + ((b - k) << 1) + k, i1 = i0 + half;
-      float2 w = g_tw2048[(k * (2048 / len)) & 2047];
-      if (sign > 0) w.y = -w.y;
-      const float2 x = d[i0], y = cmul(d[i1], w);
-      d[i0] = cadd(x, y);
-      d[i1] = csub(x, y);
-    }
-    __syncthreads();
+  dft8(a);
+  if (two) dft8(b);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float2 w = g_tw2048[4 * t * k];
+    d0[k * 72 + t] = k ? cmul(a[k], w) : a[k];
+    if (two) d1[k * 72 + t] = k ? cmul(b[k], w) : b[k];
   }
+  __syncthreads();
+  // stage 2
+  const int k1 = t >> 3, u = t & 7;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = d0[k1 * 72 + u + 8 * j];
+    if (two) b[j] = d1[k1 * 72 + u + 8 * j];
+  }
+  __syncthreads();
+  dft8(a);
+  if (two) dft8(b);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    const float2 w = g_tw2048[32 * u * k];
+    d0[u * 66 + k1 + 8 * k] = k ? cmul(a[k], w) : a[k];
+    if (two) d1[u * 66 + k1 + 8 * k] = k ? cmul(b[k], w) : b[k];
+  }
+  __syncthreads();
+  // stage 3
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = d0[j * 66 + t];
+    if (two) b[j] = d1[j * 66 + t];
+  }
+  __syncthreads();
+  dft8(a);
+  if (two) dft8(b);
+#pragma unroll
+  for (int k = 0; k < 8; k++) {
+    d0[t + 64 * k] = a[k];
+    if (two) d1[t + 64 * k] = b[k];
+  }
+  __syncthreads();
 }
 
-// in-place 128-point backward FFT of shared-memory data by ONE warp (no CTA barriers)
-__device__ void warp_ifft128(float2 *d, int lane) {
-  for (int i = lane; i < 128; i += 32) {
-    const int j = (int)(__brev((unsigned)i) >> 25);
-    if (i < j) {
-      const float2 t = d[i];
-      d[i] = d[j];
-      d[j] = t;
-    }
+// Largest magnitude of the 128-point DFT of x[l + 8 j] (j = 0..15 in v) by a group of 8 consecutive
+// lanes l, in registers: 128 = 16 x 8, decimation in frequency with one exchange through `buf` (136
+// float2 per group, groups of a warp 136 apart: conflict-free on both sides).  Warp-synchronous.
+__device__ __forceinline__ float group8_fft128_peak(float2 *v, float2 *buf, int l) {
+  dft16(v);
+#pragma unroll
+  for (int n1 = 0; n1 < 16; n1++) {
+    const float2 w = g_tw2048[16 * l * n1];
+    buf[(n1 >> 1) * 17 + (n1 & 1) * 8 + l] = n1 ? cmul(v[n1], w) : v[n1];
   }
   __syncwarp();
-  for (int len = 2; len <= 128; len <<= 1) {
-    const int half = len >> 1;
-    for (int b = lane; b < 64; b += 32) {
-      const int k = b & (half - 1);
-      const int i0 = ((b - k) << 1) + k, i1 = i0 + half;
-      float2 w = g_tw2048[(k * (2048 / len)) & 2047];
-      w.y = -w.y;
-      const float2 x = d[i0], y = cmul(d[i1], w);
-      d[i0] = cadd(x, y);
-      d[i1] = csub(x, y);
-    }
-    __syncwarp();
+  float2 a[8], b[8];
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    a[j] = buf[l * 17 + j];
+    b[j] = buf[l * 17 + 8 + j];
   }
+  __syncwarp();
+  dft8(a);
+  dft8(b);
+  float m = 0.f;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    m = fmaxf(m, a[j].x * a[j].x + a[j].y * a[j].y);
+    m = fmaxf(m, b[j].x * b[j].x + b[j].y * b[j].y);
+  }
+#pragma unroll
+  for (int o = 4; o; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  return sqrtf(m);  // sqrt is monotonic: the largest magnitude is the root of the largest square
 }
 
 #ifndef SYNC_CTAS_PER_SM
@@ -985,7 +1031,7 @@ __device__ __forceinline__ int spec_slot(int bin) {
 struct SyncSmem {
   union {              // never live at the same time:
     float2 xch[XCH_ELEMS];  // FFT exchange buffer (inside fft_window)
-    float2 work[1536];      // correlation buffers (between the FFTs)
+    float2 work[16 * 136];  // correlation buffers (between the FFTs): 3 x FFT512_PITCH or 16 groups x 136
   };
   // FFT output by bin, without the bins nobody reads: the carriers are bins 1..768 and 1280..2047
   // (fine time sync reads 3..770 and 1280..2047, the coarse frequency search 1280..1435)
@@ -1115,25 +1161,25 @@ __device__ void fft_window(SyncSmem &sm, const Src &src, int start, const Tw &tw
 }
 
 // sdr_sync.c:71-202 on the PRS spectrum in sm.spec: correlate 1536 carriers with conj(PRS),
-// 1536-point inverse DFT (3 x 512 + radix-3 combine), first maximum of the magnitude.
+// 1536-point inverse DFT, first maximum of the magnitude.  Only magnitudes are used, and
+// |IDFT(c)| = |DFT(conj c)|: the forward transform of conj(c) = conj(spec) * PRS is computed, as
+// three 512-point transforms of the samples i = 3 q + r and a radix-3 combine.
 __device__ int fine_time_from_spec(SyncSmem &sm) {
   const int p = threadIdx.x;
   for (int i = p; i < 1536; i += FFT_THREADS) {
     const int bin = i < 768 ? i + 1280 : i - 765;  // sic: off by two in the upper half
-    sm.work[(i % 3) * 512 + i / 3] = cmulc(sm.spec[spec_slot(bin)], prs_value(i));
+    const float2 c = cmulc(sm.spec[spec_slot(bin)], prs_value(i));
+    sm.work[(i % 3) * FFT512_PITCH + i / 3] = make_float2(c.x, -c.y);
   }
   __syncthreads();
-  block_fft_pow2(sm.work, 9, +1, 3);
+  block_fft512x3(sm.work);
   float best = -99999.f;
   int best_i = 0x7fffffff;
   for (int k = p; k < 1536; k += FFT_THREADS) {
     const int km = k & 511;
-    float sn, cs;
     float2 acc = sm.work[km];
-    sincospif(2.0f * (float)k / 1536.0f, &sn, &cs);
-    acc = cadd(acc, cmul(sm.work[512 + km], make_float2(cs, sn)));
-    sincospif(2.0f * (float)((2 * k) % 1536) / 1536.0f, &sn, &cs);
-    acc = cadd(acc, cmul(sm.work[1024 + km], make_float2(cs, sn)));
+    acc = cadd(acc, cmul(sm.work[FFT512_PITCH + km], g_tw1536[k]));
+    acc = cadd(acc, cmul(sm.work[2 * FFT512_PITCH + km], g_tw1536[2 * k < 1536 ? 2 * k : 2 * k - 1536]));
     const float mag = sqrtf(acc.x * acc.x + acc.y * acc.y);
     if (mag > best) {  // ascending k per thread: the first maximum is kept
       best = mag;
@@ -1147,28 +1193,31 @@ __device__ int fine_time_from_spec(SyncSmem &sm) {
 }
 
 // sdr_sync.c:205-258 on the spectrum in sm.spec (natural order; the reference's fftshifted
-// index i is bin (i + 1024) mod 2048).  The 29 hypotheses are independent: each warp takes every
-// fourth one and runs its 128-point inverse FFT on its own; the reference keeps the first k whose
-// peak is strictly larger, i.e. the largest peak with the smallest k on ties.
+// index i is bin (i + 1024) mod 2048).  The 29 hypotheses are independent: a group of 8 lanes takes
+// one (16 at a time), holds its 128 correlation products in registers and only needs the largest
+// magnitude of their inverse DFT, which is that of the forward DFT of the conjugates.  The reference
+// keeps the first k whose peak is strictly larger, i.e. the largest peak with the smallest k on ties.
 __device__ int coarse_freq_from_spec(SyncSmem &sm) {
-  const int p = threadIdx.x, lane = p & 31, warp = p >> 5;
-  float2 *buf = sm.work + 128 * warp;
+  const int p = threadIdx.x, l = p & 7, g = p >> 3;
+  float2 *buf = sm.work + 136 * g;
   float best = -99999.f;
   int best_k = 99;
-  for (int k = -14 + warp; k <= 14; k += 4) {
-    for (int s = lane; s < 128; s += 32)
-      buf[s] = cmulc(sm.spec[spec_slot((14 + k + 256 + s + 1024) & 2047)], prs_value(14 + s));
-    __syncwarp();
-    warp_ifft128(buf, lane);
-    float mag = -99999.f;
-    for (int s = lane; s < 128; s += 32) mag = fmaxf(mag, sqrtf(buf[s].x * buf[s].x + buf[s].y * buf[s].y));
+  for (int round = 0; round < 2; round++) {  // a group's hypotheses in ascending order; all lanes take
+    const int kk = -14 + g + 16 * round;     // part in both rounds (warp-wide exchange and shuffles)
+    const bool valid = kk <= 14;
+    const int k = valid ? kk : 14;
+    float2 v[16];
 #pragma unroll
-    for (int o = 16; o; o >>= 1) mag = fmaxf(mag, __shfl_xor_sync(0xffffffffu, mag, o));
-    if (mag > best) {  // ascending k within the warp
+    for (int j = 0; j < 16; j++) {
+      const int s = l + 8 * j;
+      const float2 c = cmulc(sm.spec[spec_slot((14 + k + 256 + s + 1024) & 2047)], prs_value(14 + s));
+      v[j] = make_float2(c.x, -c.y);
+    }
+    const float mag = group8_fft128_peak(v, buf, l);
+    if (valid && mag > best) {
       best = mag;
       best_k = k;
     }
-    __syncwarp();
   }
   float bv;
   int bi;
