@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(256) msc_gather_periods_kernel(const uint8_t *
   __shared__ uint32_t pl[16][CIF_PLANE_WORDS];
   __shared__ uint32_t lin[CIF_WORDS + 1];
   __shared__ CifJob job;
-  __shared__ DepTab dep[64];
+  __shared__ __align__(16) DepTab dep[64];
   if (threadIdx.x < sizeof(CifJob) / 4)
     reinterpret_cast<uint32_t *>(&job)[threadIdx.x] = reinterpret_cast<const uint32_t *>(&jobs[blockIdx.x])[threadIdx.x];
   for (uint32_t i = threadIdx.x; i < sizeof(dep) / 4; i += blockDim.x)
@@ -281,24 +281,37 @@ __global__ void __launch_bounds__(256) msc_gather_periods_kernel(const uint8_t *
   deinterleave_to_smem(cifs, job, pl, lin);
   const uint2 *pd = reinterpret_cast<const uint2 *>(periods) + job.per0;
   uint2 *dst = reinterpret_cast<uint2 *>(steps + job.row_base);
-  for (uint32_t p = threadIdx.x; p < job.nper; p += blockDim.x) {
-    const uint2 d = __ldg(pd + p);
-    const uint32_t idx = d.x >> 16, in = d.x & 0xffffu;
-    uint2 packed = make_uint2(0u, 0u);
-    if (idx != 0xffu) {
-      const DepTab &t = dep[idx];
-      const uint32_t wi = in >> 5;
+  static_assert(sizeof(DepTab) == 80, "five 16-byte vectors per deposit table");
+  const uint4 *dq = reinterpret_cast<const uint4 *>(dep);
+  const uint32_t nper = job.nper;
+  // Branch-free: always eight deposit terms (unused ones have mask 0), and a padding period (table
+  // index 0xff) takes row 63, which is all zero, so it stores 0 whatever it read.
+  // four periods per thread and pass, descriptors fetched ahead of their use
+  for (uint32_t p0 = threadIdx.x; p0 < nper; p0 += 4 * blockDim.x) {
+    uint2 d[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t p = p0 + u * blockDim.x;
+      d[u] = p < nper ? __ldg(pd + p) : make_uint2(0xffu << 16, 0xffffffffu);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      if (d[u].y == 0xffffffffu) break;
+      const uint32_t idx = min(d[u].x >> 16, 63u), in = d[u].x & 0xffffu;
+      const uint32_t wi = min(in >> 5, (uint32_t)CIF_WORDS - 1u);
       // up to 32 consecutive channel bits starting at bit `in`
-      const uint32_t x = wi < CIF_WORDS ? __funnelshift_r(lin[wi], lin[wi + 1], in & 31u) : 0u;
-      uint32_t rn = 0;  // received bits as one nibble per step
-      for (uint32_t k = 0; k < t.n_terms; k++) rn |= (x << t.shift[k]) & t.mask[k];
+      const uint32_t x = __funnelshift_r(lin[wi], lin[wi + 1], in & 31u);
+      const uint4 hd = dq[5 * idx], s0 = dq[5 * idx + 1], s1 = dq[5 * idx + 2], m0 = dq[5 * idx + 3],
+                  m1 = dq[5 * idx + 4];
+      // received bits as one nibble per step
+      const uint32_t rn = ((x << s0.x) & m0.x) | ((x << s0.y) & m0.y) | ((x << s0.z) & m0.z) |
+                          ((x << s0.w) & m0.w) | ((x << s1.x) & m1.x) | ((x << s1.y) & m1.y) |
+                          ((x << s1.z) & m1.z) | ((x << s1.w) & m1.w);
       uint32_t lo = rn & 0xffffu, hi = rn >> 16;
       lo = (lo | (lo << 8)) & 0x00ff00ffu;
       hi = (hi | (hi << 8)) & 0x00ff00ffu;
-      packed.x = ((lo | (lo << 4)) & 0x0f0f0f0fu) | t.e_lo;
-      packed.y = ((hi | (hi << 4)) & 0x0f0f0f0fu) | t.e_hi;
+      dst[d[u].y] = make_uint2(((lo | (lo << 4)) & 0x0f0f0f0fu) | hd.y, ((hi | (hi << 4)) & 0x0f0f0f0fu) | hd.z);
     }
-    dst[d.y] = packed;
   }
 }
 
