@@ -37,16 +37,18 @@ __host__ __device__ static inline uint64_t vit_group_dec_words(uint32_t nsteps) 
 __host__ __device__ static inline uint32_t vit_row_bytes(uint32_t nsteps) { return (nsteps + 15u) & ~15u; }
 
 // Persistent launch shape: VIT_CTAS_PER_SM CTAs of VIT_WARPS warps on every SM, each warp with its
-// own work list.  Measured on B200 (1024 streams, whole receive step / MSC launch alone):
-//   1 x 16 warps (whole register file)  2.58 ms / 1.18 ms      3 x 4 warps  2.50 ms / 1.21 ms
-//   1 x  8 warps                        2.54 ms / 1.26 ms      2 x 4 warps  2.71 ms / 1.40 ms
-// Twelve warps in three small CTAs leave a quarter of the registers to the demodulator's CTAs of
-// the next frames, whose FP32 work then shares the SM with the decoder's integer work.
+// own work list.  Measured on B200 (1024 streams, ETI frames/s of the whole receiver, bench.py):
+//   1 x  8 warps  3.98 M      3 x 4 warps  3.94 M      1 x 12 / 1 x 16 warps  3.82 M
+//   2 x  8 warps  3.78 M      2 x 4 warps  3.50 M (nothing stops three of its CTAs from landing on one SM)
+// Two warps per scheduler are enough to keep the integer pipe busy, and one 8-warp CTA (35 K
+// registers) leaves room for a demodulator CTA of the following frames (21.5 K) on every SM, whose
+// FP32 and shared-memory work then runs beside the decoder's integer work.  (With round 1's
+// 128-register demodulator the best shape was 3 x 4.)
 #ifndef DABGPU_VIT_WARPS
-#define DABGPU_VIT_WARPS 4
+#define DABGPU_VIT_WARPS 8
 #endif
 #ifndef DABGPU_VIT_CTAS_PER_SM
-#define DABGPU_VIT_CTAS_PER_SM 3
+#define DABGPU_VIT_CTAS_PER_SM 1
 #endif
 enum { VIT_WARPS = DABGPU_VIT_WARPS, VIT_CTAS_PER_SM = DABGPU_VIT_CTAS_PER_SM };
 int device_sm_count();
