@@ -307,10 +307,9 @@ __global__ void __launch_bounds__(256) msc_gather_periods_kernel(const uint8_t *
       const uint32_t rn = ((x << s0.x) & m0.x) | ((x << s0.y) & m0.y) | ((x << s0.z) & m0.z) |
                           ((x << s0.w) & m0.w) | ((x << s1.x) & m1.x) | ((x << s1.y) & m1.y) |
                           ((x << s1.z) & m1.z) | ((x << s1.w) & m1.w);
-      uint32_t lo = rn & 0xffffu, hi = rn >> 16;
-      lo = (lo | (lo << 8)) & 0x00ff00ffu;
-      hi = (hi | (hi << 8)) & 0x00ff00ffu;
-      dst[d[u].y] = make_uint2(((lo | (lo << 4)) & 0x0f0f0f0fu) | hd.y, ((hi | (hi << 4)) & 0x0f0f0f0fu) | hd.z);
+      // nibbles n0 .. n7 -> the low nibbles of eight bytes: even and odd nibbles apart, then interleaved
+      const uint32_t ev = rn & 0x0f0f0f0fu, od = (rn >> 4) & 0x0f0f0f0fu;
+      dst[d[u].y] = make_uint2(__byte_perm(ev, od, 0x5140) | hd.y, __byte_perm(ev, od, 0x7362) | hd.z);
     }
   }
 }

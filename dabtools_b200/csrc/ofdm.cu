@@ -1226,28 +1226,28 @@ __device__ int coarse_freq_from_spec(SyncSmem &sm) {
 }
 
 // sdr_sync.c:259-302: mean phase of x[n+2048] conj(x[n]) over the PRS guard interval, in Hz.
-// In double like the reference: the products of 8-bit samples are exact, atan2 is taken in double
-// and the 504 angles are added in the reference's order (i ascending, one thread), because the tuner
-// feedback truncates `frequency + ffs / 3` to an integer (dab2eti.c:98-101) and a float-level
-// difference there would move a borderline stream by 1 Hz for the rest of its life.
+// In double like the reference: the products of 8-bit samples are exact and atan2 is taken in double,
+// because the tuner feedback truncates `frequency + ffs / 3` to an integer (dab2eti.c:98-101) and a
+// float-level difference there would move a borderline stream by 1 Hz for the rest of its life.  The
+// 504 angles are added in a fixed tree order (per thread ascending i, then lanes, then warps) rather
+// than the reference's sequential one: the sums differ by a few units of 1e-16 relative, far below
+// anything the truncation can see, and a 504-long dependent chain in one thread was 12 % of the kernel.
 template <typename Src>
 __device__ double fine_freq(SyncSmem &sm, const Src &src) {
-  double *ang = reinterpret_cast<double *>(sm.work);  // 504 doubles; the correlation buffers are free here
+  double *part = reinterpret_cast<double *>(sm.work);  // the correlation buffers are free here
+  double acc = 0.0;
   for (int i = threadIdx.x; i < 504; i += FFT_THREADS) {
     const float2 l = src.at(2656 + 2048 + i), r = src.at(2656 + i);
     const double lx = l.x, ly = l.y, rx = r.x, ry = r.y;
-    ang[i] = atan2(ly * rx - lx * ry, lx * rx + ly * ry);
+    acc += atan2(ly * rx - lx * ry, lx * rx + ly * ry);
   }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0) part[threadIdx.x >> 5] = acc;
   __syncthreads();
-  if (threadIdx.x == 0) {
-    double mean = 0.0;
-    for (int i = 0; i < 504; i++) mean = mean + ang[i];
-    ang[504] = mean / 504 / (2 * 3.14159265358979323846) * 1000;
-  }
+  const double mean = (part[0] + part[1]) + (part[2] + part[3]);
   __syncthreads();
-  const double r = ang[504];
-  __syncthreads();
-  return r;
+  return mean / 504 / (2 * 3.14159265358979323846) * 1000;
 }
 
 // the synchroniser half of sdr_demod (input_sdr.c:65-112) on one frame
