@@ -36,6 +36,21 @@ def test_viterbi_batch_matches_oracle(gpu, port, nbits, p_flip, p_erase):
         assert np.array_equal(got_s, np.stack([port.descramble(w) for w in want]))
 
 
+def test_viterbi_batch_persistent_launch_with_ragged_tail(gpu, port):
+    """Enough codewords for the persistent launch shape (one 8-warp CTA per SM, static work lists:
+    VitBatch::plan needs >= 8 groups per SM) with a last group of 13 lanes: every codeword must still
+    come out as the oracle decodes it, whichever warp's list it landed in."""
+    nbits, uniq = 768, 1300
+    rng = np.random.default_rng(99)
+    soft_u, _ = _soft_batch(port, rng, uniq, nbits, 0.06, 0.3)
+    want_u = np.stack([port.viterbi(soft_u[i], nbits) for i in range(uniq)])
+    n = 32 * 1200 + 13
+    idx = rng.permutation(n) % uniq
+    got = gpu.viterbi_batch(np.ascontiguousarray(soft_u[idx]), nbits)
+    assert got.shape == (n, nbits // 8)
+    assert np.array_equal(got, want_u[idx])
+
+
 def test_viterbi_adversarial(gpu, port):
     nbits = 768
     n = 4 * (nbits + 6)
