@@ -166,6 +166,9 @@ __device__ __forceinline__ void pair_acs(const Metrics &m, const Patterns &P, ui
   // IADD3 1.198 ms per launch, the form above 1.165 ms.  Slower or within 2 %: (1) mask/record on the
   // FMA pipe (f = umulhi(t & 0x80808080, 1 << 25), m = f * 255, dec = f * 2^k + dec): -10 %; (2) the
   // compare as t = b * -1 + (a * 1 + K) with run-time factors (two dependent multiply-adds per compare).
+  // (3) 2 X + (0x7f - e) read from a second table so that A - B and both compares are two-input adds
+  // (no IADD3 left in the loop, 121 instructions per step): 1.217 -> 1.213 ms, not worth 16 KB more
+  // shared memory per CTA -- with two warps per scheduler the kernel waits on latency, not on a pipe.
   const uint32_t m0 = prmt(t0, 0u, 0xba98u);
   const uint32_t m1 = prmt(t1, 0u, 0xba98u);
   decE |= m0 & C;
